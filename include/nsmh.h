@@ -1,0 +1,164 @@
+/*
+ * nsmh.h — C ABI of the B200-native MinHash read-overlap engine (libnsmh.so).
+ *
+ * This is the drop-in boundary for NanoSpring's read-overlap stage: the entry
+ * points below are what an FFI binding of the reference's
+ *     class ReadFilter / class MinHashReadFilter   (include/ReadFilter.h:15-139)
+ * would bind.  Plain pointers and sizes only; no C++ or torch types.  The C++
+ * adaptor nanospring_b200/cpp/GpuMinHashReadFilter.h and the Python mirror
+ * nanospring_b200/filter.py sit on top of exactly these symbols.
+ *
+ * Reference semantics kept bit-for-bit (file:line relative to the reference):
+ *  - base code A0 T1 C2 G3 via (c&2)|((c&4)>>2) for ANY byte     ReadFilter.cpp:113-115
+ *  - forward k-mers, first base most significant, 1 <= k <= 31    ReadFilter.cpp:138-152
+ *  - sketch[l] = min over k-mers x of (x XOR rand[l]), u64        ReadFilter.cpp:117-136
+ *  - len <  k-1 : sketch all-zero;  len == k-1 : all-ones         ReadFilter.cpp:21,119-124
+ *  - table j maps sketch[.][j] -> read ids                        BBHashMap.cpp:10-120
+ *  - query: ids occurring in >= thr of the n probed lists,
+ *    ascending, query read itself included                        ReadFilter.cpp:65-83
+ *  - the n random numbers are an INPUT (the reference draws them from
+ *    std::random_device, ReadFilter.cpp:49-63); nsmh_rand_from_seed() gives the
+ *    numbers std::mt19937_64(seed) would have produced.
+ *
+ * Every function returns NSMH_OK (0) or a negative NSMH_E* code; the message is
+ * available from nsmh_last_error() (thread-local).  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with NSMH_ECUDA.
+ *
+ * Thread safety: one handle may be shared by many host threads for
+ * nsmh_query_string / nsmh_query_strings / nsmh_query_sketches after
+ * nsmh_build() (the contract of getFilteredReads, called concurrently from the
+ * OpenMP region at Consensus.cpp:29,189).  All other calls on one handle must
+ * be serialised by the caller (initialize() is single-threaded, Compressor.cpp:76).
+ */
+#ifndef NSMH_H_
+#define NSMH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSMH_OK 0
+#define NSMH_EINVAL (-1)   /* bad argument (k outside 1..31, n == 0, null pointer ...) */
+#define NSMH_ECUDA (-2)    /* CUDA runtime error / no device */
+#define NSMH_ESTATE (-3)   /* call order violated (e.g. query before build) */
+#define NSMH_ENOMEM (-4)   /* host or device allocation failed */
+#define NSMH_ERANGE (-5)   /* caller's output buffer too small; required size reported */
+
+typedef struct nsmh_ctx *nsmh_handle;
+
+/* ---- lifetime / parameters (MinHashReadFilter fields k, n, overlapSketchThreshold:
+ *      ReadFilter.h:37-42; CLI defaults 23/60/6: main.cpp:57-62) ------------------- */
+int nsmh_create(uint32_t k, uint32_t n, uint32_t overlap_sketch_thr, const uint64_t *rand_numbers,
+                int device, nsmh_handle *out);
+int nsmh_destroy(nsmh_handle h);
+const char *nsmh_last_error(void);
+const char *nsmh_version(void);
+
+/* First n outputs of std::mt19937_64(seed): what generateRandomNumbers()
+ * (ReadFilter.cpp:49-63) draws once random_device has returned `seed`.  Host only. */
+int nsmh_rand_from_seed(uint32_t seed, uint32_t n, uint64_t *out);
+
+/* Pinned host memory for staging reads / results (optional; any host memory works). */
+int nsmh_host_alloc(size_t bytes, void **out);
+int nsmh_host_free(void *p);
+
+/* ---- reads -> device (replaces ReadData::getRead + DnaBitset on the host,
+ *      ReadData.cpp:225-235, dnaToBits.cpp:11-103) --------------------------------- */
+/* Concatenated ASCII bases of num_reads reads; read i = bases[offsets[i] .. offsets[i+1]).
+ * Host buffers.  Copies host->device in chunks overlapped with the on-device 2-bit pack. */
+int nsmh_load_reads_ascii(nsmh_handle h, const char *bases, const uint64_t *offsets,
+                          uint32_t num_reads);
+/* Same, but both buffers are already device-resident (device pointers). */
+int nsmh_load_reads_ascii_device(nsmh_handle h, const char *d_bases, const uint64_t *d_offsets,
+                                 uint32_t num_reads, uint64_t total_bases);
+/* Reads already 2-bit packed in the reference's DnaBitset layout (4 bases per byte,
+ * first base in bits 7..6, every read byte aligned; dnaToBits.cpp:11-36), concatenated.
+ * lengths[i] = bases of read i.  Host buffers.  Bytes are taken as exact A/C/G/T. */
+int nsmh_load_reads_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32_t *lengths,
+                              uint32_t num_reads);
+int nsmh_num_reads(nsmh_handle h, uint32_t *num_reads, uint64_t *total_bases);
+
+/* ---- MinHashReadFilter::initialize() (ReadFilter.cpp:11-47), split in its two stages --- */
+/* Sketch every loaded read: sketches[read][hash], row-major u64, on the device. */
+int nsmh_sketch(nsmh_handle h);
+/* mode: 0 = filtered (prefix-filter kernel + exact fix-up, default), 1 = brute force
+ * (every k-mer x every hash, the reference's operation count).  Results are identical. */
+int nsmh_set_sketch_mode(nsmh_handle h, int mode);
+int nsmh_get_sketches(nsmh_handle h, uint64_t *out /* [num_reads * n], host */);
+/* Device address of the local sketch matrix (for NCCL all-gather by the host program). */
+int nsmh_sketches_device_ptr(nsmh_handle h, uint64_t **d_ptr);
+/* Use an external device-resident sketch matrix [table_reads][n] as the table contents
+ * (multi-GPU: the all-gathered sketches).  Local read i is global read id_base + i.
+ * The buffer must stay valid until nsmh_build() returns. */
+int nsmh_set_table_sketches(nsmh_handle h, const uint64_t *d_sketches, uint32_t table_reads,
+                            uint32_t id_base);
+/* populateHashTables() (ReadFilter.cpp:159-172): build the n key -> read-id tables. */
+int nsmh_build(nsmh_handle h);
+/* Number of distinct keys of table j (BBHashMap::numKeys, BBHashMap.cpp:35). */
+int nsmh_table_num_keys(nsmh_handle h, uint32_t j, uint32_t *num_keys);
+
+/* ---- bulk query: every loaded read against the tables --------------------------------
+ * rc = 0: the read's own sketch (getFilteredReads(sketch[]), ReadFilter.cpp:65-83);
+ * rc = 1: the read's reverse-complement string (Consensus.cpp:181-191).
+ * Result is CSR, device resident until the next bulk query: offsets[num_reads+1], ids[total]. */
+int nsmh_query_all(nsmh_handle h, int rc, uint64_t *total_ids);
+int nsmh_query_all_result(nsmh_handle h, uint64_t *offsets /* [num_reads+1] host */,
+                          uint32_t *ids /* [total_ids] host */);
+int nsmh_query_all_device_ptrs(nsmh_handle h, uint64_t **d_offsets, uint32_t **d_ids);
+
+/* ---- online query: ReadFilter::getFilteredReads(const std::string&, std::vector<read_t>&)
+ *      (ReadFilter.h:24-25, ReadFilter.cpp:85-97).  Thread-safe, re-entrant. -------------
+ * Writes min(count, cap) ids to out and the full count to *count; returns NSMH_ERANGE
+ * if count > cap (call again with a larger buffer). */
+int nsmh_query_string(nsmh_handle h, const char *s, size_t len, uint32_t *out, size_t cap,
+                      size_t *count);
+/* Batch of strings in one launch sequence (e.g. forward + reverse-complement window).
+ * offsets_out[num_strings+1]; ids_out capacity cap. */
+int nsmh_query_strings(nsmh_handle h, const char *bases, const uint64_t *offsets,
+                       uint32_t num_strings, uint64_t *offsets_out, uint32_t *ids_out, size_t cap);
+/* Batch of ready-made sketches [num_queries][n] (host). */
+int nsmh_query_sketches(nsmh_handle h, const uint64_t *sketches, uint32_t num_queries,
+                        uint64_t *offsets_out, uint32_t *ids_out, size_t cap);
+
+/* ---- instrumentation ------------------------------------------------------------------ */
+/* Device time (CUDA events on the engine's stream) of the last call of each stage, ms. */
+typedef struct {
+    float h2d_pack_ms;   /* nsmh_load_reads_ascii: H2D + pack, whole call */
+    float pack_ms;       /* pack kernels only */
+    float sketch_ms;     /* nsmh_sketch */
+    float sketch_main_ms;   /* main sketch kernel only */
+    float build_ms;      /* nsmh_build */
+    float query_ms;      /* nsmh_query_all */
+    uint64_t sketch_fixups;   /* (read,hash) pairs the exact fix-up pass had to rescan */
+    uint64_t query_pairs;     /* gathered (query,id) pairs in the last bulk query */
+    uint32_t kernel_launches; /* kernels launched by this handle since creation */
+} nsmh_stats;
+int nsmh_get_stats(nsmh_handle h, nsmh_stats *out);
+/* The engine's CUDA stream (cudaStream_t as void*), for event timing by the host program. */
+int nsmh_stream(nsmh_handle h, void **stream);
+int nsmh_synchronize(nsmh_handle h);
+
+/* ---- synthetic nanopore-like reads (bench / test tooling; follows the reference's
+ *      util/old_code/createData.py: random genome, ins/del/sub errors, 50% RC) --------- */
+typedef struct {
+    uint64_t genome_len;    /* 50e6 in the BASELINE configs */
+    uint64_t genome_seed;
+    uint64_t read_seed;
+    float p_ins, p_del, p_sub;   /* 0.03 / 0.03 / 0.04 */
+    float p_rc;                  /* 0.5 */
+} nsmh_synth_params;
+/* Writes reads first_read .. first_read+num_reads of the synthetic set into bases
+ * (ASCII, host).  offsets[num_reads+1] are the caller-chosen read boundaries. */
+int nsmh_synth_reads_host(const nsmh_synth_params *p, uint64_t first_read, uint32_t num_reads,
+                          const uint64_t *offsets, char *bases);
+/* Same content generated directly into device memory (device pointers). */
+int nsmh_synth_reads_device(int device, const nsmh_synth_params *p, uint64_t first_read,
+                            uint32_t num_reads, const uint64_t *d_offsets, char *d_bases);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSMH_H_ */

@@ -1,0 +1,650 @@
+// C ABI of libnsmh.so (include/nsmh.h): context management and the host-side
+// orchestration of the kernels in pack.cu / sketch.cu / table.cu / query.cu.
+// Mirrors the call sequence of the reference:
+//   Compressor.cpp:69-76   rF.k/n/overlapSketchThreshold = ...; rF.initialize(rD)
+//   ReadFilter.cpp:11-47   initialize(): sketch all reads, populateHashTables()
+//   Consensus.cpp:189      rF->getFilteredReads(string, results)  (concurrent callers)
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "nsmh_internal.cuh"
+
+namespace nsmh {
+
+static thread_local std::string g_err;
+
+void set_error(const std::string &msg) { g_err = msg; }
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file,
+             line, what);
+    g_err = buf;
+    cudaGetLastError();   // clear sticky-free errors
+    return e == cudaErrorMemoryAllocation ? NSMH_ENOMEM : NSMH_ECUDA;
+}
+
+int DevBuf::ensure(size_t bytes, cudaStream_t s, size_t keep) {
+    if (bytes <= cap && p) return NSMH_OK;
+    size_t want = bytes + bytes / 8 + 256;
+    void *np = nullptr;
+    NSMH_CK(cudaMallocAsync(&np, want, s));
+    if (p) {
+        if (keep) NSMH_CK(cudaMemcpyAsync(np, p, keep < cap ? keep : cap, cudaMemcpyDeviceToDevice, s));
+        NSMH_CK(cudaFreeAsync(p, s));
+    }
+    p = np;
+    cap = want;
+    return NSMH_OK;
+}
+
+void DevBuf::release(cudaStream_t s) {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    cap = 0;
+}
+
+static void free_ws(QueryWs &ws, cudaStream_t s) {
+    DevBuf *bufs[] = {&ws.qsketch, &ws.pbegin, &ws.pcnt, &ws.poff, &ws.pairs, &ws.pairs_alt, &ws.flags,
+                      &ws.qcount, &ws.out_off, &ws.out_ids, &ws.nsel, &ws.cub_tmp, &ws.str_bases,
+                      &ws.tile_start};
+    for (DevBuf *b : bufs) b->release(s);
+    ws.str_reads.release(s);
+    if (ws.h_pinned) cudaFreeHost(ws.h_pinned);
+    ws.h_pinned = nullptr;
+    ws.h_pinned_cap = 0;
+}
+
+static int ensure_pinned(QueryWs &ws, size_t bytes) {
+    if (bytes <= ws.h_pinned_cap) return NSMH_OK;
+    if (ws.h_pinned) cudaFreeHost(ws.h_pinned);
+    ws.h_pinned = nullptr;
+    ws.h_pinned_cap = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    NSMH_CK(cudaMallocHost(&ws.h_pinned, want));
+    ws.h_pinned_cap = want;
+    return NSMH_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+static float elapsed(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, a, b) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+    return ms;
+}
+
+// MT19937-64 (Matsumoto & Nishimura; the engine behind std::mt19937_64).
+static void mt19937_64_stream(uint32_t seed, uint32_t n, uint64_t *out) {
+    const int NN = 312, MM = 156;
+    std::vector<uint64_t> mt(NN);
+    mt[0] = seed;
+    for (int i = 1; i < NN; ++i) mt[i] = 6364136223846793005ULL * (mt[i - 1] ^ (mt[i - 1] >> 62)) + i;
+    int idx = NN;
+    for (uint32_t o = 0; o < n; ++o) {
+        if (idx >= NN) {
+            for (int i = 0; i < NN; ++i) {
+                uint64_t x = (mt[i] & 0xFFFFFFFF80000000ULL) | (mt[(i + 1) % NN] & 0x7FFFFFFFULL);
+                uint64_t xa = x >> 1;
+                if (x & 1) xa ^= 0xB5026F5AA96619E9ULL;
+                mt[i] = mt[(i + MM) % NN] ^ xa;
+            }
+            idx = 0;
+        }
+        uint64_t y = mt[idx++];
+        y ^= (y >> 29) & 0x5555555555555555ULL;
+        y ^= (y << 17) & 0x71D67FFFEDA60000ULL;
+        y ^= (y << 37) & 0xFFF7EEE000000000ULL;
+        y ^= y >> 43;
+        out[o] = y;
+    }
+}
+
+} // namespace nsmh
+
+using namespace nsmh;
+
+#define CTX_GUARD(h)                                                   \
+    if (!(h)) return fail(NSMH_EINVAL, "null handle");                 \
+    DeviceGuard guard__((h)->device);                                  \
+    if (!guard__.ok) return fail(NSMH_ECUDA, "cudaSetDevice failed")
+
+extern "C" {
+
+const char *nsmh_last_error(void) { return g_err.c_str(); }
+const char *nsmh_version(void) { return "nsmh 0.1 (sm_100a)"; }
+
+int nsmh_rand_from_seed(uint32_t seed, uint32_t n, uint64_t *out) {
+    if (!out && n) return fail(NSMH_EINVAL, "rand_from_seed: null output");
+    mt19937_64_stream(seed, n, out);
+    return NSMH_OK;
+}
+
+int nsmh_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(NSMH_EINVAL, "host_alloc: null output");
+    NSMH_CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return NSMH_OK;
+}
+
+int nsmh_host_free(void *p) {
+    if (p) NSMH_CK(cudaFreeHost(p));
+    return NSMH_OK;
+}
+
+int nsmh_create(uint32_t k, uint32_t n, uint32_t thr, const uint64_t *rand_numbers, int device,
+                nsmh_handle *out) {
+    if (!out) return fail(NSMH_EINVAL, "create: null output handle");
+    *out = nullptr;
+    // k == 32 is undefined behaviour in the reference (1ull << 64, ReadFilter.cpp:145); k == 0 is
+    // rejected by its CLI (main.cpp:120-121).
+    if (k < 1 || k > 31) return fail(NSMH_EINVAL, "create: k must be in 1..31");
+    if (n < 1) return fail(NSMH_EINVAL, "create: n must be >= 1");
+    if (!rand_numbers) return fail(NSMH_EINVAL, "create: rand_numbers is null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(NSMH_ECUDA, "create: no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(NSMH_EINVAL, "create: device index out of range");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(NSMH_ECUDA, "create: cudaSetDevice failed");
+    nsmh_ctx *c = new (std::nothrow) nsmh_ctx();
+    if (!c) return fail(NSMH_ENOMEM, "create: out of host memory");
+    c->device = device;
+    c->k = k;
+    c->n = n;
+    c->thr = thr;
+    c->rand.assign(rand_numbers, rand_numbers + n);
+    int rc = NSMH_OK;
+    do {
+        cudaDeviceProp prop;
+        if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { rc = cuda_fail(e, "props", __FILE__, __LINE__); break; }
+        c->num_sms = prop.multiProcessorCount;
+        if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(e, "stream", __FILE__, __LINE__); break; }
+        if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) { rc = cuda_fail(e, "stream", __FILE__, __LINE__); break; }
+        for (auto &ev : c->ev)
+            if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rc = cuda_fail(e, "event", __FILE__, __LINE__); break; }
+        if (rc) break;
+        // keep freed blocks in the pool: the bench re-runs the same sizes every step
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thresh = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh);
+        }
+        if ((rc = c->d_rand.ensure(n * sizeof(uint64_t), c->stream))) break;
+        if ((rc = c->counters.ensure(8 * sizeof(uint64_t), c->stream))) break;
+        if ((e = cudaMemcpyAsync(c->d_rand.p, c->rand.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { rc = cuda_fail(e, "memcpy", __FILE__, __LINE__); break; }
+        if ((e = cudaMemsetAsync(c->counters.p, 0, 8 * sizeof(uint64_t), c->stream)) != cudaSuccess) { rc = cuda_fail(e, "memset", __FILE__, __LINE__); break; }
+        if ((rc = build_filter_tables(c))) break;
+        c->bulk.stream = c->stream;
+    } while (0);
+    if (rc) {
+        nsmh_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return NSMH_OK;
+}
+
+int nsmh_destroy(nsmh_handle h) {
+    if (!h) return NSMH_OK;
+    std::string keep = g_err;
+    {
+        DeviceGuard guard(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        for (QueryWs *ws : h->pool) {
+            if (ws->stream) cudaStreamSynchronize(ws->stream);
+            free_ws(*ws, ws->stream);
+            if (ws->stream) cudaStreamDestroy(ws->stream);
+            delete ws;
+        }
+        h->pool.clear();
+        cudaStream_t s = h->stream;
+        free_ws(h->bulk, s);
+        DevBuf *bufs[] = {&h->d_rand, &h->d_ftab_hit, &h->d_ftab_first, &h->d_ftab_next, &h->sketches,
+                          &h->tile_start, &h->counters, &h->item_slot, &h->item_rank, &h->build_tmp,
+                          &h->tables.keys, &h->tables.cnt, &h->tables.begin, &h->tables.ids};
+        for (DevBuf *b : bufs) b->release(s);
+        if (h->reads.external_offsets) { h->reads.offsets.p = nullptr; h->reads.offsets.cap = 0; }
+        h->reads.release(s);
+        if (s) cudaStreamSynchronize(s);
+        for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+        if (h->stream) cudaStreamDestroy(h->stream);
+        if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+        cudaGetLastError();
+    }
+    delete h;
+    g_err = keep;
+    return NSMH_OK;
+}
+
+// -------------------------------------------------------------------- reads --
+static int set_offsets_host(nsmh_ctx *c, const uint64_t *offsets, uint32_t num_reads) {
+    ReadSet &rs = c->reads;
+    if (rs.external_offsets) { rs.offsets.p = nullptr; rs.offsets.cap = 0; rs.external_offsets = false; }
+    for (uint32_t i = 0; i < num_reads; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(NSMH_EINVAL, "load_reads: offsets must be non-decreasing");
+    if (offsets[0] != 0) return fail(NSMH_EINVAL, "load_reads: offsets[0] must be 0");
+    rs.num_reads = num_reads;
+    NSMH_TRY(rs.offsets.ensure(((size_t)num_reads + 1) * sizeof(uint64_t), c->stream));
+    NSMH_CK(cudaMemcpyAsync(rs.offsets.p, offsets, ((size_t)num_reads + 1) * sizeof(uint64_t),
+                            cudaMemcpyHostToDevice, c->stream));
+    return NSMH_OK;
+}
+
+static void invalidate(nsmh_ctx *c) {
+    c->reads_loaded = false;
+    c->sketched = false;
+    c->tables.built = false;
+    c->bulk_valid = false;
+    c->table_sketches = nullptr;
+    c->table_reads = 0;
+    c->id_base = 0;
+}
+
+int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
+    CTX_GUARD(c);
+    if (!offsets) return fail(NSMH_EINVAL, "load_reads_ascii: null offsets");
+    const uint64_t total = offsets[num_reads];
+    if (total && !bases) return fail(NSMH_EINVAL, "load_reads_ascii: null bases");
+    invalidate(c);
+    NSMH_CK(cudaEventRecord(c->ev[0], c->stream));
+    NSMH_TRY(set_offsets_host(c, offsets, num_reads));
+    NSMH_TRY(alloc_packed(c->reads, total, c->stream));
+    // Double-buffered chunks: H2D of chunk i+1 on the copy stream overlaps the pack of chunk i.
+    const uint64_t chunk = 64ULL << 20;   // bases per chunk, multiple of 16
+    DevBuf stage[2];
+    cudaEvent_t copied[2], packed[2];
+    for (int i = 0; i < 2; ++i) {
+        NSMH_CK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        NSMH_CK(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
+    }
+    int rc = NSMH_OK;
+    const size_t stage_bytes = (size_t)std::min<uint64_t>(chunk, total ? total : 1) + 16;
+    for (int i = 0; i < 2 && !rc; ++i) rc = stage[i].ensure(stage_bytes, c->stream);
+    if (!rc && cudaEventRecord(packed[0], c->stream) != cudaSuccess) rc = NSMH_ECUDA;
+    if (!rc && cudaEventRecord(packed[1], c->stream) != cudaSuccess) rc = NSMH_ECUDA;
+    int bi = 0;
+    for (uint64_t b0 = 0; b0 < total && !rc; b0 += chunk, bi ^= 1) {
+        const uint64_t nb = std::min<uint64_t>(chunk, total - b0);
+        cudaError_t e;
+        if ((e = cudaStreamWaitEvent(c->copy_stream, packed[bi], 0)) != cudaSuccess) { rc = cuda_fail(e, "wait", __FILE__, __LINE__); break; }
+        if ((e = cudaMemcpyAsync(stage[bi].p, bases + b0, nb, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
+        if ((e = cudaEventRecord(copied[bi], c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
+        if ((e = cudaStreamWaitEvent(c->stream, copied[bi], 0)) != cudaSuccess) { rc = cuda_fail(e, "wait", __FILE__, __LINE__); break; }
+        rc = pack_ascii(c->reads, stage[bi].as<char>(), b0, nb, c->stream, &c->launches);
+        if (!rc && (e = cudaEventRecord(packed[bi], c->stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
+    }
+    if (!rc) {
+        cudaEventRecord(c->ev[1], c->stream);
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+    }
+    for (int i = 0; i < 2; ++i) {
+        stage[i].release(c->stream);
+        cudaEventDestroy(copied[i]);
+        cudaEventDestroy(packed[i]);
+    }
+    if (rc) return rc;
+    c->stats.h2d_pack_ms = elapsed(c->ev[0], c->ev[1]);
+    c->reads_loaded = true;
+    return NSMH_OK;
+}
+
+int nsmh_load_reads_ascii_device(nsmh_handle c, const char *d_bases, const uint64_t *d_offsets,
+                                 uint32_t num_reads, uint64_t total_bases) {
+    CTX_GUARD(c);
+    if (!d_offsets) return fail(NSMH_EINVAL, "load_reads_ascii_device: null offsets");
+    if (total_bases && !d_bases) return fail(NSMH_EINVAL, "load_reads_ascii_device: null bases");
+    invalidate(c);
+    ReadSet &rs = c->reads;
+    if (!rs.external_offsets) rs.offsets.release(c->stream);
+    rs.offsets.p = const_cast<uint64_t *>(d_offsets);   // borrowed, never freed
+    rs.offsets.cap = ((size_t)num_reads + 1) * sizeof(uint64_t);
+    rs.external_offsets = true;
+    rs.num_reads = num_reads;
+    NSMH_CK(cudaEventRecord(c->ev[0], c->stream));
+    NSMH_TRY(alloc_packed(rs, total_bases, c->stream));
+    NSMH_TRY(pack_ascii(rs, d_bases, 0, total_bases, c->stream, &c->launches));
+    NSMH_CK(cudaEventRecord(c->ev[1], c->stream));
+    c->reads_loaded = true;
+    return NSMH_OK;
+}
+
+int nsmh_load_reads_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths,
+                              uint32_t num_reads) {
+    CTX_GUARD(c);
+    if (num_reads && (!packed || !lengths)) return fail(NSMH_EINVAL, "load_reads_dnabitset: null input");
+    invalidate(c);
+    std::vector<uint64_t> off((size_t)num_reads + 1, 0), boff((size_t)num_reads + 1, 0);
+    for (uint32_t i = 0; i < num_reads; ++i) {
+        off[i + 1] = off[i] + lengths[i];
+        boff[i + 1] = boff[i] + (lengths[i] + 3) / 4;
+    }
+    NSMH_TRY(set_offsets_host(c, off.data(), num_reads));
+    NSMH_TRY(alloc_packed(c->reads, off[num_reads], c->stream));
+    DevBuf d_src, d_boff;
+    int rc = d_src.ensure(boff[num_reads] + 16, c->stream);
+    if (!rc) rc = d_boff.ensure(boff.size() * sizeof(uint64_t), c->stream);
+    cudaError_t e = cudaSuccess;
+    if (!rc && (e = cudaMemcpyAsync(d_src.p, packed, boff[num_reads], cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
+    if (!rc && (e = cudaMemcpyAsync(d_boff.p, boff.data(), boff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
+    if (!rc) rc = pack_from_dnabitset(c->reads, d_src.as<uint8_t>(), d_boff.as<uint64_t>(), c->stream, &c->launches);
+    if (!rc && (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+    d_src.release(c->stream);
+    d_boff.release(c->stream);
+    if (rc) return rc;
+    c->reads_loaded = true;
+    return NSMH_OK;
+}
+
+int nsmh_num_reads(nsmh_handle c, uint32_t *num_reads, uint64_t *total_bases) {
+    if (!c) return fail(NSMH_EINVAL, "null handle");
+    if (num_reads) *num_reads = c->reads.num_reads;
+    if (total_bases) *total_bases = c->reads.total_bases;
+    return NSMH_OK;
+}
+
+// ------------------------------------------------------------- initialize() --
+int nsmh_set_sketch_mode(nsmh_handle c, int mode) {
+    if (!c) return fail(NSMH_EINVAL, "null handle");
+    if (mode != 0 && mode != 1) return fail(NSMH_EINVAL, "set_sketch_mode: mode must be 0 or 1");
+    c->sketch_mode = mode;
+    return NSMH_OK;
+}
+
+int nsmh_sketch(nsmh_handle c) {
+    CTX_GUARD(c);
+    if (!c->reads_loaded) return fail(NSMH_ESTATE, "sketch: no reads loaded");
+    c->sketched = false;
+    c->tables.built = false;
+    c->bulk_valid = false;
+    NSMH_TRY(c->sketches.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream));
+    NSMH_CK(cudaEventRecord(c->ev[2], c->stream));
+    NSMH_TRY(sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp,
+                          c->sketch_mode, c->stream, &c->launches, c->ev[4], c->ev[5]));
+    NSMH_CK(cudaEventRecord(c->ev[3], c->stream));
+    c->sketched = true;
+    c->table_sketches = c->sketches.as<uint64_t>();
+    c->table_reads = c->reads.num_reads;
+    c->id_base = 0;
+    return NSMH_OK;
+}
+
+int nsmh_get_sketches(nsmh_handle c, uint64_t *out) {
+    CTX_GUARD(c);
+    if (!c->sketched) return fail(NSMH_ESTATE, "get_sketches: call nsmh_sketch first");
+    size_t bytes = (size_t)c->reads.num_reads * c->n * sizeof(uint64_t);
+    if (bytes && !out) return fail(NSMH_EINVAL, "get_sketches: null output");
+    if (bytes) NSMH_CK(cudaMemcpyAsync(out, c->sketches.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    return NSMH_OK;
+}
+
+int nsmh_sketches_device_ptr(nsmh_handle c, uint64_t **d_ptr) {
+    if (!c || !d_ptr) return fail(NSMH_EINVAL, "sketches_device_ptr: null argument");
+    if (!c->sketched) return fail(NSMH_ESTATE, "sketches_device_ptr: call nsmh_sketch first");
+    *d_ptr = c->sketches.as<uint64_t>();
+    return NSMH_OK;
+}
+
+int nsmh_set_table_sketches(nsmh_handle c, const uint64_t *d_sketches, uint32_t table_reads,
+                            uint32_t id_base) {
+    if (!c) return fail(NSMH_EINVAL, "null handle");
+    if (table_reads && !d_sketches) return fail(NSMH_EINVAL, "set_table_sketches: null pointer");
+    c->table_sketches = d_sketches;
+    c->table_reads = table_reads;
+    c->id_base = id_base;
+    c->tables.built = false;
+    c->bulk_valid = false;
+    return NSMH_OK;
+}
+
+int nsmh_build(nsmh_handle c) {
+    CTX_GUARD(c);
+    if (!c->table_sketches && c->table_reads)
+        return fail(NSMH_ESTATE, "build: no sketches (call nsmh_sketch or nsmh_set_table_sketches)");
+    if (!c->sketched && c->table_sketches == nullptr)
+        return fail(NSMH_ESTATE, "build: no sketches (call nsmh_sketch or nsmh_set_table_sketches)");
+    NSMH_CK(cudaEventRecord(c->ev[6], c->stream));
+    NSMH_TRY(build_tables(c));
+    NSMH_CK(cudaEventRecord(c->ev[7], c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    c->stats.build_ms = elapsed(c->ev[6], c->ev[7]);
+    return NSMH_OK;
+}
+
+int nsmh_table_num_keys(nsmh_handle c, uint32_t j, uint32_t *num_keys) {
+    CTX_GUARD(c);
+    if (!num_keys) return fail(NSMH_EINVAL, "table_num_keys: null output");
+    return table_num_keys(c, j, num_keys);
+}
+
+// --------------------------------------------------------------- bulk query --
+int nsmh_query_all(nsmh_handle c, int rc_mode, uint64_t *total_ids) {
+    CTX_GUARD(c);
+    if (!c->sketched) return fail(NSMH_ESTATE, "query_all: call nsmh_sketch first");
+    if (!c->tables.built) return fail(NSMH_ESTATE, "query_all: call nsmh_build first");
+    QueryWs &ws = c->bulk;
+    ws.stream = c->stream;
+    c->bulk_valid = false;
+    cudaEvent_t e0, e1;
+    NSMH_CK(cudaEventCreate(&e0));
+    NSMH_CK(cudaEventCreate(&e1));
+    int rc = NSMH_OK;
+    cudaEventRecord(e0, c->stream);
+    const uint64_t *q = c->sketches.as<uint64_t>();
+    if (rc_mode) {
+        // sketch the reverse-complement strings, as the caller's second query does
+        // (Consensus.cpp:181-191 via the public string overload, ReadFilter.cpp:85-97)
+        ws.str_reads.offsets.p = c->reads.offsets.p;   // same boundaries, borrowed
+        ws.str_reads.offsets.cap = c->reads.offsets.cap;
+        rc = pack_reverse_complement(c->reads, ws.str_reads, c->stream, &ws.launches);
+        if (!rc) rc = ws.qsketch.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream);
+        if (!rc) rc = sketch_reads(c, ws.str_reads, ws.qsketch.as<uint64_t>(), ws.tile_start, ws.cub_tmp,
+                                   c->sketch_mode, c->stream, &ws.launches, nullptr, nullptr);
+        ws.str_reads.offsets.p = nullptr;
+        ws.str_reads.offsets.cap = 0;
+        q = ws.qsketch.as<uint64_t>();
+    }
+    if (!rc) rc = query_sketches_device(c, ws, q, c->reads.num_reads, c->stream);
+    cudaEventRecord(e1, c->stream);
+    cudaStreamSynchronize(c->stream);
+    if (!rc) {
+        c->stats.query_ms = elapsed(e0, e1);
+        c->stats.query_pairs = ws.last_pairs;
+        c->bulk_valid = true;
+        if (total_ids) *total_ids = ws.last_total;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+int nsmh_query_all_result(nsmh_handle c, uint64_t *offsets, uint32_t *ids) {
+    CTX_GUARD(c);
+    if (!c->bulk_valid) return fail(NSMH_ESTATE, "query_all_result: no bulk query result");
+    QueryWs &ws = c->bulk;
+    if (offsets)
+        NSMH_CK(cudaMemcpyAsync(offsets, ws.out_off.p, ((size_t)ws.last_nq + 1) * sizeof(uint64_t),
+                                cudaMemcpyDeviceToHost, c->stream));
+    if (ids && ws.last_total)
+        NSMH_CK(cudaMemcpyAsync(ids, ws.out_ids.p, ws.last_total * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    return NSMH_OK;
+}
+
+int nsmh_query_all_device_ptrs(nsmh_handle c, uint64_t **d_offsets, uint32_t **d_ids) {
+    if (!c) return fail(NSMH_EINVAL, "null handle");
+    if (!c->bulk_valid) return fail(NSMH_ESTATE, "query_all_device_ptrs: no bulk query result");
+    if (d_offsets) *d_offsets = c->bulk.out_off.as<uint64_t>();
+    if (d_ids) *d_ids = c->bulk.out_ids.as<uint32_t>();
+    return NSMH_OK;
+}
+
+// ------------------------------------------------------------- online query --
+static QueryWs *acquire_ws(nsmh_ctx *c) {
+    {
+        std::lock_guard<std::mutex> lk(c->pool_mu);
+        if (!c->pool.empty()) {
+            QueryWs *ws = c->pool.back();
+            c->pool.pop_back();
+            return ws;
+        }
+    }
+    QueryWs *ws = new (std::nothrow) QueryWs();
+    if (!ws) return nullptr;
+    if (cudaStreamCreateWithFlags(&ws->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ws;
+        return nullptr;
+    }
+    return ws;
+}
+
+static void release_ws(nsmh_ctx *c, QueryWs *ws) {
+    std::lock_guard<std::mutex> lk(c->pool_mu);
+    c->launches += ws->launches;
+    ws->launches = 0;
+    c->pool.push_back(ws);
+}
+
+static int copy_csr_out(QueryWs &ws, uint32_t nq, uint64_t *offsets_out, uint32_t *ids_out, size_t cap) {
+    cudaStream_t s = ws.stream;
+    const size_t ncopy = std::min<size_t>(cap, ws.last_total);
+    if (offsets_out)
+        NSMH_CK(cudaMemcpyAsync(offsets_out, ws.out_off.p, ((size_t)nq + 1) * sizeof(uint64_t),
+                                cudaMemcpyDeviceToHost, s));
+    if (ncopy && ids_out)
+        NSMH_CK(cudaMemcpyAsync(ids_out, ws.out_ids.p, ncopy * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    NSMH_CK(cudaStreamSynchronize(s));
+    if (ws.last_total > cap) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "query: output needs %llu ids, capacity is %zu",
+                 (unsigned long long)ws.last_total, cap);
+        return fail(NSMH_ERANGE, buf);
+    }
+    return NSMH_OK;
+}
+
+static int query_strings_impl(nsmh_ctx *c, QueryWs &ws, const char *bases, const uint64_t *offsets,
+                              uint32_t nq, uint64_t *offsets_out, uint32_t *ids_out, size_t cap) {
+    cudaStream_t s = ws.stream;
+    const uint64_t total = offsets[nq];
+    for (uint32_t i = 0; i < nq; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(NSMH_EINVAL, "query_strings: offsets must be non-decreasing");
+    if (offsets[0] != 0) return fail(NSMH_EINVAL, "query_strings: offsets[0] must be 0");
+    // stage strings + offsets through pinned memory so concurrent callers never block each other
+    const size_t off_bytes = ((size_t)nq + 1) * sizeof(uint64_t);
+    NSMH_TRY(ensure_pinned(ws, off_bytes + total + 16));
+    memcpy(ws.h_pinned, offsets, off_bytes);
+    if (total) memcpy(static_cast<char *>(ws.h_pinned) + off_bytes, bases, total);
+    ReadSet &rs = ws.str_reads;
+    rs.num_reads = nq;
+    NSMH_TRY(rs.offsets.ensure(off_bytes, s));
+    NSMH_TRY(ws.str_bases.ensure(total + 16, s));
+    NSMH_CK(cudaMemcpyAsync(rs.offsets.p, ws.h_pinned, off_bytes, cudaMemcpyHostToDevice, s));
+    if (total)
+        NSMH_CK(cudaMemcpyAsync(ws.str_bases.p, static_cast<char *>(ws.h_pinned) + off_bytes, total,
+                                cudaMemcpyHostToDevice, s));
+    NSMH_TRY(alloc_packed(rs, total, s));
+    NSMH_TRY(pack_ascii(rs, ws.str_bases.as<char>(), 0, total, s, &ws.launches));
+    NSMH_TRY(ws.qsketch.ensure(std::max<size_t>((size_t)nq * c->n, 1) * sizeof(uint64_t), s));
+    NSMH_TRY(sketch_reads(c, rs, ws.qsketch.as<uint64_t>(), ws.tile_start, ws.cub_tmp, c->sketch_mode, s,
+                          &ws.launches, nullptr, nullptr));
+    NSMH_TRY(query_sketches_device(c, ws, ws.qsketch.as<uint64_t>(), nq, s));
+    return copy_csr_out(ws, nq, offsets_out, ids_out, cap);
+}
+
+int nsmh_query_strings(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_strings,
+                       uint64_t *offsets_out, uint32_t *ids_out, size_t cap) {
+    CTX_GUARD(c);
+    if (!offsets) return fail(NSMH_EINVAL, "query_strings: null offsets");
+    if (offsets[num_strings] && !bases) return fail(NSMH_EINVAL, "query_strings: null bases");
+    if (!c->tables.built) return fail(NSMH_ESTATE, "query_strings: call nsmh_build first");
+    QueryWs *ws = acquire_ws(c);
+    if (!ws) return fail(NSMH_ENOMEM, "query_strings: cannot create a query workspace");
+    int rc = query_strings_impl(c, *ws, bases, offsets, num_strings, offsets_out, ids_out, cap);
+    release_ws(c, ws);
+    return rc;
+}
+
+int nsmh_query_string(nsmh_handle c, const char *s, size_t len, uint32_t *out, size_t cap, size_t *count) {
+    uint64_t offsets[2] = {0, (uint64_t)len};
+    uint64_t off_out[2] = {0, 0};
+    int rc = nsmh_query_strings(c, s, offsets, 1, off_out, out, cap);
+    if (count && (rc == NSMH_OK || rc == NSMH_ERANGE)) *count = (size_t)off_out[1];
+    return rc;
+}
+
+int nsmh_query_sketches(nsmh_handle c, const uint64_t *sketches, uint32_t num_queries,
+                        uint64_t *offsets_out, uint32_t *ids_out, size_t cap) {
+    CTX_GUARD(c);
+    if (num_queries && !sketches) return fail(NSMH_EINVAL, "query_sketches: null sketches");
+    if (!c->tables.built) return fail(NSMH_ESTATE, "query_sketches: call nsmh_build first");
+    QueryWs *ws = acquire_ws(c);
+    if (!ws) return fail(NSMH_ENOMEM, "query_sketches: cannot create a query workspace");
+    int rc = NSMH_OK;
+    const size_t bytes = (size_t)num_queries * c->n * sizeof(uint64_t);
+    do {
+        if ((rc = ws->qsketch.ensure(std::max<size_t>(bytes, 8), ws->stream))) break;
+        if ((rc = ensure_pinned(*ws, bytes + 16))) break;
+        memcpy(ws->h_pinned, sketches, bytes);
+        if (bytes) {
+            cudaError_t e = cudaMemcpyAsync(ws->qsketch.p, ws->h_pinned, bytes, cudaMemcpyHostToDevice, ws->stream);
+            if (e != cudaSuccess) { rc = cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
+        }
+        if ((rc = query_sketches_device(c, *ws, ws->qsketch.as<uint64_t>(), num_queries, ws->stream))) break;
+        rc = copy_csr_out(*ws, num_queries, offsets_out, ids_out, cap);
+    } while (0);
+    release_ws(c, ws);
+    return rc;
+}
+
+// ----------------------------------------------------------- instrumentation --
+int nsmh_get_stats(nsmh_handle c, nsmh_stats *out) {
+    CTX_GUARD(c);
+    if (!out) return fail(NSMH_EINVAL, "get_stats: null output");
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    if (c->reads_loaded) c->stats.pack_ms = c->stats.pack_ms;   // device-resident loads: see below
+    if (c->reads.external_offsets && c->reads_loaded) c->stats.pack_ms = elapsed(c->ev[0], c->ev[1]);
+    if (c->sketched) {
+        c->stats.sketch_ms = elapsed(c->ev[2], c->ev[3]);
+        c->stats.sketch_main_ms = elapsed(c->ev[4], c->ev[5]);
+    }
+    unsigned long long fix = 0;
+    NSMH_CK(cudaMemcpy(&fix, c->counters.p, sizeof fix, cudaMemcpyDeviceToHost));
+    c->stats.sketch_fixups = fix;
+    c->stats.kernel_launches = c->launches + c->bulk.launches;
+    *out = c->stats;
+    return NSMH_OK;
+}
+
+int nsmh_stream(nsmh_handle c, void **stream) {
+    if (!c || !stream) return fail(NSMH_EINVAL, "stream: null argument");
+    *stream = c->stream;
+    return NSMH_OK;
+}
+
+int nsmh_synchronize(nsmh_handle c) {
+    CTX_GUARD(c);
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    return NSMH_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,175 @@
+// Internal declarations of libnsmh.so (not part of the ABI; see include/nsmh.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/nsmh.h"
+
+namespace nsmh {
+
+// ---------------------------------------------------------------- errors --
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define NSMH_CK(call)                                                              \
+    do {                                                                           \
+        cudaError_t e__ = (call);                                                  \
+        if (e__ != cudaSuccess) return ::nsmh::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+#define NSMH_TRY(expr)                 \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != NSMH_OK) return rc__; \
+    } while (0)
+
+// ---------------------------------------------------------------- buffers --
+// Grow-only device buffer on a stream-ordered pool.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    // keep > 0: preserve the first `keep` bytes when the buffer has to grow
+    int ensure(size_t bytes, cudaStream_t s, size_t keep = 0);
+    void release(cudaStream_t s);
+    template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+// ------------------------------------------------------------- constants --
+constexpr int kWordBases = 16;          // bases per packed u32 word, first base in bits 31..30
+constexpr int kTileWords = 128;         // words (2048 k-mer start positions) per sketch tile
+constexpr int kFilterMaxBits = 12;      // largest prefix width b of the sketch filter tables
+constexpr int kFilterTabSize = 1 << (kFilterMaxBits + 1);  // table for b lives at [2^b, 2^(b+1))
+constexpr int kFilterLambdaLog2 = 3;    // b = floor(log2(#kmers)) - 3  => 8..16 k-mers expected per bucket
+constexpr uint64_t kEmptyKey = ~0ULL;   // empty marker of the hash tables (key ~0 has its own slot)
+constexpr int kPackPadWords = 8;        // zero words after the last packed word (k-mer window overrun)
+
+// A set of reads resident on the device: the reference's ReadData as far as the
+// MinHash path needs it (ReadData.h:26-60), 2-bit packed in ONE continuous
+// stream: read i occupies global bases [offsets[i], offsets[i+1]).
+struct ReadSet {
+    uint32_t num_reads = 0;
+    uint64_t total_bases = 0;
+    uint64_t num_words = 0;     // ceil(total_bases/16)
+    DevBuf offsets;             // u64 [num_reads+1]
+    DevBuf packed;              // u32 [num_words + kPackPadWords]
+    bool external_offsets = false;
+    const uint64_t *d_offsets() const { return offsets.as<uint64_t>(); }
+    void release(cudaStream_t s) { offsets.release(s); packed.release(s); }
+};
+
+// Hash tables: one open-addressing region of (cap+1) slots per hash function.
+struct Tables {
+    bool built = false;
+    uint32_t table_reads = 0;   // rows of the sketch matrix the tables were built from
+    uint32_t log2cap = 0;
+    uint64_t cap = 0;           // slots per region (power of two); slot `cap` holds key ~0
+    DevBuf keys;                // u64 [n*(cap+1)]
+    DevBuf cnt;                 // u32 [n*(cap+1)]  group size
+    DevBuf begin;               // u32 [n*(cap+1)]  start of the group in ids
+    DevBuf ids;                 // u32 [table_reads*n] read ids grouped by (table, key)
+};
+
+// Scratch of one bulk / online query (owns its stream so that concurrent host
+// threads never share mutable state).
+struct QueryWs {
+    cudaStream_t stream = nullptr;
+    DevBuf qsketch;     // u64 [nq*n]  (string queries)
+    DevBuf pbegin, pcnt;   // u32 [nq*n]
+    DevBuf poff;        // u64 [nq*n+1]
+    DevBuf pairs, pairs_alt;   // u64 [T]
+    DevBuf flags;       // u8 [T]
+    DevBuf qcount;      // u32 [nq]
+    DevBuf out_off;     // u64 [nq+1]
+    DevBuf out_ids;     // u32 [total]
+    DevBuf nsel;        // u64 [2]
+    DevBuf cub_tmp;
+    DevBuf str_bases;   // staging for query strings
+    ReadSet str_reads;
+    DevBuf tile_start;  // sketch scratch
+    void *h_pinned = nullptr;
+    size_t h_pinned_cap = 0;
+    uint64_t last_total = 0;
+    uint64_t last_pairs = 0;
+    uint32_t last_nq = 0;
+    uint32_t launches = 0;
+};
+
+} // namespace nsmh
+
+struct nsmh_ctx {
+    int device = 0;
+    uint32_t k = 0, n = 0, thr = 0;
+    std::vector<uint64_t> rand;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    int sketch_mode = 0;
+    int num_sms = 148;
+
+    nsmh::DevBuf d_rand;        // u64 [n]
+    nsmh::DevBuf d_ftab_hit;    // u8 [kFilterTabSize]     1 = some hash targets this prefix
+    nsmh::DevBuf d_ftab_first;  // u8 [kFilterTabSize]     first hash of the chain
+    nsmh::DevBuf d_ftab_next;   // u8 [(kFilterMaxBits+1)*n] next hash in chain, 0xFF = end
+
+    nsmh::ReadSet reads;
+    bool reads_loaded = false;
+    nsmh::DevBuf sketches;      // u64 [num_reads*n]
+    bool sketched = false;
+    nsmh::DevBuf tile_start;    // u32 [num_reads+1]
+    nsmh::DevBuf counters;      // u64 [8] device counters (fix-ups ...)
+
+    const uint64_t *table_sketches = nullptr;   // rows the tables are built from
+    uint32_t table_reads = 0, id_base = 0;
+    nsmh::Tables tables;
+    nsmh::DevBuf item_slot, item_rank;   // build scratch, u32 [table_reads*n]
+    nsmh::DevBuf build_tmp;
+
+    nsmh::QueryWs bulk;         // nsmh_query_all workspace (uses ctx stream)
+    bool bulk_valid = false;
+    std::mutex pool_mu;
+    std::vector<nsmh::QueryWs *> pool;   // idle online-query workspaces
+
+    nsmh_stats stats = {};
+    uint32_t launches = 0;
+};
+
+namespace nsmh {
+
+// ---- cub_ops.cu (library primitives: scan / radix sort / select) -----------
+cudaError_t cub_exclusive_sum_u32(void *tmp, size_t &tmp_bytes, const uint32_t *in, uint32_t *out,
+                                  size_t n, cudaStream_t s);
+cudaError_t cub_exclusive_sum_u32_to_u64(void *tmp, size_t &tmp_bytes, const uint32_t *in,
+                                         uint64_t *out, size_t n, cudaStream_t s);
+cudaError_t cub_sort_keys_u64(void *tmp, size_t &tmp_bytes, uint64_t *keys, uint64_t *alt,
+                              size_t n, int begin_bit, int end_bit, bool &result_in_alt,
+                              cudaStream_t s);
+cudaError_t cub_select_low32_flagged(void *tmp, size_t &tmp_bytes, const uint64_t *in,
+                                     const uint8_t *flags, uint32_t *out, uint64_t *num_selected,
+                                     size_t n, cudaStream_t s);
+
+// ---- pack.cu -----------------------------------------------------------------
+int pack_ascii(ReadSet &rs, const char *d_bases, uint64_t first_base, uint64_t num_bases,
+               cudaStream_t s, uint32_t *launches);
+int alloc_packed(ReadSet &rs, uint64_t total_bases, cudaStream_t s);
+int pack_reverse_complement(const ReadSet &src, ReadSet &dst, cudaStream_t s, uint32_t *launches);
+int pack_from_dnabitset(ReadSet &rs, const uint8_t *d_src, const uint64_t *d_src_byte_off,
+                        cudaStream_t s, uint32_t *launches);
+
+// ---- sketch.cu ---------------------------------------------------------------
+int build_filter_tables(nsmh_ctx *c);
+int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &tile_start,
+                 DevBuf &cub_tmp, int mode, cudaStream_t s, uint32_t *launches, cudaEvent_t ev0,
+                 cudaEvent_t ev1);
+
+// ---- table.cu ----------------------------------------------------------------
+int build_tables(nsmh_ctx *c);
+int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
+
+// ---- query.cu ----------------------------------------------------------------
+int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq,
+                          cudaStream_t s);
+
+} // namespace nsmh

@@ -274,10 +274,17 @@ int orc_query_all(const orc_tables *T, const char *bases, const uint64_t *offset
         if (!rc) {
             res[i] = orc_query_sketch(T, sketches + (size_t)i * T->n, thr, &cnt[i]);
         } else {
+            /* The caller never sees the raw input bytes: ReadData stores 2 bits per base
+             * (dnaToBits.cpp:11-36) and getRead() returns the letters "ATCG"[code]
+             * (ReadData.cpp:225-235, dnaToBits.cpp:81-98).  That string is what gets
+             * reverse-complemented, so every base is complemented, N included (N -> G -> C). */
             size_t len = (size_t)(offsets[i + 1] - offsets[i]);
+            char *canon = (char *)malloc(len ? len : 1);
             char *buf = (char *)malloc(len ? len : 1);
-            orc_reverse_complement(bases + offsets[i], len, buf);
+            for (size_t j = 0; j < len; ++j) canon[j] = "ATCG"[orc_base_to_int(bases[offsets[i] + j])];
+            orc_reverse_complement(canon, len, buf);
             res[i] = orc_query_string(T, buf, len, k, rnd, thr, &cnt[i]);
+            free(canon);
             free(buf);
         }
     }

@@ -1,0 +1,252 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI
+(include/nsmh.h via nanospring_b200.filter), against
+  * the committed outputs of the UNMODIFIED reference (tests/golden/*), and
+  * the CPU oracle (oracle/minhash_oracle.c) on the same seeded inputs.
+Bit-exact everywhere: sketches (u64) and candidate sets (ascending u32 ids per read).
+"""
+import threading
+
+import numpy as np
+import pytest
+
+import nanospring_b200 as ns
+from nanospring_b200.filter import MinHashReadFilter, ReadData
+
+pytestmark = pytest.mark.gpu
+
+
+def make_filter(k, n, thr, rnd, mode=0):
+    f = MinHashReadFilter()
+    f.k, f.n, f.overlapSketchThreshold = k, n, thr
+    f.randNumbers = np.asarray(rnd, dtype=np.uint64)
+    f.sketchMode = mode
+    return f
+
+
+def assert_csr_equal(got, want, what):
+    off_g, ids_g = got
+    off_w, ids_w = want
+    assert off_g.shape == off_w.shape, what
+    bad = np.nonzero(off_g != off_w)[0]
+    assert bad.size == 0, f"{what}: offsets first differ at read {bad[:1]}"
+    assert ids_g.size == ids_w.size and (ids_g == ids_w).all(), f"{what}: ids differ"
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_edge_set_all_configs(edge, mode):
+    """Empty reads, len k-2..k+1, non-ACGT bytes, duplicates, homopolymers, one long read:
+    the reference's full outputs for seven (k, n, thr) settings."""
+    rd = ReadData(edge["bases"], edge["offsets"])
+    for ci, (seed, k, n, thr) in enumerate(edge["cfgs"]):
+        k, n, thr = int(k), int(n), int(thr)
+        f = make_filter(k, n, thr, edge[f"rand_{ci}"], mode)
+        f.initialize(rd)
+        sk = f.sketches()
+        want = edge[f"sketches_{ci}"]
+        bad = np.argwhere(sk != want)
+        assert bad.size == 0, f"cfg {ci} mode {mode}: sketch differs at (read,hash) {bad[:3].tolist()}"
+        assert_csr_equal(f.queryAll(False), (edge[f"fwd_off_{ci}"], edge[f"fwd_ids_{ci}"]), f"cfg {ci} fwd")
+        assert_csr_equal(f.queryAll(True), (edge[f"rc_off_{ci}"], edge[f"rc_ids_{ci}"]), f"cfg {ci} rc")
+        f.close()
+
+
+@pytest.mark.parametrize("idx", [0, 1, 2])
+def test_c1_reference_ci_file(orc, c1_reads, c1_golden, idx):
+    """BASELINE config #1: util/test_file.fastq.gz, checked against the golden checksums of
+    the reference AND element-wise against the oracle."""
+    bases, offsets = c1_reads
+    g = c1_golden["settings"][idx]
+    rnd = ns.rand_from_seed(g["seed"], g["n"])
+    assert "%016x" % rnd[0] == g["rand_first"] and "%016x" % rnd[-1] == g["rand_last"]
+    f = make_filter(g["k"], g["n"], g["thr"], rnd)
+    f.initialize(ReadData(bases, offsets))
+    sk = f.sketches()
+    assert "%016x" % orc.fnv_u64(sk.ravel()) == g["fnv_sketches"]
+    want = orc.sketch_all(bases, offsets, g["k"], g["n"], rnd)
+    assert (sk == want).all()
+    off, ids = f.queryAll(False)
+    assert int(off[-1]) == g["fwd_total"]
+    assert "%016x" % orc.fnv_csr(off, ids) == g["fwd_fnv"]
+    assert [int(x) for x in ids[int(off[4]):int(off[5])]] == g["fwd_cands_read4"]
+    offr, idsr = f.queryAll(True)
+    assert int(offr[-1]) == g["rc_total"]
+    assert "%016x" % orc.fnv_csr(offr, idsr) == g["rc_fnv"]
+    T = orc.build_tables(want)
+    assert_csr_equal((off, ids), T.query_all(bases, offsets, want, g["k"], rnd, g["thr"], 0), "fwd")
+    assert_csr_equal((offr, idsr), T.query_all(bases, offsets, want, g["k"], rnd, g["thr"], 1), "rc")
+    # distinct keys per table == BBHashMap::numKeys
+    for j in (0, g["n"] // 2, g["n"] - 1):
+        assert f.tableNumKeys(j) == T.num_keys(j)
+    f.close()
+
+
+def test_c1_brute_force_kernel_equals_filter_kernel(c1_reads, c1_golden, orc):
+    bases, offsets = c1_reads
+    g = c1_golden["settings"][0]
+    rnd = ns.rand_from_seed(g["seed"], g["n"])
+    f = make_filter(g["k"], g["n"], g["thr"], rnd, mode=1)
+    f.load(ReadData(bases, offsets))
+    f.sketch()
+    assert "%016x" % orc.fnv_u64(f.sketches().ravel()) == g["fnv_sketches"]
+    f.close()
+
+
+def test_c1_dnabitset_loader(c1_raw, c1_golden, orc):
+    """Reads handed over in the reference's own 2-bit layout (DnaBitset)."""
+    packed, lengths = c1_raw
+    g = c1_golden["settings"][0]
+    f = make_filter(g["k"], g["n"], g["thr"], ns.rand_from_seed(g["seed"], g["n"]))
+    f.load_dnabitset(packed, lengths)
+    f.sketch()
+    assert "%016x" % orc.fnv_u64(f.sketches().ravel()) == g["fnv_sketches"]
+    f.close()
+
+
+@pytest.mark.parametrize("k,n,thr", [(23, 60, 6), (15, 30, 3), (31, 120, 12), (16, 33, 4), (17, 7, 1)])
+def test_synthetic_reads_vs_oracle(orc, k, n, thr):
+    """Nanopore-like synthetic reads (createData.py recipe, 10% error, 20x coverage of a small
+    genome so that real overlaps exist), ragged lengths incl. tile-boundary cases."""
+    lengths = ns.synth_lengths(1500, 3000, seed=3)
+    lengths[:12] = [0, 1, k - 2, k - 1, k, k + 1, 2047 + k, 2048 + k, 2049 + k, 4096 + k - 1, 150000, 33]
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=200_000, genome_seed=5, read_seed=6))
+    rnd = ns.rand_from_seed(20261017, n)
+    f = make_filter(k, n, thr, rnd)
+    f.initialize(rd)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    sk = f.sketches()
+    bad = np.argwhere(sk != want)
+    assert bad.size == 0, f"sketch differs at {bad[:3].tolist()}"
+    T = orc.build_tables(want)
+    fwd = f.queryAll(False)
+    assert_csr_equal(fwd, T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 0), "fwd")
+    assert int(fwd[0][-1]) > rd.numReads          # real overlaps were found, not only self hits
+    assert_csr_equal(f.queryAll(True), T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 1), "rc")
+    f.close()
+
+
+def test_device_synth_equals_host_synth():
+    import torch
+    lengths = ns.synth_lengths(400, 2000, seed=9)
+    p = ns.synth_params(genome_len=100_000, genome_seed=3, read_seed=4)
+    rd = ns.synth_reads_host(lengths, p, first_read=17)
+    d_off = torch.from_numpy(rd.offsets.astype(np.int64)).cuda()
+    d_bases = torch.zeros(int(rd.offsets[-1]) + 16, dtype=torch.uint8, device="cuda")
+    import ctypes as C
+    ns._lib.check(ns.lib().nsmh_synth_reads_device(0, C.byref(p), 17, lengths.size, d_off.data_ptr(),
+                                                   d_bases.data_ptr()))
+    got = d_bases[:int(rd.offsets[-1])].cpu().numpy()
+    assert (got == rd.bases).all()
+
+
+def test_online_query_matches_reference_semantics(orc, edge):
+    """getFilteredReads(string): forward windows, reverse complements, foreign strings, short
+    strings; also from many host threads at once (Consensus.cpp:29,189)."""
+    bases, offsets = edge["bases"], edge["offsets"]
+    seed, k, n, thr = (int(v) for v in edge["cfgs"][0])
+    rnd = edge["rand_0"]
+    f = make_filter(k, n, thr, rnd)
+    f.initialize(ReadData(bases, offsets))
+    T = orc.build_tables(edge["sketches_0"])
+    rd = ReadData(bases, offsets)
+    queries = [rd.getRead(i) for i in (0, 1, 3, 20, 27, 30, 60, 100, 164, 165, 166, 167, 168)]
+    queries += [rd.getRead(164)[500:4500], ns.reverse_complement(rd.getRead(164)[1000:3000]),
+                b"ACGT" * 100, b"", b"A" * 22, b"A" * 21, b"N" * 50]
+    want = [T.query_string(q, k, rnd, thr) for q in queries]
+    for q, w in zip(queries, want):
+        got = f.getFilteredReads(q)
+        assert got.dtype == np.uint32 and (got == w).all()
+    res = []
+    f.getFilteredReads(queries[0], res)
+    assert res == [int(x) for x in want[0]]
+    for got, w in zip(f.getFilteredReadsBatch(queries), want):
+        assert (got == w).all()
+    # concurrent callers
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(5):
+                for q, w in list(zip(queries, want))[tid % 3::3]:
+                    got = f.getFilteredReads(q)
+                    if got.size != w.size or (got != w).any():
+                        errors.append((tid, len(q)))
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[:3]
+    # raw sketches (private overload, ReadFilter.cpp:65-83)
+    off, ids = f.querySketches(edge["sketches_0"][:50])
+    assert_csr_equal((off, ids), (edge["fwd_off_0"][:51], edge["fwd_ids_0"][:int(edge["fwd_off_0"][50])]), "sk")
+    f.close()
+
+
+def test_error_behaviour():
+    f = MinHashReadFilter()
+    f.k = 32                                   # UB in the reference (1ull << 64); rejected here
+    with pytest.raises(ns.NsmhError):
+        f.initialize([b"ACGT"])
+    f = MinHashReadFilter()
+    f.k, f.n = 5, 4
+    f.randNumbers = ns.rand_from_seed(1, 4)
+    f._create()
+    with pytest.raises(ns.NsmhError):
+        f.sketch()                             # no reads loaded
+    f.load([b"ACGTACGT", b"ACGTAC"])
+    with pytest.raises(ns.NsmhError):
+        f.queryAll()                           # not sketched / built
+    f.sketch()
+    with pytest.raises(ns.NsmhError):
+        f.getFilteredReads(b"ACGTACG")         # tables not built
+    f.build()
+    assert f.getFilteredReads(b"ACGTACGT").size == 0     # thr 6 > n 4: nothing can qualify
+    f.close()
+
+
+def test_threshold_extremes(orc):
+    """thr = 0 / 1 (every id that shares a slot), thr = n (identical sketches only), thr > n."""
+    lengths = ns.synth_lengths(300, 800, seed=5)
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=20_000, genome_seed=8, read_seed=9,
+                                                      p_ins=0.0, p_del=0.0, p_sub=0.01))
+    k, n = 15, 16
+    rnd = ns.rand_from_seed(77, n)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    T = orc.build_tables(want)
+    for thr in (0, 1, 2, n, n + 1):
+        f = make_filter(k, n, thr, rnd)
+        f.initialize(rd)
+        assert_csr_equal(f.queryAll(False), T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 0), f"thr {thr}")
+        f.close()
+
+
+def test_large_roundtrip_properties():
+    """BASELINE-size-independent properties on a larger synthetic set (no oracle needed):
+    brute-force and filter kernels agree bit for bit; every read finds itself; candidate lists
+    ascend; the relation is symmetric for the forward self-query."""
+    lengths = ns.synth_lengths(20000, 8000, seed=12)
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=5_000_000, genome_seed=21, read_seed=22))
+    rnd = ns.rand_from_seed(20261017, 60)
+    f = make_filter(23, 60, 6, rnd, mode=0)
+    f.initialize(rd)
+    sk0 = f.sketches()
+    off, ids = f.queryAll(False)
+    b = make_filter(23, 60, 6, rnd, mode=1)
+    b.load(rd)
+    b.sketch()
+    assert (b.sketches() == sk0).all()
+    b.close()
+    N = rd.numReads
+    owner = np.repeat(np.arange(N, dtype=np.int64), np.diff(off.astype(np.int64)))
+    assert (np.bincount(owner[owner == ids], minlength=N) == 1).all()  # self is a candidate
+    d = np.diff(ids.astype(np.int64))
+    boundaries = off[1:-1].astype(np.int64) - 1
+    inner = np.ones(d.size, dtype=bool)
+    inner[boundaries[(boundaries >= 0) & (boundaries < d.size)]] = False
+    assert (d[inner] > 0).all()                                        # ascending, no duplicates
+    fwd = set(zip(owner.tolist(), ids.tolist()))
+    assert all((j, i) in fwd for (i, j) in fwd)                        # symmetric
+    f.close()
