@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the MinHash read-overlap stage (BASELINE.json metric: Gbases/s sketch+lookup).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic reads:
+    2-bit pack -> sketch (n minima per read) -> build n hash tables -> bulk lookup (forward
+    self-query of every read, CSR of candidate ids left on the device).
+Workload at N=1 = BASELINE.json configs[1]: 100 000 synthetic nanopore-like reads, ~10 kb
+mean (mixed-gamma lengths), 10 % error (3 % ins, 3 % del, 4 % sub), 50 % reverse strand,
+random 50 Mb genome, k=23, n=60, overlap-sketch-thr=6.  At N>1 every rank owns one such
+shard (weak scaling); sketches are all-gathered over NCCL and every rank builds the full
+tables and queries its own shard.
+
+`value`  : device-resident Gbases/s (ASCII reads already in HBM when the clock starts).
+`e2e`    : the same metric through the public API with HOST buffers: pinned ASCII reads are
+           copied host->device and the candidate CSR is copied back inside the timed region.
+`--impl reference` times the reference's own CPU implementation (oracle/_ref, the unmodified
+ReadFilter.cpp/BBHashMap.cpp; falls back to the C port in oracle/) on all host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+K, NHASH, THR = 23, 60, 6
+READS_PER_GPU = 100_000
+MEAN_LEN = 10_000
+RAND_SEED = 20261017
+GENOME_LEN = 50_000_000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def workload_name(n_gpus):
+    return (f"synthetic {READS_PER_GPU * n_gpus} nanopore reads (~10 kb mean mixed-gamma, 10% error, "
+            f"50 Mb random genome), k={K} n={NHASH} thr={THR}" + (f", {n_gpus} shards of {READS_PER_GPU}" if n_gpus > 1 else ""))
+
+
+def shard_lengths(rank):
+    import nanospring_b200 as ns
+    return ns.synth_lengths(READS_PER_GPU, MEAN_LEN, seed=1000 + rank)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            inside = t0 - 0.05 <= ts <= t1 + 0.15
+            try:
+                if inside:
+                    sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            if inside:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------
+def reference_arm(args, rank):
+    """The reference's own CPU implementation on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import nanospring_b200 as ns
+    from oracle.oracle import Oracle, RefLib
+    cores = os.cpu_count() or 1
+    sample_reads = 10_000
+    lengths = shard_lengths(0)[:sample_reads]
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=GENOME_LEN))
+    rnd = ns.rand_from_seed(RAND_SEED, NHASH)
+    bases_total = int(rd.offsets[-1])
+    use_ref = RefLib.available()
+
+    def one_step():
+        t0 = time.perf_counter()
+        if use_ref:
+            rf = RefLib.get().create(rd.bases, rd.offsets, K, NHASH, THR, rnd, threads=cores)
+            rf.query_all(0, threads=cores)
+            rf.close()
+        else:
+            orc = Oracle.get()
+            orc.set_num_threads(cores)
+            sk = orc.sketch_all(rd.bases, rd.offsets, K, NHASH, rnd)
+            T = orc.build_tables(sk)
+            T.query_all(rd.bases, rd.offsets, sk, K, rnd, THR, 0)
+        return time.perf_counter() - t0
+
+    for _ in range(args.warmup):
+        one_step()
+    ts = [one_step() for _ in range(args.steps)]
+    total = sum(ts)
+    value = bases_total * args.steps / total / 1e9
+    sample = (f"first {sample_reads} reads of shard 0 ({bases_total / 1e9:.3f} Gbases): sketch + "
+              f"populateHashTables + getFilteredReads(sketch) for every read, {cores} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": "Gbases/s MinHash sketch+lookup", "value": value, "unit": "Gbases/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": cores,
+                         "kind": "reference" if use_ref else "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nsmh", choices=["nsmh", "reference"])
+    ap.add_argument("--sketch-mode", type=int, default=0, help="0 filtered kernel, 1 brute force")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "nsmh" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import nanospring_b200 as ns
+    from nanospring_b200 import shard
+    from nanospring_b200._lib import check, lib
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    n_gpus = world
+
+    # ---- synthetic shard, generated on the device; a pinned host copy feeds the e2e leg ----
+    lengths = shard_lengths(rank)
+    offsets = np.zeros(lengths.size + 1, dtype=np.uint64)
+    offsets[1:] = np.cumsum(lengths, dtype=np.uint64)
+    total_bases = int(offsets[-1])
+    params = ns.synth_params(genome_len=GENOME_LEN)
+    d_off = torch.from_numpy(offsets.astype(np.int64)).cuda()
+    d_bases = torch.empty(total_bases + 64, dtype=torch.uint8, device="cuda")
+    check(lib().nsmh_synth_reads_device(local_rank, C.byref(params), rank * READS_PER_GPU, lengths.size,
+                                        d_off.data_ptr(), d_bases.data_ptr()))
+    h_bases = torch.empty(total_bases, dtype=torch.uint8, pin_memory=True)
+    h_bases.copy_(d_bases[:total_bases])
+    torch.cuda.synchronize()
+    host_rd = ns.ReadData(h_bases.numpy(), offsets)
+    log(f"[rank {rank}] shard: {lengths.size} reads, {total_bases / 1e9:.3f} Gbases, max read {int(lengths.max())}")
+
+    f = ns.MinHashReadFilter(device=local_rank)
+    f.k, f.n, f.overlapSketchThreshold = K, NHASH, THR
+    f.randNumbers = ns.rand_from_seed(RAND_SEED, NHASH)
+    f.sketchMode = args.sketch_mode
+    f._create()
+    rows_per_rank = [READS_PER_GPU] * world
+    ext = torch.cuda.ExternalStream(f.stream(), device=local_rank)
+    keep = {}
+
+    def device_step():
+        f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
+        f.sketch()
+        if world > 1:
+            keep["g"] = shard.gather_and_build(f, lengths.size, rows_per_rank, rank)
+        else:
+            f.build()
+        return f.queryAll(False, fetch=False)
+
+    def e2e_step():
+        f.load(host_rd)
+        f.sketch()
+        if world > 1:
+            keep["g"] = shard.gather_and_build(f, lengths.size, rows_per_rank, rank)
+        else:
+            f.build()
+        off, ids = f.queryAll(False, fetch=True)
+        return off, ids
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.time()
+        e0.record(ext)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(ext)
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out, t0, t1
+
+    for _ in range(args.warmup):
+        device_step()
+    launches0 = f.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ms_dev, total_ids, t0, t1 = timed(device_step, args.steps)
+    clocks = sampler.stop(t0, t1)
+    st = f.stats()
+    launches = st["kernel_launches"] - launches0
+    all_bases = total_bases
+    if dist is not None:
+        t = torch.tensor([total_bases], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        all_bases = int(t.item())
+    value = all_bases * args.steps / (ms_dev * 1e-3) / 1e9
+
+    # per-phase device times of the last step (CUDA events inside the library)
+    phases = {"pack_ms": st["pack_ms"], "sketch_ms": st["sketch_ms"], "sketch_main_kernel_ms": st["sketch_main_ms"],
+              "build_ms": st["build_ms"], "query_ms": st["query_ms"], "sketch_fixups_total": st["sketch_fixups"],
+              "query_pairs": st["query_pairs"], "candidate_ids": int(total_ids)}
+
+    # ---- e2e: host buffers in, CSR out ----
+    for _ in range(2):
+        e2e_step()
+    ms_e2e, (off, ids), _, _ = timed(e2e_step, args.steps)
+    e2e_value = all_bases * args.steps / (ms_e2e * 1e-3) / 1e9
+    h2d = total_bases + offsets.nbytes
+    d2h = off.nbytes + ids.nbytes
+
+    # ---- roofline of the dominant kernel (sketch_filter_kernel / sketch_brute_kernel) ----
+    hbm_peak, peak_src, sm_max = peaks()
+    mean_len = total_bases / lengths.size
+    alg_bytes = total_bases * 0.25 + lengths.size * NHASH * 8          # packed bases in + sketch rows out
+    sk_ms = st["sketch_main_ms"]
+    achieved = alg_bytes / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else 0.0
+    # the reference's operation count on the INT32 pipe: (6n+6) lane-ops per base
+    int_ops = total_bases * (6 * NHASH + 6)
+    int_peak = 148 * 64 * sm_max * 1e6          # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH rt_SMSP=2)
+    roofline = {"bound": "hbm", "kernel": "sketch_filter_kernel" if args.sketch_mode == 0 else "sketch_brute_kernel",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "peak_source": peak_src, "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sk_ms,
+                "kernel_gbases_per_s": total_bases / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else None,
+                "int32_reference_count": {"lane_ops_per_base": 6 * NHASH + 6,
+                                          "achieved_tops": int_ops / (sk_ms * 1e-3) / 1e12 if sk_ms > 0 else None,
+                                          "nominal_alu_peak_tops": int_peak / 1e12,
+                                          "frac": (int_ops / (sk_ms * 1e-3)) / int_peak if sk_ms > 0 else None,
+                                          "note": "filter kernel skips most (k-mer,hash) pairs exactly; >1 means faster than the brute-force INT32 roof"}}
+
+    if dist is not None:
+        dist.barrier()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "Gbases/s MinHash sketch+lookup", "value": value, "unit": "Gbases/s", "n_gpus": n_gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(n_gpus), "k": K, "num_hash": NHASH, "overlap_sketch_thr": THR,
+                   "reads_per_gpu": READS_PER_GPU, "bases_per_gpu": total_bases, "mean_read_len": mean_len,
+                   "sketch_mode": "filter" if args.sketch_mode == 0 else "brute",
+                   "l2": "inputs larger than L2 (1 GB ASCII + 0.25 GB packed per step vs 126 MB L2)",
+                   "step": "pack + sketch + build tables + bulk forward lookup, CSR left on device"},
+        "phases_last_step": phases,
+        "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "clocks": clocks,
+    }
+
+    # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample ----
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        from oracle.oracle import Oracle, RefLib
+        cores = os.cpu_count() or 1
+        sample_reads = 20_000
+        sub = ns.ReadData(host_rd.bases[:int(offsets[sample_reads])].copy(), offsets[:sample_reads + 1].copy())
+        rnd = ns.rand_from_seed(RAND_SEED, NHASH)
+        t0 = time.perf_counter()
+        if RefLib.available():
+            rf = RefLib.get().create(sub.bases, sub.offsets, K, NHASH, THR, rnd, threads=cores)
+            c_off, c_ids = rf.query_all(0, threads=cores)
+            detail = {"sketch_ms": rf.sketch_ms, "build_ms": rf.build_ms, "query_ms": rf.query_ms}
+            rf.close()
+            kind = "reference"
+        else:
+            orc = Oracle.get()
+            orc.set_num_threads(cores)
+            sk = orc.sketch_all(sub.bases, sub.offsets, K, NHASH, rnd)
+            T = orc.build_tables(sk)
+            c_off, c_ids = T.query_all(sub.bases, sub.offsets, sk, K, rnd, THR, 0)
+            detail = {}
+            kind = "port"
+        dt = time.perf_counter() - t0
+        sb = int(sub.offsets[-1])
+        line["cpu_baseline"] = {"value": sb / dt / 1e9, "unit": "Gbases/s", "cores": cores, "kind": kind,
+                                "sample": f"first {sample_reads} reads of the workload ({sb / 1e9:.3f} Gbases), "
+                                          f"sketch + tables + forward lookup, {cores} OpenMP threads",
+                                "seconds": dt, **detail}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
