@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--impl", default="nsmh", choices=["nsmh", "reference"])
     ap.add_argument("--sketch-mode", type=int, default=0, help="0 filtered kernel, 1 brute force")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "nsmh" else args.warmup
 
@@ -290,9 +291,11 @@ def main():
               "query_pairs": st["query_pairs"], "candidate_ids": int(total_ids)}
 
     # ---- e2e: host buffers in, CSR out ----
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         e2e_step()
-    ms_e2e, (off, ids), _, _ = timed(e2e_step, args.steps)
+    ms_e2e, (off, ids), _, _ = timed(e2e_step, 1 if args.no_e2e else args.steps)
+    if args.no_e2e:
+        ms_e2e *= args.steps
     e2e_value = all_bases * args.steps / (ms_e2e * 1e-3) / 1e9
     h2d = total_bases + offsets.nbytes
     d2h = off.nbytes + ids.nbytes

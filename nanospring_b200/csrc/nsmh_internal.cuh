@@ -40,10 +40,12 @@ struct DevBuf {
 
 // ------------------------------------------------------------- constants --
 constexpr int kWordBases = 16;          // bases per packed u32 word, first base in bits 31..30
-constexpr int kTileWords = 128;         // words (2048 k-mer start positions) per sketch tile
+constexpr int kTileWords = 1024;        // default words (16384 k-mer start positions) per sketch tile
 constexpr int kFilterMaxBits = 12;      // largest prefix width b of the sketch filter tables
 constexpr int kFilterTabSize = 1 << (kFilterMaxBits + 1);  // table for b lives at [2^b, 2^(b+1))
-constexpr int kFilterLambdaLog2 = 3;    // b = floor(log2(#kmers)) - 3  => 8..16 k-mers expected per bucket
+constexpr int kFilterLambdaLog2 = 3;    // default: b = floor(log2(#kmers)) - 3  => 8..16 k-mers expected per bucket
+constexpr int kFilter3MaxBits = 10;     // 3-positions-per-lookup tables: window of b+4 bits
+constexpr int kFilter3TabSize = 1 << (kFilter3MaxBits + 5);   // table for b lives at [2^(b+4), 2^(b+5))
 constexpr uint64_t kEmptyKey = ~0ULL;   // empty marker of the hash tables (key ~0 has its own slot)
 constexpr int kPackPadWords = 8;        // zero words after the last packed word (k-mer window overrun)
 
@@ -61,16 +63,24 @@ struct ReadSet {
     void release(cudaStream_t s) { offsets.release(s); packed.release(s); }
 };
 
+// One 16-byte hash-table slot = one 32-byte sector per probe.  Slots start as
+// all-ones: key ~0 is the empty marker and cntm1 (group size - 1) wraps to 0 on
+// the first insert.  val = the read id itself for a group of one, else the start
+// of the group in Tables::ids.
+struct __align__(16) Slot {
+    uint64_t key;
+    uint32_t val;
+    uint32_t cntm1;
+};
+
 // Hash tables: one open-addressing region of (cap+1) slots per hash function.
 struct Tables {
     bool built = false;
     uint32_t table_reads = 0;   // rows of the sketch matrix the tables were built from
     uint32_t log2cap = 0;
     uint64_t cap = 0;           // slots per region (power of two); slot `cap` holds key ~0
-    DevBuf keys;                // u64 [n*(cap+1)]
-    DevBuf cnt;                 // u32 [n*(cap+1)]  group size
-    DevBuf begin;               // u32 [n*(cap+1)]  start of the group in ids
-    DevBuf ids;                 // u32 [table_reads*n] read ids grouped by (table, key)
+    DevBuf slots;               // Slot [n*(cap+1)]
+    DevBuf ids;                 // u32 read ids of the groups with two or more members
 };
 
 // Scratch of one bulk / online query (owns its stream so that concurrent host
@@ -78,11 +88,17 @@ struct Tables {
 struct QueryWs {
     cudaStream_t stream = nullptr;
     DevBuf qsketch;     // u64 [nq*n]  (string queries)
-    DevBuf pbegin, pcnt;   // u32 [nq*n]
-    DevBuf poff;        // u64 [nq*n+1]
+    DevBuf pval, pcnt;  // u32 [nq*n]  probe results
+    DevBuf heavy_list;  // u32 [nq]    queries that overflow the warp buffer
+    DevBuf counters;    // u64 [4]
+    DevBuf hc;          // u32 [nh*n+1], global path
+    DevBuf hoff;        // u64 [nh*n+1]
+    DevBuf hout;        // u32 results of heavy queries
+    DevBuf hcnt;        // u32 [nh+1]
+    DevBuf hstart;      // u64 [nh+1]
     DevBuf pairs, pairs_alt;   // u64 [T]
     DevBuf flags;       // u8 [T]
-    DevBuf qcount;      // u32 [nq]
+    DevBuf qcount;      // u32 [nq+1]
     DevBuf out_off;     // u64 [nq+1]
     DevBuf out_ids;     // u32 [total]
     DevBuf nsel;        // u64 [2]
@@ -113,6 +129,10 @@ struct nsmh_ctx {
     nsmh::DevBuf d_ftab_hit;    // u8 [kFilterTabSize]     1 = some hash targets this prefix
     nsmh::DevBuf d_ftab_first;  // u8 [kFilterTabSize]     first hash of the chain
     nsmh::DevBuf d_ftab_next;   // u8 [(kFilterMaxBits+1)*n] next hash in chain, 0xFF = end
+    nsmh::DevBuf d_ftab_hit3;   // u8 [kFilter3TabSize]    3 hit bits per (b+4)-bit window
+    int lambda_log2 = nsmh::kFilterLambdaLog2;
+    int sketch_variant = 0;     // 0: 3-position lookups + dense hit rounds, 1: first version (A/B runs)
+    uint32_t tile_words = nsmh::kTileWords;
 
     nsmh::ReadSet reads;
     bool reads_loaded = false;

@@ -1,83 +1,319 @@
 // Candidate lookup on the device.  Replaces
 //   MinHashReadFilter::getFilteredReads(kMer_t sketch[], results)   (src/ReadFilter.cpp:65-83)
 //   BBHashMap::pushMatchesInVector                                  (src/BBHashMap.cpp:101-120)
-// for a whole batch of query sketches at once: n exact probes per query, the id
-// lists of all probes are gathered as (query, id) pairs, sorted, and an id is
-// emitted when it occurs at least overlapSketchThreshold times.  Output per query
-// is ascending and contains the query read itself, exactly like the reference's
-// std::sort + upper_bound run counting.
+// for a whole batch of query sketches: n exact probes per query, the id lists of
+// all probes are gathered, sorted, and an id is emitted when it occurs at least
+// overlapSketchThreshold times.  Output per query is ascending and contains the
+// query read itself, exactly like the reference's std::sort + upper_bound loop.
+//
+// lookup_kernel: one warp per query.  Lanes probe the n tables (one 16-byte slot
+// load per probe), a warp scan places the id lists in a warp-private shared-memory
+// buffer, a bitonic network sorts it, and run lengths are compared against the
+// threshold.  Pass 1 (COUNT) stores the probe results and the per-query result
+// count; after one prefix sum pass 2 (EMIT) repeats the cheap on-chip part and
+// writes the CSR in place.  Queries whose gathered lists exceed the buffer (short
+// reads that all share the all-zero / all-ones sketch) take the global
+// path: (query, id) pairs, one radix sort, run flags, compaction.
+#include <algorithm>
+
 #include "nsmh_internal.cuh"
 
 namespace nsmh {
+
+constexpr int kLookupCap = 2048;     // ids per warp-private buffer
+constexpr int kLookupWarps = 8;
+
+struct LookupArgs {
+    const uint64_t *qsk;     // [nq][n]
+    const Slot *slots;
+    const uint32_t *ids;
+    uint32_t *pval, *pcnt;   // [nq][n] probe results (first id / start in ids, group size)
+    uint32_t *qcount;        // [nq+1]
+    const uint64_t *out_off; // [nq+1]   (EMIT)
+    uint32_t *out_ids;       //          (EMIT)
+    uint32_t *heavy_list;    // [nq]
+    unsigned long long *counters;   // [0] number of heavy queries, [1] total gathered pairs
+    uint64_t cap;
+    uint32_t log2cap, nq, n, thr;
+};
 
 __device__ __forceinline__ uint64_t slot_hash_q(uint64_t key, uint32_t log2cap) {
     return (key * 0x9E3779B97F4A7C15ULL) >> (64 - log2cap);
 }
 
-// one thread per (query, hash): exact probe -> [begin, begin+cnt) in ids
-__global__ void __launch_bounds__(256)
-probe_kernel(const uint64_t *__restrict__ qsk, uint64_t items, uint32_t n, uint64_t cap,
-             uint32_t log2cap, const uint64_t *__restrict__ keys, const uint32_t *__restrict__ cnt,
-             const uint32_t *__restrict__ begin, uint32_t *__restrict__ pbegin,
-             uint32_t *__restrict__ pcnt) {
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < items;
-         t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t l = (uint32_t)(t % n);
-        const uint64_t key = qsk[t];
-        const uint64_t base = (uint64_t)l * (cap + 1);
-        uint64_t s = base + cap;
-        bool found = true;
-        if (key != kEmptyKey) {
-            uint64_t h = slot_hash_q(key, log2cap);
-            for (;;) {
-                s = base + h;
-                uint64_t kk = keys[s];
-                if (kk == key) break;
-                if (kk == kEmptyKey) { found = false; break; }
-                h = (h + 1) & (cap - 1);
-            }
-        }
-        uint32_t c = found ? cnt[s] : 0u;
-        pcnt[t] = c;
-        pbegin[t] = c ? begin[s] : 0u;
+// exact probe of table l: group size (0 = absent) and val (the id itself for a
+// group of one, else the start of the group in ids)
+__device__ __forceinline__ uint32_t probe_slot(const Slot *__restrict__ slots, uint64_t cap,
+                                               uint32_t log2cap, uint32_t l, uint64_t key, uint32_t &val) {
+    const Slot *region = slots + (uint64_t)l * (cap + 1);
+    if (key == kEmptyKey) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(region + cap));
+        val = v.z;
+        return v.w + 1u;          // untouched slot: 0xFFFFFFFF + 1 = 0
+    }
+    uint64_t h = slot_hash_q(key, log2cap);
+    for (;;) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(region + h));
+        const uint64_t kk = ((uint64_t)v.y << 32) | v.x;
+        if (kk == key) { val = v.z; return v.w + 1u; }
+        if (kk == kEmptyKey) { val = 0; return 0; }
+        h = (h + 1) & (cap - 1);
     }
 }
 
-// one thread per (query, hash): copy the group's ids as (local query << 32 | id)
+template <bool EMIT>
+__global__ void __launch_bounds__(kLookupWarps * 32)
+lookup_kernel(LookupArgs a) {
+    extern __shared__ uint32_t s_buf[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *buf = s_buf + (size_t)warp * kLookupCap;
+    const uint32_t total_warps = gridDim.x * kLookupWarps;
+    unsigned long long pairs_local = 0;
+
+    for (uint32_t q = blockIdx.x * kLookupWarps + warp; q < a.nq; q += total_warps) {
+        // ---- probe the n tables, lay the id lists out in the buffer ----
+        uint32_t T = 0;
+        for (uint32_t l0 = 0; l0 < a.n; l0 += 32) {
+            const uint32_t l = l0 + lane;
+            uint32_t val = 0, c = 0;
+            if (l < a.n) {
+                const size_t t = (size_t)q * a.n + l;
+                if (!EMIT) {
+                    c = probe_slot(a.slots, a.cap, a.log2cap, l, a.qsk[t], val);
+                    a.pval[t] = val;
+                    a.pcnt[t] = c;
+                } else {
+                    c = a.pcnt[t];
+                    val = a.pval[t];
+                }
+            }
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t off = T + incl - c;
+            if ((uint64_t)T + round_total <= kLookupCap) {
+                if (c == 1) buf[off] = val;
+                else if (c > 1 && c <= 8)
+                    for (uint32_t r = 0; r < c; ++r) buf[off + r] = a.ids[val + r];
+                uint32_t big = __ballot_sync(0xffffffffu, c > 8);
+                while (big) {
+                    const int src = __ffs(big) - 1;
+                    big &= big - 1;
+                    const uint32_t bv = __shfl_sync(0xffffffffu, val, src);
+                    const uint32_t bc = __shfl_sync(0xffffffffu, c, src);
+                    const uint32_t bo = __shfl_sync(0xffffffffu, off, src);
+                    for (uint32_t r = lane; r < bc; r += 32) buf[bo + r] = a.ids[bv + r];
+                }
+            }
+            // saturate: the sum of n group sizes can exceed 32 bits only in theory
+            T = (uint64_t)T + round_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + round_total;
+        }
+        if (!EMIT) pairs_local += lane == 0 ? T : 0;
+        if (T > kLookupCap) {                     // global path handles this query
+            if (!EMIT && lane == 0) {
+                a.qcount[q] = 0;
+                a.heavy_list[atomicAdd(a.counters, 1ULL)] = q;
+            }
+            continue;
+        }
+        // ---- sort (bitonic network over the padded buffer) ----
+        uint32_t P = 32;
+        while (P < T) P <<= 1;
+        for (uint32_t i = T + lane; i < P; i += 32) buf[i] = 0xFFFFFFFFu;
+        __syncwarp();
+        for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                for (uint32_t i = lane; i < P / 2; i += 32) {
+                    const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                    const uint32_t hi = lo | j;
+                    const uint32_t x = buf[lo], y = buf[hi];
+                    const bool asc = (lo & kk) == 0;
+                    if ((x > y) == asc) { buf[lo] = y; buf[hi] = x; }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- run lengths against the threshold (ReadFilter.cpp:76-82) ----
+        uint32_t emitted = 0;
+        const uint64_t out0 = EMIT ? a.out_off[q] : 0;
+        for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool ok = false;
+            uint32_t v = 0;
+            if (i < T) {
+                v = buf[i];
+                const bool head = i == 0 || buf[i - 1] != v;
+                ok = head && (a.thr <= 1 || (i + a.thr - 1 < T && buf[i + a.thr - 1] == v));
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            if (EMIT && ok) a.out_ids[out0 + emitted + __popc(m & ((1u << lane) - 1))] = v;
+            emitted += __popc(m);
+        }
+        if (!EMIT && lane == 0) a.qcount[q] = emitted;
+        __syncwarp();
+    }
+    if (!EMIT && lane == 0 && pairs_local) atomicAdd(a.counters + 1, pairs_local);
+}
+
+// ---------------------------------------------------------------- global path --
 __global__ void __launch_bounds__(256)
-gather_pairs_kernel(uint64_t item0, uint64_t items, uint32_t n, uint32_t q0,
-                    const uint32_t *__restrict__ pbegin, const uint32_t *__restrict__ pcnt,
-                    const uint64_t *__restrict__ poff, uint64_t pair0,
-                    const uint32_t *__restrict__ ids, uint32_t id_base, uint64_t *__restrict__ pairs) {
-    for (uint64_t t = item0 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < item0 + items;
-         t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t c = pcnt[t];
-        if (!c) continue;
-        const uint64_t q = t / n - q0;
-        const uint32_t *src = ids + pbegin[t];
-        uint64_t *dst = pairs + (poff[t] - pair0);
-        for (uint32_t r = 0; r < c; ++r) dst[r] = (q << 32) | (uint64_t)(src[r] + id_base);
+heavy_counts_kernel(const uint32_t *__restrict__ heavy_list, uint64_t items, uint32_t n,
+                    const uint32_t *__restrict__ pcnt, uint32_t *__restrict__ hc) {
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < items;
+         t += (uint64_t)gridDim.x * blockDim.x)
+        hc[t] = pcnt[(size_t)heavy_list[t / n] * n + t % n];
+}
+
+// one warp per (heavy query, hash): copy the group's ids as (local heavy index << 32 | id)
+__global__ void __launch_bounds__(256)
+heavy_gather_kernel(const uint32_t *__restrict__ heavy_list, uint64_t item0, uint64_t items, uint32_t n,
+                    uint32_t h0, const uint32_t *__restrict__ pval, const uint32_t *__restrict__ pcnt,
+                    const uint64_t *__restrict__ hoff, uint64_t pair0, const uint32_t *__restrict__ ids,
+                    uint64_t *__restrict__ pairs) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t t = item0 + blockIdx.x * (uint64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+         t < item0 + items; t += warps) {
+        const uint64_t h = t / n;
+        const size_t src_t = (size_t)heavy_list[h] * n + t % n;
+        const uint32_t c = pcnt[src_t], val = pval[src_t];
+        uint64_t *dst = pairs + (hoff[t] - pair0);
+        const uint64_t tag = (h - h0) << 32;
+        if (c == 1) { if (lane == 0) dst[0] = tag | val; }
+        else for (uint32_t r = lane; r < c; r += 32) dst[r] = tag | ids[val + r];
     }
 }
 
 // sorted pairs -> flag the first element of every run of length >= thr
 __global__ void __launch_bounds__(256)
-flag_runs_kernel(const uint64_t *__restrict__ pairs, uint64_t T, uint32_t thr, uint32_t q0,
-                 uint8_t *__restrict__ flags, uint32_t *__restrict__ qcount) {
+flag_runs_kernel(const uint64_t *__restrict__ pairs, uint64_t T, uint32_t thr,
+                 const uint32_t *__restrict__ heavy_list, uint32_t h0, uint8_t *__restrict__ flags,
+                 uint32_t *__restrict__ qcount) {
     for (uint64_t p = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; p < T;
          p += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t v = pairs[p];
         bool head = p == 0 || pairs[p - 1] != v;
         bool ok = head && (thr <= 1 || (p + thr - 1 < T && pairs[p + thr - 1] == v));
         flags[p] = ok;
-        if (ok) atomicAdd(qcount + q0 + (uint32_t)(v >> 32), 1u);
+        if (ok) atomicAdd(qcount + heavy_list[h0 + (uint32_t)(v >> 32)], 1u);
     }
 }
 
-static int grid_for(uint64_t items, int sms) {
-    uint64_t b = (items + 255) / 256;
+__global__ void __launch_bounds__(256)
+heavy_result_counts_kernel(const uint32_t *__restrict__ heavy_list, uint32_t nh,
+                           const uint32_t *__restrict__ qcount, uint32_t *__restrict__ hcnt) {
+    for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += gridDim.x * blockDim.x)
+        hcnt[h] = qcount[heavy_list[h]];
+}
+
+// one warp per heavy query: move its results to their place in the CSR
+__global__ void __launch_bounds__(256)
+heavy_copy_kernel(const uint32_t *__restrict__ heavy_list, uint32_t nh, const uint32_t *__restrict__ hcnt,
+                  const uint64_t *__restrict__ hstart, const uint32_t *__restrict__ hout,
+                  const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t h = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); h < nh; h += warps) {
+        const uint32_t *src = hout + hstart[h];
+        uint32_t *dst = out_ids + out_off[heavy_list[h]];
+        for (uint32_t r = lane; r < hcnt[h]; r += 32) dst[r] = src[r];
+    }
+}
+
+static int grid_for(uint64_t items, int sms, int per_block = 256) {
+    uint64_t b = (items + per_block - 1) / per_block;
     uint64_t cap = (uint64_t)sms * 16;
     return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+// Queries that overflowed the warp buffer: global (heavy index, id) pair sort in batches.
+static int heavy_path(nsmh_ctx *c, QueryWs &ws, uint32_t nh, cudaStream_t s) {
+    Tables &T = c->tables;
+    const uint32_t n = c->n;
+    const uint64_t items = (uint64_t)nh * n;
+    uint32_t *hl = ws.heavy_list.as<uint32_t>();
+    NSMH_TRY(ws.hc.ensure((items + 1) * sizeof(uint32_t), s));
+    NSMH_TRY(ws.hoff.ensure((items + 1) * sizeof(uint64_t), s));
+    NSMH_CK(cudaMemsetAsync(ws.hc.as<uint32_t>() + items, 0, sizeof(uint32_t), s));
+    heavy_counts_kernel<<<grid_for(items, c->num_sms), 256, 0, s>>>(hl, items, n, ws.pcnt.as<uint32_t>(),
+                                                                    ws.hc.as<uint32_t>());
+    NSMH_CK(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.hc.as<uint32_t>(), ws.hoff.as<uint64_t>(), items + 1, s));
+    NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
+    NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.hc.as<uint32_t>(), ws.hoff.as<uint64_t>(), items + 1, s));
+    ws.launches += 3;
+    // pair offset of every heavy query, on the host, to cut batches that fit the scratch budget
+    std::vector<uint64_t> hstart_pairs((size_t)nh + 1);
+    NSMH_CK(cudaMemcpy2DAsync(hstart_pairs.data(), sizeof(uint64_t), ws.hoff.p, (size_t)n * sizeof(uint64_t),
+                              sizeof(uint64_t), nh, cudaMemcpyDeviceToHost, s));
+    NSMH_CK(cudaMemcpyAsync(&hstart_pairs[nh], ws.hoff.as<uint64_t>() + items, sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost, s));
+    NSMH_CK(cudaStreamSynchronize(s));
+    size_t free_b = 0, total_b = 0;
+    NSMH_CK(cudaMemGetInfo(&free_b, &total_b));
+    uint64_t budget = (uint64_t)((free_b + ws.pairs.cap + ws.pairs_alt.cap + ws.flags.cap) * 0.6 / 21.0);
+    if (budget < (1u << 20)) budget = 1u << 20;
+    uint64_t hout_total = 0;
+    NSMH_TRY(ws.nsel.ensure(4 * sizeof(uint64_t), s));
+    for (uint32_t h0 = 0; h0 < nh;) {
+        uint32_t h1 = h0 + 1;   // at least one query per batch
+        while (h1 < nh && hstart_pairs[h1 + 1] - hstart_pairs[h0] <= budget) ++h1;
+        const uint64_t pair0 = hstart_pairs[h0], Tn = hstart_pairs[h1] - pair0;
+        if (Tn) {
+            NSMH_TRY(ws.pairs.ensure(Tn * sizeof(uint64_t), s));
+            NSMH_TRY(ws.pairs_alt.ensure(Tn * sizeof(uint64_t), s));
+            NSMH_TRY(ws.flags.ensure(Tn, s));
+            const uint64_t bitems = (uint64_t)(h1 - h0) * n;
+            heavy_gather_kernel<<<grid_for(bitems, c->num_sms, 8), 256, 0, s>>>(
+                hl, (uint64_t)h0 * n, bitems, n, h0, ws.pval.as<uint32_t>(), ws.pcnt.as<uint32_t>(),
+                ws.hoff.as<uint64_t>(), pair0, T.ids.as<uint32_t>(), ws.pairs.as<uint64_t>());
+            NSMH_CK(cudaGetLastError());
+            int hbits = 1;
+            while ((1ULL << hbits) < (uint64_t)(h1 - h0)) ++hbits;
+            bool in_alt = false;
+            tmp_bytes = 0;
+            NSMH_CK(cub_sort_keys_u64(nullptr, tmp_bytes, ws.pairs.as<uint64_t>(), ws.pairs_alt.as<uint64_t>(),
+                                      Tn, 0, 32 + hbits, in_alt, s));
+            NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
+            NSMH_CK(cub_sort_keys_u64(ws.cub_tmp.p, tmp_bytes, ws.pairs.as<uint64_t>(),
+                                      ws.pairs_alt.as<uint64_t>(), Tn, 0, 32 + hbits, in_alt, s));
+            const uint64_t *sorted = in_alt ? ws.pairs_alt.as<uint64_t>() : ws.pairs.as<uint64_t>();
+            flag_runs_kernel<<<grid_for(Tn, c->num_sms), 256, 0, s>>>(sorted, Tn, c->thr, hl, h0,
+                                                                      ws.flags.as<uint8_t>(), ws.qcount.as<uint32_t>());
+            NSMH_CK(cudaGetLastError());
+            NSMH_TRY(ws.hout.ensure((hout_total + Tn) * sizeof(uint32_t), s, hout_total * sizeof(uint32_t)));
+            tmp_bytes = 0;
+            NSMH_CK(cub_select_low32_flagged(nullptr, tmp_bytes, sorted, ws.flags.as<uint8_t>(),
+                                             ws.hout.as<uint32_t>() + hout_total, ws.nsel.as<uint64_t>(), Tn, s));
+            NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
+            NSMH_CK(cub_select_low32_flagged(ws.cub_tmp.p, tmp_bytes, sorted, ws.flags.as<uint8_t>(),
+                                             ws.hout.as<uint32_t>() + hout_total, ws.nsel.as<uint64_t>(), Tn, s));
+            ws.launches += 6 + (32 + hbits + 7) / 8;
+            uint64_t nsel = 0;
+            NSMH_CK(cudaMemcpyAsync(&nsel, ws.nsel.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            NSMH_CK(cudaStreamSynchronize(s));
+            hout_total += nsel;
+        }
+        h0 = h1;
+    }
+    // where every heavy query's results start in hout
+    NSMH_TRY(ws.hcnt.ensure(((size_t)nh + 1) * sizeof(uint32_t), s));
+    NSMH_TRY(ws.hstart.ensure(((size_t)nh + 1) * sizeof(uint64_t), s));
+    NSMH_CK(cudaMemsetAsync(ws.hcnt.as<uint32_t>() + nh, 0, sizeof(uint32_t), s));
+    heavy_result_counts_kernel<<<grid_for(nh, c->num_sms), 256, 0, s>>>(hl, nh, ws.qcount.as<uint32_t>(),
+                                                                        ws.hcnt.as<uint32_t>());
+    NSMH_CK(cudaGetLastError());
+    tmp_bytes = 0;
+    NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.hcnt.as<uint32_t>(), ws.hstart.as<uint64_t>(), (size_t)nh + 1, s));
+    NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
+    NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.hcnt.as<uint32_t>(), ws.hstart.as<uint64_t>(), (size_t)nh + 1, s));
+    ws.launches += 3;
+    return NSMH_OK;
 }
 
 // Query nq device-resident sketches [nq][n] against the tables.  Result CSR in
@@ -92,120 +328,74 @@ int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, u
     ws.last_total = 0;
     ws.last_pairs = 0;
     NSMH_TRY(ws.out_off.ensure(((size_t)nq + 1) * sizeof(uint64_t), s));
-    NSMH_TRY(ws.qcount.ensure(((size_t)nq + 1) * sizeof(uint32_t), s));
-    NSMH_CK(cudaMemsetAsync(ws.qcount.p, 0, ((size_t)nq + 1) * sizeof(uint32_t), s));
     if (nq == 0) {
         NSMH_CK(cudaMemsetAsync(ws.out_off.p, 0, sizeof(uint64_t), s));
         NSMH_CK(cudaStreamSynchronize(s));
         return NSMH_OK;
     }
-    NSMH_TRY(ws.pbegin.ensure(items * sizeof(uint32_t), s));
-    NSMH_TRY(ws.pcnt.ensure((items + 1) * sizeof(uint32_t), s));
-    NSMH_TRY(ws.poff.ensure((items + 1) * sizeof(uint64_t), s));
-    NSMH_TRY(ws.nsel.ensure(4 * sizeof(uint64_t), s));
-    NSMH_CK(cudaMemsetAsync(ws.pcnt.as<uint32_t>() + items, 0, sizeof(uint32_t), s));
+    NSMH_TRY(ws.qcount.ensure(((size_t)nq + 1) * sizeof(uint32_t), s));
+    NSMH_TRY(ws.pval.ensure(items * sizeof(uint32_t), s));
+    NSMH_TRY(ws.pcnt.ensure(items * sizeof(uint32_t), s));
+    NSMH_TRY(ws.heavy_list.ensure((size_t)nq * sizeof(uint32_t), s));
+    NSMH_TRY(ws.counters.ensure(4 * sizeof(uint64_t), s));
+    NSMH_CK(cudaMemsetAsync(ws.counters.p, 0, 4 * sizeof(uint64_t), s));
+    NSMH_CK(cudaMemsetAsync(ws.qcount.as<uint32_t>() + nq, 0, sizeof(uint32_t), s));
 
-    probe_kernel<<<grid_for(items, c->num_sms), 256, 0, s>>>(
-        d_qsketch, items, n, T.cap, T.log2cap, T.keys.as<uint64_t>(), T.cnt.as<uint32_t>(),
-        T.begin.as<uint32_t>(), ws.pbegin.as<uint32_t>(), ws.pcnt.as<uint32_t>());
+    static bool attr_set = false;
+    const size_t smem = (size_t)kLookupWarps * kLookupCap * sizeof(uint32_t);
+    if (!attr_set) {
+        NSMH_CK(cudaFuncSetAttribute(lookup_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSMH_CK(cudaFuncSetAttribute(lookup_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    LookupArgs a;
+    a.qsk = d_qsketch;
+    a.slots = T.slots.as<Slot>();
+    a.ids = T.ids.as<uint32_t>();
+    a.pval = ws.pval.as<uint32_t>();
+    a.pcnt = ws.pcnt.as<uint32_t>();
+    a.qcount = ws.qcount.as<uint32_t>();
+    a.out_off = ws.out_off.as<uint64_t>();
+    a.out_ids = nullptr;
+    a.heavy_list = ws.heavy_list.as<uint32_t>();
+    a.counters = ws.counters.as<unsigned long long>();
+    a.cap = T.cap;
+    a.log2cap = T.log2cap;
+    a.nq = nq;
+    a.n = n;
+    a.thr = c->thr;
+    int blocks = (int)std::min<uint64_t>(((uint64_t)nq + kLookupWarps - 1) / kLookupWarps, (uint64_t)c->num_sms * 3);
+    lookup_kernel<false><<<blocks, kLookupWarps * 32, smem, s>>>(a);
     ++ws.launches;
     NSMH_CK(cudaGetLastError());
+    unsigned long long cnt[2] = {0, 0};
+    NSMH_CK(cudaMemcpyAsync(cnt, ws.counters.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+    NSMH_CK(cudaStreamSynchronize(s));
+    const uint32_t nh = (uint32_t)cnt[0];
+    ws.last_pairs = cnt[1];
+    // a result id needs at least one gathered pair, so #pairs bounds the output size
+    NSMH_TRY(ws.out_ids.ensure((size_t)std::max<uint64_t>(cnt[1], 1) * sizeof(uint32_t), s));
+    a.out_ids = ws.out_ids.as<uint32_t>();
+    if (nh) NSMH_TRY(heavy_path(c, ws, nh, s));
+
     size_t tmp_bytes = 0;
-    NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.pcnt.as<uint32_t>(),
-                                         ws.poff.as<uint64_t>(), items + 1, s));
+    NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
     NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
-    NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.pcnt.as<uint32_t>(),
-                                         ws.poff.as<uint64_t>(), items + 1, s));
-    ws.launches += 2;
-    uint64_t total_pairs = 0;
-    NSMH_CK(cudaMemcpyAsync(&total_pairs, ws.poff.as<uint64_t>() + items, sizeof(uint64_t),
-                            cudaMemcpyDeviceToHost, s));
-    NSMH_CK(cudaStreamSynchronize(s));
-    ws.last_pairs = total_pairs;
-
-    // Batches of whole queries whose pairs fit the scratch budget.
-    size_t free_b = 0, total_b = 0;
-    NSMH_CK(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t budget_pairs = (uint64_t)((free_b + ws.pairs.cap + ws.pairs_alt.cap + ws.flags.cap) * 0.6 / 21.0);
-    if (budget_pairs < (1u << 20)) budget_pairs = 1u << 20;
-    std::vector<uint64_t> qstart;   // pair offset of every query (only needed when batching)
-    std::vector<uint32_t> cuts{0, nq};
-    if (total_pairs > budget_pairs) {
-        qstart.resize((size_t)nq + 1);
-        NSMH_CK(cudaMemcpy2DAsync(qstart.data(), sizeof(uint64_t), ws.poff.p, (size_t)n * sizeof(uint64_t),
-                                  sizeof(uint64_t), nq, cudaMemcpyDeviceToHost, s));
-        NSMH_CK(cudaStreamSynchronize(s));
-        qstart[nq] = total_pairs;
-        cuts.assign(1, 0);
-        uint32_t q = 0;
-        while (q < nq) {
-            uint32_t e = q + 1;   // at least one query per batch
-            while (e < nq && qstart[e + 1] - qstart[q] <= budget_pairs) ++e;
-            cuts.push_back(e);
-            q = e;
-        }
-    }
-
-    // pass A: per batch gather + sort + flag (counts per query); results appended to out_ids
-    // in query order because batches are processed in order and sorted by (query, id).
-    // We do not know the output size in advance; select writes at most T entries per batch.
-    // Two-step per batch: flag (gives exact per-query counts), then select into place.
-    uint64_t out_total = 0;
-    for (size_t bi = 0; bi + 1 < cuts.size(); ++bi) {
-        const uint32_t q0 = cuts[bi], q1 = cuts[bi + 1];
-        const uint64_t item0 = (uint64_t)q0 * n, bitems = (uint64_t)(q1 - q0) * n;
-        uint64_t pair0, pair1;
-        if (qstart.empty()) { pair0 = 0; pair1 = total_pairs; }
-        else { pair0 = qstart[q0]; pair1 = qstart[q1]; }
-        const uint64_t Tn = pair1 - pair0;
-        if (Tn == 0) continue;
-        NSMH_TRY(ws.pairs.ensure(Tn * sizeof(uint64_t), s));
-        NSMH_TRY(ws.pairs_alt.ensure(Tn * sizeof(uint64_t), s));
-        NSMH_TRY(ws.flags.ensure(Tn, s));
-        gather_pairs_kernel<<<grid_for(bitems, c->num_sms), 256, 0, s>>>(
-            item0, bitems, n, q0, ws.pbegin.as<uint32_t>(), ws.pcnt.as<uint32_t>(),
-            ws.poff.as<uint64_t>(), pair0, T.ids.as<uint32_t>(), 0u, ws.pairs.as<uint64_t>());
+    NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
+    lookup_kernel<true><<<blocks, kLookupWarps * 32, smem, s>>>(a);
+    ws.launches += 3;
+    NSMH_CK(cudaGetLastError());
+    if (nh) {
+        heavy_copy_kernel<<<grid_for(nh, c->num_sms, 8), 256, 0, s>>>(
+            ws.heavy_list.as<uint32_t>(), nh, ws.hcnt.as<uint32_t>(), ws.hstart.as<uint64_t>(),
+            ws.hout.as<uint32_t>(), ws.out_off.as<uint64_t>(), ws.out_ids.as<uint32_t>());
         ++ws.launches;
         NSMH_CK(cudaGetLastError());
-        int qbits = 1;
-        while ((1ULL << qbits) < (uint64_t)(q1 - q0)) ++qbits;
-        bool in_alt = false;
-        tmp_bytes = 0;
-        NSMH_CK(cub_sort_keys_u64(nullptr, tmp_bytes, ws.pairs.as<uint64_t>(), ws.pairs_alt.as<uint64_t>(),
-                                  Tn, 0, 32 + qbits, in_alt, s));
-        NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
-        NSMH_CK(cub_sort_keys_u64(ws.cub_tmp.p, tmp_bytes, ws.pairs.as<uint64_t>(),
-                                  ws.pairs_alt.as<uint64_t>(), Tn, 0, 32 + qbits, in_alt, s));
-        ws.launches += 2 + (32 + qbits + 7) / 8;   // histogram + onesweep passes (approximate)
-        const uint64_t *sorted = in_alt ? ws.pairs_alt.as<uint64_t>() : ws.pairs.as<uint64_t>();
-        flag_runs_kernel<<<grid_for(Tn, c->num_sms), 256, 0, s>>>(sorted, Tn, c->thr, q0,
-                                                                  ws.flags.as<uint8_t>(),
-                                                                  ws.qcount.as<uint32_t>());
-        ++ws.launches;
-        NSMH_CK(cudaGetLastError());
-        // worst case every pair is selected
-        NSMH_TRY(ws.out_ids.ensure((out_total + Tn) * sizeof(uint32_t), s, out_total * sizeof(uint32_t)));
-        tmp_bytes = 0;
-        NSMH_CK(cub_select_low32_flagged(nullptr, tmp_bytes, sorted, ws.flags.as<uint8_t>(),
-                                         ws.out_ids.as<uint32_t>() + out_total, ws.nsel.as<uint64_t>(), Tn, s));
-        NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
-        NSMH_CK(cub_select_low32_flagged(ws.cub_tmp.p, tmp_bytes, sorted, ws.flags.as<uint8_t>(),
-                                         ws.out_ids.as<uint32_t>() + out_total, ws.nsel.as<uint64_t>(), Tn, s));
-        ws.launches += 2;
-        uint64_t nsel = 0;
-        NSMH_CK(cudaMemcpyAsync(&nsel, ws.nsel.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        NSMH_CK(cudaStreamSynchronize(s));
-        out_total += nsel;
     }
-    tmp_bytes = 0;
-    NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.qcount.as<uint32_t>(),
-                                         ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
-    NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
-    NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.qcount.as<uint32_t>(),
-                                         ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
-    ws.launches += 2;
+    uint64_t total = 0;
+    NSMH_CK(cudaMemcpyAsync(&total, ws.out_off.as<uint64_t>() + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
     NSMH_CK(cudaStreamSynchronize(s));
-    ws.last_total = out_total;
+    ws.last_total = total;
     return NSMH_OK;
 }
 
