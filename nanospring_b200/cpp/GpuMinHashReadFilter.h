@@ -1,0 +1,144 @@
+// GpuMinHashReadFilter — header-only C++ adaptor that makes libnsmh.so a drop-in
+// for the reference's read-overlap filter.
+//
+// It derives from the reference's abstract interface
+//     class ReadFilter { virtual void getFilteredReads(const std::string&, std::vector<read_t>&) = 0;
+//                        virtual void initialize(ReadData&) = 0; }        (include/ReadFilter.h:15-30)
+// and exposes the same public fields as MinHashReadFilter (include/ReadFilter.h:37-42):
+//     k, n, overlapSketchThreshold, tempDir
+// so the two call sites of the reference need no other change:
+//     src/Compressor.cpp:69-76   construct, assign fields, initialize(rD)
+//     src/Consensus.cpp:189      rF->getFilteredReads(string, results)   (inside `omp parallel`)
+//
+// Compile this header inside the reference tree (it includes the reference's own
+// ReadFilter.h / ReadData.h / Types.h) and link with -lnsmh.  Errors of the C ABI
+// become std::runtime_error, which the reference's main() already catches
+// (src/main.cpp:161-176).  No temp files are written; tempDir is kept for parity.
+#ifndef GPU_MINHASH_READ_FILTER_H_
+#define GPU_MINHASH_READ_FILTER_H_
+
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "ReadFilter.h"   // the reference's header: ReadFilter, ReadData, read_t, kMer_t
+#include "nsmh.h"
+
+class GpuMinHashReadFilter : public ReadFilter {
+public:
+    /** [k]-mer **/
+    size_t k = 23;
+    /** size of sketch **/
+    size_t n = 60;
+    size_t overlapSketchThreshold = 6;
+    std::string tempDir;
+    /** CUDA device ordinal **/
+    int device = 0;
+    /** Optional: fix the n random numbers (tests / reproducible runs).  Left empty, they
+     *  are drawn exactly like MinHashReadFilter::generateRandomNumbers (ReadFilter.cpp:49-63). */
+    std::vector<kMer_t> randNumbers;
+
+    GpuMinHashReadFilter() = default;
+    GpuMinHashReadFilter(const GpuMinHashReadFilter &) = delete;
+    GpuMinHashReadFilter &operator=(const GpuMinHashReadFilter &) = delete;
+    ~GpuMinHashReadFilter() override { nsmh_destroy(h_); }
+
+    /** ReadFilter.cpp:11-47: sketch every read of rD and build the n tables, on the GPU. */
+    void initialize(ReadData &rD) override {
+        nsmh_destroy(h_);
+        h_ = nullptr;
+        if (randNumbers.size() != n) generateRandomNumbers(n);
+        check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
+                          device, &h_));
+        const read_t numReads = rD.getNumReads();
+        // Pull the reads once, sequentially (in the CLI's low-memory mode getRead() takes a global
+        // mutex, ReadData.cpp:225-235), into one pinned ASCII buffer + offsets.
+        std::vector<uint64_t> offsets((size_t)numReads + 1, 0);
+        std::string s;
+        size_t cap = (size_t)rD.avgReadLen * numReads + (size_t)rD.maxReadLen + 1024, used = 0;
+        char *bases = nullptr;
+        check(nsmh_host_alloc(cap, reinterpret_cast<void **>(&bases)));
+        try {
+            for (read_t i = 0; i < numReads; ++i) {
+                rD.getRead(i, s);
+                if (used + s.size() > cap) {
+                    size_t ncap = (used + s.size()) * 2;
+                    char *nb = nullptr;
+                    check(nsmh_host_alloc(ncap, reinterpret_cast<void **>(&nb)));
+                    std::copy(bases, bases + used, nb);
+                    nsmh_host_free(bases);
+                    bases = nb;
+                    cap = ncap;
+                }
+                std::copy(s.begin(), s.end(), bases + used);
+                used += s.size();
+                offsets[i + 1] = used;
+            }
+            check(nsmh_load_reads_ascii(h_, bases, offsets.data(), numReads));
+            check(nsmh_sketch(h_));
+            check(nsmh_build(h_));
+        } catch (...) {
+            nsmh_host_free(bases);
+            throw;
+        }
+        nsmh_host_free(bases);
+    }
+
+    /** ReadFilter.cpp:85-97.  Re-entrant; called concurrently by all OpenMP threads. */
+    void getFilteredReads(const std::string &s, std::vector<read_t> &results) override {
+        results.clear();
+        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::getFilteredReads before initialize");
+        results.resize(64);
+        for (;;) {
+            size_t count = 0;
+            int rc = nsmh_query_string(h_, s.data(), s.size(), results.data(), results.size(), &count);
+            if (rc == NSMH_ERANGE) {
+                results.resize(count);
+                continue;
+            }
+            check(rc);
+            results.resize(count);
+            return;
+        }
+    }
+
+    /** A window and its reverse complement in one launch sequence (the pair of calls at
+     *  Consensus.cpp:185-191).  Optional fast path; results as the two single calls give. */
+    void getFilteredReadsPair(const std::string &fwd, const std::string &rev, std::vector<read_t> &resFwd,
+                              std::vector<read_t> &resRev) {
+        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::getFilteredReadsPair before initialize");
+        std::string both = fwd + rev;
+        uint64_t off[3] = {0, fwd.size(), fwd.size() + rev.size()}, out_off[3] = {0, 0, 0};
+        std::vector<read_t> ids(256);
+        for (;;) {
+            int rc = nsmh_query_strings(h_, both.data(), off, 2, out_off, ids.data(), ids.size());
+            if (rc == NSMH_ERANGE) {
+                ids.resize(out_off[2]);
+                continue;
+            }
+            check(rc);
+            break;
+        }
+        resFwd.assign(ids.begin(), ids.begin() + out_off[1]);
+        resRev.assign(ids.begin() + out_off[1], ids.begin() + out_off[2]);
+    }
+
+    /** Generates a sequence of n kMer_t random numbers (ReadFilter.cpp:49-63). */
+    void generateRandomNumbers(size_t count) {
+        std::random_device rd;
+        randNumbers.resize(count);
+        check(nsmh_rand_from_seed(rd(), (uint32_t)count, randNumbers.data()));
+    }
+
+    nsmh_handle handle() const { return h_; }
+
+private:
+    nsmh_handle h_ = nullptr;
+
+    static void check(int rc) {
+        if (rc != NSMH_OK) throw std::runtime_error(std::string("nsmh: ") + nsmh_last_error());
+    }
+};
+
+#endif  // GPU_MINHASH_READ_FILTER_H_

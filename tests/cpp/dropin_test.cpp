@@ -1,0 +1,92 @@
+// Drop-in test of the boundary: the reference's caller pattern
+//     ReadFilter *rF = ...;  rF->initialize(rD);                    (Compressor.cpp:69-76)
+//     #pragma omp parallel ... rF->getFilteredReads(window, results) (Consensus.cpp:29,189)
+// driven through GpuMinHashReadFilter (libnsmh.so, GPU) and, side by side, through the
+// reference's own MinHashReadFilter (oracle/_ref/libnsref.so, CPU) with the same injected
+// random numbers.  Compiled against the reference's headers by `make -C oracle dropin`;
+// run on the GPU box by tests/test_gpu_dropin.py.  Prints "DROPIN OK" on success.
+#include <omp.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <iterator>
+
+#include "GpuMinHashReadFilter.h"
+
+void nsref_fill_read_data(ReadData &rD, const char *bases, const uint64_t *offsets, uint32_t numReads);
+extern "C" {
+void *nsref_create(const char *bases, const uint64_t *offsets, uint32_t numReads, uint32_t k, uint32_t n,
+                   uint32_t thr, const uint64_t *randNumbers, int threads, const char *tmpdir,
+                   double *sketch_ms, double *build_ms);
+size_t nsref_query_string(void *h, const char *s, size_t len, uint32_t *out, size_t cap);
+void nsref_destroy(void *h);
+}
+
+int main(int argc, char **argv) {
+    if (argc < 6) {
+        std::fprintf(stderr, "usage: %s reads.bin k n thr tmpdir\n", argv[0]);
+        return 2;
+    }
+    // reads.bin: u32 numReads, u64 offsets[numReads+1], bases
+    std::ifstream in(argv[1], std::ios::binary);
+    uint32_t numReads = 0;
+    in.read(reinterpret_cast<char *>(&numReads), 4);
+    std::vector<uint64_t> offsets((size_t)numReads + 1);
+    in.read(reinterpret_cast<char *>(offsets.data()), offsets.size() * 8);
+    std::string bases(offsets[numReads], '\0');
+    in.read(&bases[0], bases.size());
+    const size_t k = std::atoi(argv[2]), n = std::atoi(argv[3]), thr = std::atoi(argv[4]);
+
+    ReadData rD;
+    nsref_fill_read_data(rD, bases.data(), offsets.data(), numReads);
+
+    GpuMinHashReadFilter gpu;
+    gpu.k = k;
+    gpu.n = n;
+    gpu.overlapSketchThreshold = thr;
+    gpu.tempDir = argv[5];
+    gpu.randNumbers.resize(n);
+    nsmh_rand_from_seed(20261017u, (uint32_t)n, gpu.randNumbers.data());
+    ReadFilter *rF = &gpu;                 // the caller only ever holds a ReadFilter* (Consensus.h:41)
+    rF->initialize(rD);
+
+    void *ref = nsref_create(bases.data(), offsets.data(), numReads, (uint32_t)k, (uint32_t)n, (uint32_t)thr,
+                             gpu.randNumbers.data(), 0, argv[5], nullptr, nullptr);
+    if (!ref) return 3;
+
+    long mismatches = 0, queries = 0, total = 0;
+#pragma omp parallel reduction(+ : mismatches, queries, total)
+    {
+        std::string s, rc;
+        std::vector<read_t> res, resRc, want((size_t)numReads + 1);
+#pragma omp for schedule(dynamic, 4)
+        for (read_t i = 0; i < numReads; ++i) {
+            rD.getRead(i, s);
+            if (s.size() > 3000) s = s.substr(s.size() / 3, 2500);      // a window, like addRelatedReads
+            rc.clear();
+            ReadData::toReverseComplement(s.begin(), s.end(), std::inserter(rc, rc.end()));
+            rF->getFilteredReads(s, res);
+            rF->getFilteredReads(rc, resRc);
+            size_t c = nsref_query_string(ref, s.data(), s.size(), want.data(), want.size());
+            if (c != res.size() || !std::equal(res.begin(), res.end(), want.begin())) ++mismatches;
+            total += (long)c;
+            c = nsref_query_string(ref, rc.data(), rc.size(), want.data(), want.size());
+            if (c != resRc.size() || !std::equal(resRc.begin(), resRc.end(), want.begin())) ++mismatches;
+            total += (long)c;
+            queries += 2;
+            if (i % 16 == 0) {   // the paired fast path gives the same two answers
+                std::vector<read_t> a, b;
+                gpu.getFilteredReadsPair(s, rc, a, b);
+                if (a != res || b != resRc) ++mismatches;
+            }
+        }
+    }
+    nsref_destroy(ref);
+    std::printf("threads %d queries %ld candidate ids %ld mismatches %ld\n", omp_get_max_threads(), queries,
+                total, mismatches);
+    if (mismatches) return 1;
+    std::printf("DROPIN OK\n");
+    return 0;
+}
