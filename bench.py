@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--sketch-mode", type=int, default=0, help="0 filtered kernel, 1 brute force")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--multi", default="auto", choices=["auto", "replicated", "partitioned"],
+                    help="N>1: all-gather sketches + full tables per rank, or tables partitioned by hash function")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "nsmh" else args.warmup
 
@@ -197,6 +199,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
     n_gpus = world
@@ -223,12 +226,16 @@ def main():
     f.sketchMode = args.sketch_mode
     f._create()
     rows_per_rank = [READS_PER_GPU] * world
+    multi = args.multi if args.multi != "auto" else "partitioned"
+    pf = shard.PartitionedFilter(f, rank, world) if (world > 1 and multi == "partitioned") else None
     ext = torch.cuda.ExternalStream(f.stream(), device=local_rank)
     keep = {}
 
     def device_step():
         f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
         f.sketch()
+        if pf is not None:
+            return pf.run(lengths.size, rows_per_rank)
         if world > 1:
             keep["g"] = shard.gather_and_build(f, lengths.size, rows_per_rank, rank)
         else:
@@ -238,6 +245,8 @@ def main():
     def e2e_step():
         f.load(host_rd)
         f.sketch()
+        if pf is not None:
+            return pf.result(lengths.size, pf.run(lengths.size, rows_per_rank))
         if world > 1:
             keep["g"] = shard.gather_and_build(f, lengths.size, rows_per_rank, rank)
         else:
@@ -290,6 +299,9 @@ def main():
               "build_ms": st["build_ms"], "query_ms": st["query_ms"], "sketch_fixups_total": st["sketch_fixups"],
               "query_pairs": st["query_pairs"], "candidate_ids": int(total_ids)}
 
+    if pf is not None:
+        phases["partitioned_stage_ms"] = {k2: round(v, 3) for k2, v in pf.last_ms.items()}
+
     # ---- e2e: host buffers in, CSR out ----
     for _ in range(0 if args.no_e2e else 2):
         e2e_step()
@@ -334,6 +346,7 @@ def main():
         "config": {"workload": workload_name(n_gpus), "k": K, "num_hash": NHASH, "overlap_sketch_thr": THR,
                    "reads_per_gpu": READS_PER_GPU, "bases_per_gpu": total_bases, "mean_read_len": mean_len,
                    "sketch_mode": "filter" if args.sketch_mode == 0 else "brute",
+                   "multi_gpu": ("n/a" if world == 1 else multi),
                    "l2": "inputs larger than L2 (1 GB ASCII + 0.25 GB packed per step vs 126 MB L2)",
                    "step": "pack + sketch + build tables + bulk forward lookup, CSR left on device"},
         "phases_last_step": phases,

@@ -109,6 +109,18 @@ int nsmh_query_all_result(nsmh_handle h, uint64_t *offsets /* [num_reads+1] host
                           uint32_t *ids /* [total_ids] host */);
 int nsmh_query_all_device_ptrs(nsmh_handle h, uint64_t **d_offsets, uint32_t **d_ids);
 
+/* ---- multi-GPU building blocks (tables partitioned by hash function across ranks) -----
+ * nsmh_probe_lists: probe this handle's n tables for num_queries device-resident sketches
+ * [num_queries][n] and gather the id lists WITHOUT counting: CSR of concatenated lists
+ * (fetch with nsmh_query_all_result / nsmh_query_all_device_ptrs).
+ * nsmh_count_lists: for num_queries queries, `parts` partial lists each (device CSR pieces
+ * d_offsets[p][num_queries+1], d_ids[p], e.g. received from the ranks that own the tables),
+ * emit the ids that occur in at least overlap_sketch_thr lists, ascending (ReadFilter.cpp:73-82).
+ * Result is the bulk CSR, as after nsmh_query_all.  parts <= 16. */
+int nsmh_probe_lists(nsmh_handle h, const uint64_t *d_sketches, uint32_t num_queries, uint64_t *total_ids);
+int nsmh_count_lists(nsmh_handle h, uint32_t num_queries, uint32_t parts, const uint64_t *const *d_offsets,
+                     const uint32_t *const *d_ids, uint64_t *total_ids);
+
 /* ---- online query: ReadFilter::getFilteredReads(const std::string&, std::vector<read_t>&)
  *      (ReadFilter.h:24-25, ReadFilter.cpp:85-97).  Thread-safe, re-entrant. -------------
  * Writes min(count, cap) ids to out and the full count to *count; returns NSMH_ERANGE

@@ -63,6 +63,8 @@ _SIGS = {
     "nsmh_query_all": [C.c_void_p, C.c_int, u64p],
     "nsmh_query_all_result": [C.c_void_p, u64p, u32p],
     "nsmh_query_all_device_ptrs": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)],
+    "nsmh_probe_lists": [C.c_void_p, C.c_void_p, C.c_uint32, u64p],
+    "nsmh_count_lists": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p],
     "nsmh_query_string": [C.c_void_p, C.c_char_p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)],
     "nsmh_query_strings": [C.c_void_p, C.c_void_p, u64p, C.c_uint32, u64p, u32p, C.c_size_t],
     "nsmh_query_sketches": [C.c_void_p, u64p, C.c_uint32, u64p, u32p, C.c_size_t],

@@ -498,6 +498,31 @@ int nsmh_query_all_device_ptrs(nsmh_handle c, uint64_t **d_offsets, uint32_t **d
     return NSMH_OK;
 }
 
+int nsmh_probe_lists(nsmh_handle c, const uint64_t *d_sketches, uint32_t num_queries, uint64_t *total_ids) {
+    CTX_GUARD(c);
+    if (num_queries && !d_sketches) return fail(NSMH_EINVAL, "probe_lists: null sketches");
+    if (!c->tables.built) return fail(NSMH_ESTATE, "probe_lists: call nsmh_build first");
+    c->bulk.stream = c->stream;
+    c->bulk_valid = false;
+    NSMH_TRY(probe_lists_device(c, c->bulk, d_sketches, num_queries, c->stream));
+    c->bulk_valid = true;
+    if (total_ids) *total_ids = c->bulk.last_total;
+    return NSMH_OK;
+}
+
+int nsmh_count_lists(nsmh_handle c, uint32_t num_queries, uint32_t parts, const uint64_t *const *d_offsets,
+                     const uint32_t *const *d_ids, uint64_t *total_ids) {
+    CTX_GUARD(c);
+    if (!d_offsets || !d_ids) return fail(NSMH_EINVAL, "count_lists: null pointer arrays");
+    c->bulk.stream = c->stream;
+    c->bulk_valid = false;
+    NSMH_TRY(count_lists_device(c, c->bulk, num_queries, parts, d_offsets, d_ids, c->stream));
+    c->bulk_valid = true;
+    c->stats.query_pairs = c->bulk.last_pairs;
+    if (total_ids) *total_ids = c->bulk.last_total;
+    return NSMH_OK;
+}
+
 // ------------------------------------------------------------- online query --
 static QueryWs *acquire_ws(nsmh_ctx *c) {
     {

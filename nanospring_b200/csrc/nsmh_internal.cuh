@@ -191,5 +191,8 @@ int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
 // ---- query.cu ----------------------------------------------------------------
 int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq,
                           cudaStream_t s);
+int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s);
+int count_lists_device(nsmh_ctx *c, QueryWs &ws, uint32_t nq, uint32_t parts, const uint64_t *const *d_offsets,
+                       const uint32_t *const *d_ids, cudaStream_t s);
 
 } // namespace nsmh

@@ -46,7 +46,16 @@ def main():
     off, ids = f.queryAll(False)
     pieces = [None] * world
     dist.all_gather_object(pieces, (np.diff(off.astype(np.int64)), ids))
-    ok = True
+    # second strategy: tables partitioned by hash function (two all-to-alls, no replicated build)
+    pf = shard.PartitionedFilter(f, rank, world)
+    ptotal = pf.run(hi - lo, rows)
+    poff, pids = pf.result(hi - lo, ptotal)
+    same = bool((poff == off).all() and pids.size == ids.size and (pids == ids).all())
+    flags = [None] * world
+    dist.all_gather_object(flags, same)
+    ok = all(flags)
+    if rank == 0:
+        print(f"partitioned tables == replicated tables on every rank: {ok}", flush=True)
     if rank == 0:
         counts = np.concatenate([p[0] for p in pieces])
         all_ids = np.concatenate([p[1] for p in pieces])
