@@ -50,7 +50,7 @@ void DevBuf::release(cudaStream_t s) {
 
 static void free_ws(QueryWs &ws, cudaStream_t s) {
     DevBuf *bufs[] = {&ws.qsketch, &ws.pval, &ws.pcnt, &ws.heavy_list, &ws.counters, &ws.hc, &ws.hoff, &ws.hout, &ws.hcnt, &ws.hstart, &ws.pairs, &ws.pairs_alt, &ws.flags,
-                      &ws.qcount, &ws.out_off, &ws.out_ids, &ws.nsel, &ws.cub_tmp, &ws.str_bases,
+                      &ws.qcount, &ws.qpos, &ws.tmp_ids, &ws.out_off, &ws.out_ids, &ws.nsel, &ws.cub_tmp, &ws.str_bases,
                       &ws.tile_start};
     for (DevBuf *b : bufs) b->release(s);
     ws.str_reads.release(s);
@@ -217,7 +217,7 @@ int nsmh_destroy(nsmh_handle h) {
         cudaStream_t s = h->stream;
         free_ws(h->bulk, s);
         DevBuf *bufs[] = {&h->d_rand, &h->d_ftab_hit, &h->d_ftab_first, &h->d_ftab_next, &h->sketches,
-                          &h->tile_start, &h->counters, &h->item_slot, &h->item_rank, &h->build_tmp,
+                          &h->tile_start, &h->counters, &h->build_multi, &h->build_tmp,
                           &h->tables.slots, &h->tables.ids};
         for (DevBuf *b : bufs) b->release(s);
         if (h->reads.external_offsets) { h->reads.offsets.p = nullptr; h->reads.offsets.cap = 0; }

@@ -73,12 +73,17 @@ struct __align__(16) Slot {
     uint32_t cntm1;
 };
 
+// home slot of a key in a region of `cap` slots (cap < 2^32, any value)
+__host__ __device__ __forceinline__ uint64_t slot_index(uint64_t key, uint64_t cap) {
+    const uint64_t h = (key * 0x9E3779B97F4A7C15ULL) >> 32;
+    return (h * cap) >> 32;
+}
+
 // Hash tables: one open-addressing region of (cap+1) slots per hash function.
 struct Tables {
     bool built = false;
     uint32_t table_reads = 0;   // rows of the sketch matrix the tables were built from
-    uint32_t log2cap = 0;
-    uint64_t cap = 0;           // slots per region (power of two); slot `cap` holds key ~0
+    uint64_t cap = 0;           // slots per region (2 * rows); slot `cap` holds key ~0
     DevBuf slots;               // Slot [n*(cap+1)]
     DevBuf ids;                 // u32 read ids of the groups with two or more members
 };
@@ -99,6 +104,8 @@ struct QueryWs {
     DevBuf pairs, pairs_alt;   // u64 [T]
     DevBuf flags;       // u8 [T]
     DevBuf qcount;      // u32 [nq+1]
+    DevBuf qpos;        // u64 [nq]    start of the query's results in tmp_ids
+    DevBuf tmp_ids;     // u32         results in completion order (before the CSR placement)
     DevBuf out_off;     // u64 [nq+1]
     DevBuf out_ids;     // u32 [total]
     DevBuf nsel;        // u64 [2]
@@ -144,7 +151,7 @@ struct nsmh_ctx {
     const uint64_t *table_sketches = nullptr;   // rows the tables are built from
     uint32_t table_reads = 0, id_base = 0;
     nsmh::Tables tables;
-    nsmh::DevBuf item_slot, item_rank;   // build scratch, u32 [table_reads*n]
+    nsmh::DevBuf build_multi;   // build scratch: members / groups of keys shared by several reads
     nsmh::DevBuf build_tmp;
 
     nsmh::QueryWs bulk;         // nsmh_query_all workspace (uses ctx stream)

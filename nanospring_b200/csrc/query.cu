@@ -25,33 +25,13 @@
 
 namespace nsmh {
 
-constexpr int kLookupCap = 2048;     // ids per warp-private buffer
+constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer
+constexpr int kHashSlots = 512;      // counting table of the common path: 512 keys + 512 counters (same buffer)
+constexpr int kHashMaxIds = 256;     // ... for up to this many gathered ids (load factor <= 0.5)
+constexpr int kWarpWords = kLookupCap + kHashMaxIds + 32;   // + result list + a few scalars
 constexpr int kLookupWarps = 8;
 constexpr int kMaxParts = 16;        // PartsSrc: at most this many partial lists per query
-
-__device__ __forceinline__ uint64_t slot_hash_q(uint64_t key, uint32_t log2cap) {
-    return (key * 0x9E3779B97F4A7C15ULL) >> (64 - log2cap);
-}
-
-// exact probe of table l: group size (0 = absent) and val (the id itself for a
-// group of one, else the start of the group in ids)
-__device__ __forceinline__ uint32_t probe_slot(const Slot *__restrict__ slots, uint64_t cap,
-                                               uint32_t log2cap, uint32_t l, uint64_t key, uint32_t &val) {
-    const Slot *region = slots + (uint64_t)l * (cap + 1);
-    if (key == kEmptyKey) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(region + cap));
-        val = v.z;
-        return v.w + 1u;          // untouched slot: 0xFFFFFFFF + 1 = 0
-    }
-    uint64_t h = slot_hash_q(key, log2cap);
-    for (;;) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(region + h));
-        const uint64_t kk = ((uint64_t)v.y << 32) | v.x;
-        if (kk == key) { val = v.z; return v.w + 1u; }
-        if (kk == kEmptyKey) { val = 0; return 0; }
-        h = (h + 1) & (cap - 1);
-    }
-}
+constexpr uint32_t kNoId = 0xFFFFFFFFu;   // read ids are < 2^32-1 (ReadData.cpp:122-124)
 
 // one id list: c ids at ptr, or (ptr == nullptr, c == 1) the single id `one`
 struct ListRef {
@@ -59,30 +39,63 @@ struct ListRef {
     uint32_t c, one;
 };
 
+// Probing is split in two so that the (random, DRAM-latency) slot loads of several lists are
+// in flight together: begin() issues the first slot load, finish() resolves the probe.
 struct ProbeSrc {
     const uint64_t *qsk;     // [nq][n]
     const Slot *slots;
     const uint32_t *ids;
-    uint32_t *pval, *pcnt;   // [nq][n] probe results (the id / start in ids, group size)
+    uint32_t *pval, *pcnt;   // [nq][n] stored probe results (nsmh_probe_lists only)
     uint64_t cap;
-    uint32_t log2cap, n;
+    uint32_t n;
+    struct Pending {
+        uint64_t key, h;
+        uint4 v;
+        uint32_t j;
+    };
     __device__ __forceinline__ uint32_t subs() const { return n; }
-    template <bool FIRST>
-    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const {
-        const size_t t = (size_t)q * n + j;
-        uint32_t val, c;
-        if (FIRST) {
-            c = probe_slot(slots, cap, log2cap, j, qsk[t], val);
-            pval[t] = val;
-            pcnt[t] = c;
+    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
+        Pending p;
+        p.j = j;
+        p.key = __ldg(qsk + (size_t)q * n + j);
+        p.h = p.key == kEmptyKey ? cap : slot_index(p.key, cap);   // key ~0 lives in the extra slot
+        p.v = __ldg(reinterpret_cast<const uint4 *>(slots + (uint64_t)j * (cap + 1) + p.h));
+        return p;
+    }
+    // group size (0 = absent) and val (the id itself for a group of one, else the start in ids)
+    __device__ __forceinline__ ListRef finish(Pending p) const {
+        const Slot *region = slots + (uint64_t)p.j * (cap + 1);
+        uint32_t c, val;
+        if (p.key == kEmptyKey) {
+            val = p.v.z;
+            c = p.v.w + 1u;          // untouched slot: 0xFFFFFFFF + 1 = 0
         } else {
-            c = pcnt[t];
-            val = pval[t];
+            for (;;) {
+                const uint64_t kk = ((uint64_t)p.v.y << 32) | p.v.x;
+                if (kk == p.key) { val = p.v.z; c = p.v.w + 1u; break; }
+                if (kk == kEmptyKey) { val = 0; c = 0; break; }
+                p.h = p.h + 1 == cap ? 0 : p.h + 1;
+                p.v = __ldg(reinterpret_cast<const uint4 *>(region + p.h));
+            }
         }
         ListRef r;
         r.c = c;
         r.one = val;
         r.ptr = c == 1 ? nullptr : ids + val;
+        return r;
+    }
+    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
+    __device__ __forceinline__ ListRef get_store(uint32_t q, uint32_t j) const {
+        const ListRef r = get(q, j);
+        pval[(size_t)q * n + j] = r.one;
+        pcnt[(size_t)q * n + j] = r.c;
+        return r;
+    }
+    __device__ __forceinline__ ListRef get_stored(uint32_t q, uint32_t j) const {
+        ListRef r;
+        r.c = pcnt[(size_t)q * n + j];
+        r.one = pval[(size_t)q * n + j];
+        r.ptr = r.c == 1 ? nullptr : ids + r.one;
         return r;
     }
 };
@@ -91,118 +104,261 @@ struct PartsSrc {
     const uint64_t *offs[kMaxParts];   // each [nq+1]
     const uint32_t *ids[kMaxParts];
     uint32_t parts;
+    struct Pending {
+        uint64_t o0, o1;
+        uint32_t j;
+    };
     __device__ __forceinline__ uint32_t subs() const { return parts; }
-    template <bool FIRST>
-    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const {
-        const uint64_t o0 = offs[j][q], o1 = offs[j][q + 1];
+    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
+        Pending p;
+        p.j = j;
+        p.o0 = offs[j][q];
+        p.o1 = offs[j][q + 1];
+        return p;
+    }
+    __device__ __forceinline__ ListRef finish(Pending p) const {
         ListRef r;
-        r.ptr = ids[j] + o0;
-        r.c = (uint32_t)(o1 - o0);
+        r.ptr = ids[p.j] + p.o0;
+        r.c = (uint32_t)(p.o1 - p.o0);
         r.one = 0;
         return r;
     }
+    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
 };
 
 struct CountArgs {
-    uint32_t *qcount;        // [nq+1]
-    const uint64_t *out_off; // [nq+1]   (EMIT)
-    uint32_t *out_ids;       //          (EMIT)
+    uint32_t *qcount;        // [nq+1] result ids per query
+    uint64_t *qpos;          // [nq]   where the query's results start in tmp_ids (~0: heavy query)
+    uint32_t *tmp_ids;       // results in completion order
+    uint64_t tmp_cap;
     uint32_t *heavy_list;    // [nq]
-    unsigned long long *counters;   // [0] number of heavy queries, [1] total gathered ids
+    unsigned long long *counters;   // [0] heavy queries, [1] gathered ids, [2] result ids (tmp cursor)
     uint32_t nq, thr;
 };
 
-template <typename Src, bool EMIT>
+__device__ __forceinline__ ListRef empty_list() {
+    ListRef r;
+    r.ptr = nullptr;
+    r.c = 0;
+    r.one = 0;
+    return r;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// counting table: one more occurrence of `id`; the lane that brings the count to `thr` emits it
+__device__ __forceinline__ void count_id(uint32_t *keys, uint32_t *cnts, uint32_t *res, uint32_t *rcount,
+                                         uint32_t id, uint32_t thr) {
+    uint32_t h = (id * 0x9E3779B1u) >> 23;      // 9 bits = kHashSlots
+    for (;;) {
+        const uint32_t prev = atomicCAS(keys + h, kNoId, id);
+        if (prev == kNoId || prev == id) break;
+        h = (h + 1) & (kHashSlots - 1);
+    }
+    if (atomicAdd(cnts + h, 1u) + 1u == thr) res[atomicAdd(rcount, 1u)] = id;
+}
+
+// ascending bitonic sort of buf[0..P), P a power of two >= 32, by one warp
+__device__ __forceinline__ void warp_bitonic_smem(uint32_t *buf, uint32_t P, int lane) {
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P / 2; i += 32) {
+                const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const uint32_t hi = lo | j;
+                const uint32_t x = buf[lo], y = buf[hi];
+                const bool asc = (lo & kk) == 0;
+                if ((x > y) == asc) { buf[lo] = y; buf[hi] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// One warp per query, ONE pass.  Common case (<= kHashMaxIds gathered ids): the ids are counted
+// in a warp-private shared-memory hash table as they arrive and an id is emitted the moment its
+// count reaches the threshold; the handful of results is sorted with warp shuffles.  Larger
+// queries (<= kLookupCap ids) are laid out, sorted with a bitonic network and run-length
+// thresholded.  Results go to tmp_ids in completion order; a prefix sum over qcount and
+// csr_place_kernel then produce the CSR.  Queries beyond kLookupCap take the global path.
+template <typename Src>
 __global__ void __launch_bounds__(kLookupWarps * 32)
 count_kernel(Src src, CountArgs a) {
-    extern __shared__ uint32_t s_buf[];
+    extern __shared__ __align__(16) uint32_t s_buf[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *buf = s_buf + (size_t)warp * kLookupCap;
+    uint32_t *buf = s_buf + (size_t)warp * kWarpWords;
+    uint32_t *keys = buf, *cnts = buf + kHashSlots;
+    uint32_t *res = buf + kLookupCap;           // kHashMaxIds entries
+    uint32_t *rcount = res + kHashMaxIds;
     const uint32_t total_warps = gridDim.x * kLookupWarps;
     const uint32_t subs = src.subs();
     unsigned long long pairs_local = 0;
 
     for (uint32_t q = blockIdx.x * kLookupWarps + warp; q < a.nq; q += total_warps) {
-        // ---- fetch the lists, lay them out in the buffer ----
-        uint32_t T = 0;
-        for (uint32_t j0 = 0; j0 < subs; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            ListRef r;
-            r.ptr = nullptr;
-            r.c = 0;
-            r.one = 0;
-            if (j < subs) r = src.template get<!EMIT>(q, j);
-            uint32_t incl = r.c;
+        // ---- common path: count while gathering ----
+        {
+            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
+            uint4 *c4 = reinterpret_cast<uint4 *>(cnts);
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+            for (int i = 0; i < kHashSlots / 4 / 32; ++i) {
+                k4[i * 32 + lane] = make_uint4(kNoId, kNoId, kNoId, kNoId);
+                c4[i * 32 + lane] = make_uint4(0, 0, 0, 0);
             }
-            const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t off = T + incl - r.c;
-            if ((uint64_t)T + round_total <= kLookupCap) {
-                if (r.c == 1) buf[off] = r.ptr ? r.ptr[0] : r.one;
-                else if (r.c > 1 && r.c <= 8)
-                    for (uint32_t i = 0; i < r.c; ++i) buf[off + i] = r.ptr[i];
-                uint32_t big = __ballot_sync(0xffffffffu, r.c > 8);
+            if (lane == 0) *rcount = 0;
+        }
+        __syncwarp();
+        uint32_t T = 0;
+        bool small = true;
+        for (uint32_t j0 = 0; j0 < subs && small; j0 += 64) {
+            const uint32_t ja = j0 + lane, jb = j0 + 32 + lane;
+            typename Src::Pending pa, pb;
+            if (ja < subs) pa = src.begin(q, ja);
+            if (jb < subs) pb = src.begin(q, jb);
+            ListRef r[2];
+            r[0] = ja < subs ? src.finish(pa) : empty_list();
+            r[1] = jb < subs ? src.finish(pb) : empty_list();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t rt = r[h].c;
+#pragma unroll
+                for (int o = 16; o; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);
+                T = (uint64_t)T + rt > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + rt;
+                if (T > kHashMaxIds) { small = false; break; }
+                if (r[h].c == 1) count_id(keys, cnts, res, rcount, r[h].ptr ? r[h].ptr[0] : r[h].one, a.thr);
+                else if (r[h].c > 1 && r[h].c <= 8)
+                    for (uint32_t i = 0; i < r[h].c; ++i) count_id(keys, cnts, res, rcount, r[h].ptr[i], a.thr);
+                uint32_t big = __ballot_sync(0xffffffffu, r[h].c > 8);
                 while (big) {
-                    const int s = __ffs(big) - 1;
+                    const int sl = __ffs(big) - 1;
                     big &= big - 1;
                     const uint32_t *bp = reinterpret_cast<const uint32_t *>(
-                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r.ptr), s));
-                    const uint32_t bc = __shfl_sync(0xffffffffu, r.c, s);
-                    const uint32_t bo = __shfl_sync(0xffffffffu, off, s);
-                    for (uint32_t i = lane; i < bc; i += 32) buf[bo + i] = bp[i];
+                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r[h].ptr), sl));
+                    const uint32_t bc = __shfl_sync(0xffffffffu, r[h].c, sl);
+                    for (uint32_t i = lane; i < bc; i += 32) count_id(keys, cnts, res, rcount, bp[i], a.thr);
                 }
             }
-            // saturate: the sum of the list sizes can exceed 32 bits only in theory
-            T = (uint64_t)T + round_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + round_total;
         }
-        if (!EMIT) pairs_local += lane == 0 ? T : 0;
-        if (T > kLookupCap) {                     // global path handles this query
-            if (!EMIT && lane == 0) {
-                a.qcount[q] = 0;
-                a.heavy_list[atomicAdd(a.counters, 1ULL)] = q;
-            }
-            continue;
-        }
-        // ---- sort (bitonic network over the padded buffer) ----
-        uint32_t P = 32;
-        while (P < T) P <<= 1;
-        for (uint32_t i = T + lane; i < P; i += 32) buf[i] = 0xFFFFFFFFu;
         __syncwarp();
-        for (uint32_t kk = 2; kk <= P; kk <<= 1) {
-            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-                for (uint32_t i = lane; i < P / 2; i += 32) {
-                    const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                    const uint32_t hi = lo | j;
-                    const uint32_t x = buf[lo], y = buf[hi];
-                    const bool asc = (lo & kk) == 0;
-                    if ((x > y) == asc) { buf[lo] = y; buf[hi] = x; }
+        uint32_t R = 0;
+        const uint32_t *out = res;
+        if (small) {
+            R = *rcount;
+            if (R > 1 && R <= 32) {
+                // shuffle bitonic sort of up to 32 results
+                uint32_t v = lane < (int)R ? res[lane] : kNoId;
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
+                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                        v = (lower == up) ? min(v, o) : max(v, o);
+                    }
                 }
                 __syncwarp();
+                if (lane < (int)R) res[lane] = v;
+                __syncwarp();
+            } else if (R > 32) {
+                uint32_t P = 64;
+                while (P < R) P <<= 1;
+                for (uint32_t i = R + lane; i < P; i += 32) res[i] = kNoId;
+                __syncwarp();
+                warp_bitonic_smem(res, P, lane);
             }
-        }
-        // ---- run lengths against the threshold (ReadFilter.cpp:76-82) ----
-        uint32_t emitted = 0;
-        const uint64_t out0 = EMIT ? a.out_off[q] : 0;
-        for (uint32_t i0 = 0; i0 < T; i0 += 32) {
-            const uint32_t i = i0 + lane;
-            bool ok = false;
-            uint32_t v = 0;
-            if (i < T) {
-                v = buf[i];
-                const bool head = i == 0 || buf[i - 1] != v;
-                ok = head && (a.thr <= 1 || (i + a.thr - 1 < T && buf[i + a.thr - 1] == v));
+        } else {
+            // ---- sort path: lay the lists out in the buffer (the counting table is abandoned) ----
+            T = 0;
+            for (uint32_t j0 = 0; j0 < subs; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                const ListRef r = j < subs ? src.get(q, j) : empty_list();
+                const uint32_t incl = warp_incl_scan(r.c, lane);
+                const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
+                const uint32_t off = T + incl - r.c;
+                if ((uint64_t)T + round_total <= kLookupCap) {
+                    if (r.c == 1) buf[off] = r.ptr ? r.ptr[0] : r.one;
+                    else if (r.c > 1 && r.c <= 8)
+                        for (uint32_t i = 0; i < r.c; ++i) buf[off + i] = r.ptr[i];
+                    uint32_t big = __ballot_sync(0xffffffffu, r.c > 8);
+                    while (big) {
+                        const int sl = __ffs(big) - 1;
+                        big &= big - 1;
+                        const uint32_t *bp = reinterpret_cast<const uint32_t *>(
+                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r.ptr), sl));
+                        const uint32_t bc = __shfl_sync(0xffffffffu, r.c, sl);
+                        const uint32_t bo = __shfl_sync(0xffffffffu, off, sl);
+                        for (uint32_t i = lane; i < bc; i += 32) buf[bo + i] = bp[i];
+                    }
+                }
+                // saturate: the sum of the list sizes can exceed 32 bits only in theory
+                T = (uint64_t)T + round_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + round_total;
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, ok);
-            if (EMIT && ok) a.out_ids[out0 + emitted + __popc(m & ((1u << lane) - 1))] = v;
-            emitted += __popc(m);
+            if (T > kLookupCap) {                     // global path handles this query
+                pairs_local += lane == 0 ? T : 0;
+                if (lane == 0) {
+                    a.qcount[q] = 0;
+                    a.qpos[q] = ~0ULL;
+                    a.heavy_list[atomicAdd(a.counters, 1ULL)] = q;
+                }
+                __syncwarp();
+                continue;
+            }
+            uint32_t P = 32;
+            while (P < T) P <<= 1;
+            for (uint32_t i = T + lane; i < P; i += 32) buf[i] = kNoId;
+            __syncwarp();
+            warp_bitonic_smem(buf, P, lane);
+            // run lengths against the threshold (ReadFilter.cpp:76-82), compacted in place
+            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                bool ok = false;
+                uint32_t v = 0;
+                if (i < T) {
+                    v = buf[i];
+                    const bool head = i == 0 || buf[i - 1] != v;
+                    ok = head && (a.thr <= 1 || (i + a.thr - 1 < T && buf[i + a.thr - 1] == v));
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                __syncwarp();       // every read of this round happens before its writes (R <= i0)
+                if (ok) buf[R + __popc(m & ((1u << lane) - 1))] = v;
+                R += __popc(m);
+                __syncwarp();
+            }
+            out = buf;
         }
-        if (!EMIT && lane == 0) a.qcount[q] = emitted;
+        pairs_local += lane == 0 ? T : 0;
+        // ---- hand the results over ----
+        unsigned long long base = 0;
+        if (lane == 0) {
+            if (R) base = atomicAdd(a.counters + 2, (unsigned long long)R);
+            a.qcount[q] = R;
+            a.qpos[q] = base;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + R <= a.tmp_cap)
+            for (uint32_t i = lane; i < R; i += 32) a.tmp_ids[base + i] = out[i];
         __syncwarp();
     }
-    if (!EMIT && lane == 0 && pairs_local) atomicAdd(a.counters + 1, pairs_local);
+    if (lane == 0 && pairs_local) atomicAdd(a.counters + 1, pairs_local);
+}
+
+// tmp_ids (completion order) -> CSR (query order); 8 lanes per query
+__global__ void __launch_bounds__(256)
+csr_place_kernel(CountArgs a, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids) {
+    const uint32_t sub = threadIdx.x & 7;
+    const uint32_t groups = gridDim.x * (blockDim.x >> 3);
+    for (uint32_t q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); q < a.nq; q += groups) {
+        const uint64_t pos = a.qpos[q];
+        if (pos == ~0ULL) continue;          // heavy query: heavy_copy_kernel places it
+        const uint32_t cnt = a.qcount[q];
+        uint32_t *dst = out_ids + out_off[q];
+        for (uint32_t i = sub; i < cnt; i += 8) dst[i] = a.tmp_ids[pos + i];
+    }
 }
 
 // ---------------------------------------------------------------- global path --
@@ -212,7 +368,7 @@ heavy_counts_kernel(Src src, const uint32_t *__restrict__ heavy_list, uint64_t i
     const uint32_t subs = src.subs();
     for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < items;
          t += (uint64_t)gridDim.x * blockDim.x)
-        hc[t] = src.template get<false>(heavy_list[t / subs], (uint32_t)(t % subs)).c;
+        hc[t] = src.get(heavy_list[t / subs], (uint32_t)(t % subs)).c;
 }
 
 // one warp per (heavy query, list): copy the ids as (local heavy index << 32 | id)
@@ -226,7 +382,7 @@ heavy_gather_kernel(Src src, const uint32_t *__restrict__ heavy_list, uint64_t i
     for (uint64_t t = item0 + blockIdx.x * (uint64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
          t < item0 + items; t += warps) {
         const uint64_t h = t / subs;
-        const ListRef r = src.template get<false>(heavy_list[h], (uint32_t)(t % subs));
+        const ListRef r = src.get(heavy_list[h], (uint32_t)(t % subs));
         uint64_t *dst = pairs + (hoff[t] - pair0);
         const uint64_t tag = (h - h0) << 32;
         if (!r.ptr) { if (lane == 0 && r.c) dst[0] = tag | r.one; }
@@ -359,7 +515,7 @@ static int heavy_path(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t subs, u
     return NSMH_OK;
 }
 
-// count pass, prefix sum, emit pass for nq queries whose lists come from `src`.
+// one counting pass, prefix sum, placement for nq queries whose lists come from `src`.
 // Result CSR in ws.out_off (u64 [nq+1]) / ws.out_ids (u32 [ws.last_total]).  Synchronises `s`.
 template <typename Src>
 static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t subs, uint32_t nq, cudaStream_t s) {
@@ -373,41 +529,58 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
         return NSMH_OK;
     }
     NSMH_TRY(ws.qcount.ensure(((size_t)nq + 1) * sizeof(uint32_t), s));
+    NSMH_TRY(ws.qpos.ensure((size_t)nq * sizeof(uint64_t), s));
     NSMH_TRY(ws.heavy_list.ensure((size_t)nq * sizeof(uint32_t), s));
     NSMH_TRY(ws.counters.ensure(4 * sizeof(uint64_t), s));
-    NSMH_CK(cudaMemsetAsync(ws.counters.p, 0, 4 * sizeof(uint64_t), s));
-    NSMH_CK(cudaMemsetAsync(ws.qcount.as<uint32_t>() + nq, 0, sizeof(uint32_t), s));
+    // results land in tmp_ids in completion order; its size is a guess that the kernel checks
+    // (the cursor keeps counting past the end), so at most one repeat with the exact size
+    if (ws.tmp_ids.cap < (size_t)nq * 16 * sizeof(uint32_t))
+        NSMH_TRY(ws.tmp_ids.ensure((size_t)nq * 16 * sizeof(uint32_t), s));
 
-    const size_t smem = (size_t)kLookupWarps * kLookupCap * sizeof(uint32_t);
-    NSMH_CK(cudaFuncSetAttribute(count_kernel<Src, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NSMH_CK(cudaFuncSetAttribute(count_kernel<Src, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = (size_t)kLookupWarps * kWarpWords * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        NSMH_CK(cudaFuncSetAttribute(count_kernel<ProbeSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSMH_CK(cudaFuncSetAttribute(count_kernel<PartsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
     CountArgs a;
     a.qcount = ws.qcount.as<uint32_t>();
-    a.out_off = ws.out_off.as<uint64_t>();
-    a.out_ids = nullptr;
+    a.qpos = ws.qpos.as<uint64_t>();
     a.heavy_list = ws.heavy_list.as<uint32_t>();
     a.counters = ws.counters.as<unsigned long long>();
     a.nq = nq;
-    a.thr = c->thr;
-    int blocks = (int)std::min<uint64_t>(((uint64_t)nq + kLookupWarps - 1) / kLookupWarps, (uint64_t)c->num_sms * 3);
-    count_kernel<Src, false><<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
-    ++ws.launches;
-    NSMH_CK(cudaGetLastError());
-    unsigned long long cnt[2] = {0, 0};
-    NSMH_CK(cudaMemcpyAsync(cnt, ws.counters.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
-    NSMH_CK(cudaStreamSynchronize(s));
+    a.thr = c->thr ? c->thr : 1;    // thr 0 and 1 both emit every gathered id once (ReadFilter.cpp:76-82)
+    int occ = 0;
+    NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_kernel<Src>, kLookupWarps * 32, smem));
+    const int blocks = (int)std::min<uint64_t>(((uint64_t)nq + kLookupWarps - 1) / kLookupWarps,
+                                               (uint64_t)c->num_sms * (occ > 0 ? occ : 1));
+    unsigned long long cnt[3] = {0, 0, 0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        a.tmp_ids = ws.tmp_ids.as<uint32_t>();
+        a.tmp_cap = ws.tmp_ids.cap / sizeof(uint32_t);
+        NSMH_CK(cudaMemsetAsync(ws.counters.p, 0, 4 * sizeof(uint64_t), s));
+        NSMH_CK(cudaMemsetAsync(ws.qcount.as<uint32_t>() + nq, 0, sizeof(uint32_t), s));
+        count_kernel<Src><<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
+        ++ws.launches;
+        NSMH_CK(cudaGetLastError());
+        NSMH_CK(cudaMemcpyAsync(cnt, ws.counters.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
+        NSMH_CK(cudaStreamSynchronize(s));
+        if (cnt[2] <= a.tmp_cap) break;
+        NSMH_TRY(ws.tmp_ids.ensure((size_t)cnt[2] * sizeof(uint32_t), s));
+    }
     const uint32_t nh = (uint32_t)cnt[0];
     ws.last_pairs = cnt[1];
     // a result id needs at least one gathered id, so their number bounds the output size
     NSMH_TRY(ws.out_ids.ensure((size_t)std::max<uint64_t>(cnt[1], 1) * sizeof(uint32_t), s));
-    a.out_ids = ws.out_ids.as<uint32_t>();
     if (nh) NSMH_TRY(heavy_path(c, ws, src, subs, nh, s));
 
     size_t tmp_bytes = 0;
     NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
     NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
     NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
-    count_kernel<Src, true><<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
+    csr_place_kernel<<<grid_for((uint64_t)nq * 8, c->num_sms), 256, 0, s>>>(a, ws.out_off.as<uint64_t>(),
+                                                                          ws.out_ids.as<uint32_t>());
     ws.launches += 3;
     NSMH_CK(cudaGetLastError());
     if (nh) {
@@ -428,16 +601,12 @@ static int make_probe_src(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, u
                           ProbeSrc &src) {
     Tables &T = c->tables;
     if (!T.built) return fail(NSMH_ESTATE, "query: tables not built (call nsmh_build)");
-    const uint64_t items = std::max<uint64_t>((uint64_t)nq * c->n, 1);
-    NSMH_TRY(ws.pval.ensure(items * sizeof(uint32_t), s));
-    NSMH_TRY(ws.pcnt.ensure(items * sizeof(uint32_t), s));
     src.qsk = d_qsketch;
     src.slots = T.slots.as<Slot>();
     src.ids = T.ids.as<uint32_t>();
-    src.pval = ws.pval.as<uint32_t>();
-    src.pcnt = ws.pcnt.as<uint32_t>();
+    src.pval = nullptr;     // only nsmh_probe_lists stores probe results
+    src.pcnt = nullptr;
     src.cap = T.cap;
-    src.log2cap = T.log2cap;
     src.n = c->n;
     return NSMH_OK;
 }
@@ -471,7 +640,7 @@ probe_totals_kernel(ProbeSrc src, uint32_t nq, uint32_t *__restrict__ qcount) {
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += warps) {
         uint32_t tot = 0;
-        for (uint32_t j = lane; j < src.n; j += 32) tot += src.get<true>(q, j).c;
+        for (uint32_t j = lane; j < src.n; j += 32) tot += src.get_store(q, j).c;
 #pragma unroll
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) qcount[q] = tot;
@@ -490,7 +659,7 @@ probe_write_kernel(ProbeSrc src, uint32_t nq, const uint64_t *__restrict__ out_o
             r.ptr = nullptr;
             r.c = 0;
             r.one = 0;
-            if (j < src.n) r = src.get<false>(q, j);
+            if (j < src.n) r = src.get_stored(q, j);
             uint32_t incl = r.c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -508,6 +677,11 @@ probe_write_kernel(ProbeSrc src, uint32_t nq, const uint64_t *__restrict__ out_o
 int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s) {
     ProbeSrc src;
     NSMH_TRY(make_probe_src(c, ws, d_qsketch, nq, s, src));
+    const uint64_t items = std::max<uint64_t>((uint64_t)nq * c->n, 1);
+    NSMH_TRY(ws.pval.ensure(items * sizeof(uint32_t), s));
+    NSMH_TRY(ws.pcnt.ensure(items * sizeof(uint32_t), s));
+    src.pval = ws.pval.as<uint32_t>();
+    src.pcnt = ws.pcnt.as<uint32_t>();
     ws.last_nq = nq;
     ws.last_total = 0;
     NSMH_TRY(ws.out_off.ensure(((size_t)nq + 1) * sizeof(uint64_t), s));
