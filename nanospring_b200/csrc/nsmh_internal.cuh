@@ -73,11 +73,14 @@ struct __align__(16) Slot {
     uint32_t cntm1;
 };
 
-// home slot of a key in a region of `cap` slots (cap < 2^32, any value)
+// home slot / bucket of a key among `cap` of them (cap < 2^32, any value)
 __host__ __device__ __forceinline__ uint64_t slot_index(uint64_t key, uint64_t cap) {
     const uint64_t h = (key * 0x9E3779B97F4A7C15ULL) >> 32;
     return (h * cap) >> 32;
 }
+
+// slots per table region: cap (even) + the slot of key ~0, padded so every region starts on a sector
+__host__ __device__ __forceinline__ uint64_t region_stride(uint64_t cap) { return cap + 2; }
 
 // Hash tables: one open-addressing region of (cap+1) slots per hash function.
 struct Tables {

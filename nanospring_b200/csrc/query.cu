@@ -39,65 +39,104 @@ struct ListRef {
     uint32_t c, one;
 };
 
-// Probing is split in two so that the (random, DRAM-latency) slot loads of several lists are
-// in flight together: begin() issues the first slot load, finish() resolves the probe.
+// The n tables, probed for a batch of query sketches.  probe_items_kernel resolves every
+// (query, hash) item and stores {val, group size}; everything downstream reads those.
 struct ProbeSrc {
     const uint64_t *qsk;     // [nq][n]
     const Slot *slots;
     const uint32_t *ids;
-    uint32_t *pval, *pcnt;   // [nq][n] stored probe results (nsmh_probe_lists only)
+    uint32_t *pval, *pcnt;   // [nq][n] probe results: the id / the start in ids, the group size
     uint64_t cap;
     uint32_t n;
+};
+
+__device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
+constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
+constexpr int kProbeRows = 256;    // queries per block = threads per block
+
+// One thread per (query, 4 adjacent hash functions): the four keys are one 32-byte sector of the
+// sketch row, every probe fetches one bucket = the two slots of one sector with ONE 256-bit
+// load, and the four results leave as 16-byte stores.  Blocks are ordered by hash function
+// (like table_insert_kernel), so the few table regions being probed at any time are L2
+// resident: DRAM streams every region once instead of serving 64-byte bursts for random
+// sectors all over the table.  The kernel is bound by the rate of 32-byte sector requests
+// (tools/micro/atom_bench.cu), hence one request per probe.
+__global__ void __launch_bounds__(kProbeRows, 4)
+probe_items_kernel(ProbeSrc src, uint32_t nq) {
+    const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
+    const uint32_t colgroups = (src.n + kProbeCols - 1) / kProbeCols;
+    const uint64_t units = (uint64_t)chunks * colgroups;
+    const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
+    const bool vec = (src.n & 3) == 0;      // rows are sector aligned
+    for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const uint32_t q = (uint32_t)(u % chunks) * kProbeRows + threadIdx.x;
+        const uint32_t l0 = (uint32_t)(u / chunks) * kProbeCols;
+        if (q >= nq) continue;
+        const size_t t0 = (size_t)q * src.n + l0;
+        uint64_t key[kProbeCols];
+        if (vec) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < kProbeCols; ++j) key[j] = l0 + j < src.n ? __ldg(src.qsk + t0 + j) : 0;
+        }
+        uint64_t b[kProbeCols], sa[kProbeCols], sb[kProbeCols], sc[kProbeCols], sd[kProbeCols];
+#pragma unroll
+        for (int j = 0; j < kProbeCols; ++j) {
+            b[j] = key[j] == kEmptyKey ? nb : slot_index(key[j], nb);   // key ~0 lives in the extra slot
+            const uint32_t l = min(l0 + j, src.n - 1);
+            ldg256(src.slots + (uint64_t)l * rstride + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
+        }
+        uint32_t val[kProbeCols], cnt[kProbeCols];
+#pragma unroll
+        for (int j = 0; j < kProbeCols; ++j) {
+            const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
+            for (;;) {
+                // slot = {key, val | (cnt-1) << 32}
+                if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
+                if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
+                if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
+                ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
+            }
+        }
+        if (vec) {
+            *reinterpret_cast<uint4 *>(src.pval + t0) = make_uint4(val[0], val[1], val[2], val[3]);
+            *reinterpret_cast<uint4 *>(src.pcnt + t0) = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kProbeCols; ++j)
+                if (l0 + j < src.n) { src.pval[t0 + j] = val[j]; src.pcnt[t0 + j] = cnt[j]; }
+        }
+    }
+}
+
+// id lists from stored probe results
+struct StoredSrc {
+    const uint32_t *pval, *pcnt;   // [nq][n]
+    const uint32_t *ids;
+    uint32_t n;
     struct Pending {
-        uint64_t key, h;
-        uint4 v;
-        uint32_t j;
+        uint32_t val, c;
     };
     __device__ __forceinline__ uint32_t subs() const { return n; }
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
-        p.j = j;
-        p.key = __ldg(qsk + (size_t)q * n + j);
-        p.h = p.key == kEmptyKey ? cap : slot_index(p.key, cap);   // key ~0 lives in the extra slot
-        p.v = __ldg(reinterpret_cast<const uint4 *>(slots + (uint64_t)j * (cap + 1) + p.h));
+        p.val = __ldg(pval + (size_t)q * n + j);
+        p.c = __ldg(pcnt + (size_t)q * n + j);
         return p;
     }
-    // group size (0 = absent) and val (the id itself for a group of one, else the start in ids)
     __device__ __forceinline__ ListRef finish(Pending p) const {
-        const Slot *region = slots + (uint64_t)p.j * (cap + 1);
-        uint32_t c, val;
-        if (p.key == kEmptyKey) {
-            val = p.v.z;
-            c = p.v.w + 1u;          // untouched slot: 0xFFFFFFFF + 1 = 0
-        } else {
-            for (;;) {
-                const uint64_t kk = ((uint64_t)p.v.y << 32) | p.v.x;
-                if (kk == p.key) { val = p.v.z; c = p.v.w + 1u; break; }
-                if (kk == kEmptyKey) { val = 0; c = 0; break; }
-                p.h = p.h + 1 == cap ? 0 : p.h + 1;
-                p.v = __ldg(reinterpret_cast<const uint4 *>(region + p.h));
-            }
-        }
         ListRef r;
-        r.c = c;
-        r.one = val;
-        r.ptr = c == 1 ? nullptr : ids + val;
+        r.c = p.c;
+        r.one = p.val;
+        r.ptr = p.c == 1 ? nullptr : ids + p.val;
         return r;
     }
     __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
-    __device__ __forceinline__ ListRef get_store(uint32_t q, uint32_t j) const {
-        const ListRef r = get(q, j);
-        pval[(size_t)q * n + j] = r.one;
-        pcnt[(size_t)q * n + j] = r.c;
-        return r;
-    }
-    __device__ __forceinline__ ListRef get_stored(uint32_t q, uint32_t j) const {
-        ListRef r;
-        r.c = pcnt[(size_t)q * n + j];
-        r.one = pval[(size_t)q * n + j];
-        r.ptr = r.c == 1 ? nullptr : ids + r.one;
-        return r;
-    }
 };
 
 struct PartsSrc {
@@ -540,7 +579,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     const size_t smem = (size_t)kLookupWarps * kWarpWords * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) {
-        NSMH_CK(cudaFuncSetAttribute(count_kernel<ProbeSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSMH_CK(cudaFuncSetAttribute(count_kernel<StoredSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NSMH_CK(cudaFuncSetAttribute(count_kernel<PartsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
@@ -597,24 +636,44 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     return NSMH_OK;
 }
 
-static int make_probe_src(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s,
-                          ProbeSrc &src) {
+// probe the n tables for nq device-resident sketches [nq][n]; results in ws.pval / ws.pcnt
+static int probe_all(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s,
+                     StoredSrc &stored) {
     Tables &T = c->tables;
     if (!T.built) return fail(NSMH_ESTATE, "query: tables not built (call nsmh_build)");
+    const uint64_t items = (uint64_t)nq * c->n;
+    if (items >= (1ULL << 32)) return fail(NSMH_EINVAL, "query: queries*n too large for 32-bit item indices");
+    NSMH_TRY(ws.pval.ensure(std::max<uint64_t>(items, 1) * sizeof(uint32_t), s));
+    NSMH_TRY(ws.pcnt.ensure(std::max<uint64_t>(items, 1) * sizeof(uint32_t), s));
+    ProbeSrc src;
     src.qsk = d_qsketch;
     src.slots = T.slots.as<Slot>();
     src.ids = T.ids.as<uint32_t>();
-    src.pval = nullptr;     // only nsmh_probe_lists stores probe results
-    src.pcnt = nullptr;
+    src.pval = ws.pval.as<uint32_t>();
+    src.pcnt = ws.pcnt.as<uint32_t>();
     src.cap = T.cap;
     src.n = c->n;
+    if (items) {
+        const uint64_t units = (uint64_t)((nq + kProbeRows - 1) / kProbeRows) * ((c->n + kProbeCols - 1) / kProbeCols);
+        // persistent grid = the blocks that are resident together (L2 locality of the regions)
+        int occ = 0;
+        NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_items_kernel, kProbeRows, 0));
+        const int blocks = (int)std::min<uint64_t>(units, (uint64_t)c->num_sms * (occ > 0 ? occ : 1));
+        probe_items_kernel<<<blocks, kProbeRows, 0, s>>>(src, nq);
+        ++ws.launches;
+        NSMH_CK(cudaGetLastError());
+    }
+    stored.pval = src.pval;
+    stored.pcnt = src.pcnt;
+    stored.ids = src.ids;
+    stored.n = c->n;
     return NSMH_OK;
 }
 
 // Query nq device-resident sketches [nq][n] against the tables.
 int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s) {
-    ProbeSrc src;
-    NSMH_TRY(make_probe_src(c, ws, d_qsketch, nq, s, src));
+    StoredSrc src;
+    NSMH_TRY(probe_all(c, ws, d_qsketch, nq, s, src));
     return count_and_emit(c, ws, src, c->n, nq, s);
 }
 
@@ -635,12 +694,12 @@ int count_lists_device(nsmh_ctx *c, QueryWs &ws, uint32_t nq, uint32_t parts, co
 // Multi-GPU building block: probe the n tables for every query and gather the id lists,
 // no counting: CSR of concatenated lists in ws.out_off / ws.out_ids.
 __global__ void __launch_bounds__(256)
-probe_totals_kernel(ProbeSrc src, uint32_t nq, uint32_t *__restrict__ qcount) {
+probe_totals_kernel(StoredSrc src, uint32_t nq, uint32_t *__restrict__ qcount) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += warps) {
         uint32_t tot = 0;
-        for (uint32_t j = lane; j < src.n; j += 32) tot += src.get_store(q, j).c;
+        for (uint32_t j = lane; j < src.n; j += 32) tot += src.pcnt[(size_t)q * src.n + j];
 #pragma unroll
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (lane == 0) qcount[q] = tot;
@@ -648,24 +707,15 @@ probe_totals_kernel(ProbeSrc src, uint32_t nq, uint32_t *__restrict__ qcount) {
 }
 
 __global__ void __launch_bounds__(256)
-probe_write_kernel(ProbeSrc src, uint32_t nq, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids) {
+probe_write_kernel(StoredSrc src, uint32_t nq, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     for (uint32_t q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < nq; q += warps) {
         uint64_t base = out_off[q];
         for (uint32_t j0 = 0; j0 < src.n; j0 += 32) {
             const uint32_t j = j0 + lane;
-            ListRef r;
-            r.ptr = nullptr;
-            r.c = 0;
-            r.one = 0;
-            if (j < src.n) r = src.get_stored(q, j);
-            uint32_t incl = r.c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
+            const ListRef r = j < src.n ? src.get(q, j) : empty_list();
+            const uint32_t incl = warp_incl_scan(r.c, lane);
             uint32_t *dst = out_ids + base + (incl - r.c);
             if (r.c == 1 && !r.ptr) dst[0] = r.one;
             else for (uint32_t i = 0; i < r.c; ++i) dst[i] = r.ptr[i];
@@ -675,13 +725,8 @@ probe_write_kernel(ProbeSrc src, uint32_t nq, const uint64_t *__restrict__ out_o
 }
 
 int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s) {
-    ProbeSrc src;
-    NSMH_TRY(make_probe_src(c, ws, d_qsketch, nq, s, src));
-    const uint64_t items = std::max<uint64_t>((uint64_t)nq * c->n, 1);
-    NSMH_TRY(ws.pval.ensure(items * sizeof(uint32_t), s));
-    NSMH_TRY(ws.pcnt.ensure(items * sizeof(uint32_t), s));
-    src.pval = ws.pval.as<uint32_t>();
-    src.pcnt = ws.pcnt.as<uint32_t>();
+    StoredSrc src;
+    NSMH_TRY(probe_all(c, ws, d_qsketch, nq, s, src));
     ws.last_nq = nq;
     ws.last_total = 0;
     NSMH_TRY(ws.out_off.ensure(((size_t)nq + 1) * sizeof(uint64_t), s));

@@ -7,9 +7,10 @@
 // the structure is an exact dictionary key -> list of read ids and its answers do
 // not depend on the MPHF.
 //
-// Here: one open-addressing region of cap+1 16-byte slots {key, val, cnt-1} per
-// hash function (cap = 2*reads; the extra slot holds the key that equals the empty
-// marker ~0).  A probe is ONE 16-byte load = one 32-byte sector.
+// Here: one open-addressing region of 16-byte slots {key, val, cnt-1} per hash function
+// (cap = 2*reads slots + one extra slot for the key that equals the empty marker ~0).
+// The two slots of a 32-byte sector form a bucket: a probe fetches one sector and checks
+// both, so nearly every probe sequence ends after a single DRAM access.
 //   pass 1  insert : linear probing; an empty slot is claimed with ONE 128-bit
 //                    compare-and-swap that writes key, read id and count together, so a
 //                    group of one (most groups) is finished by a single atomic and needs
@@ -38,11 +39,15 @@ struct BuildArgs {
     const uint64_t *sk;     // [rows][n]
     Slot *slots;            // [n][cap+1]
     uint32_t *ids;
-    uint32_t *m_slot, *m_id, *m_rank;   // members that arrived second or later
-    uint32_t *g_slot;                   // slots of groups with two or more members
-    unsigned int *counters;             // [0] ids cursor, [1] multi members, [2] multi groups
+    // Members that arrived second or later, and the slots of their groups.  Every block of
+    // the insert kernel appends to its own segment of seg_cap entries (shared-memory cursor):
+    // a single global cursor would serialise ~10^5 same-address atomics per build.
+    uint32_t *m_slot, *m_id, *m_rank;
+    uint32_t *g_slot;
+    unsigned int *counters;             // [0] ids cursor
+    unsigned int *seg_count;            // [2*segments] members, groups of every segment
     uint64_t cap;
-    uint32_t rows, n;
+    uint32_t rows, n, seg_cap, segments;
 };
 
 // 128-bit compare-and-swap on a slot; returns the previous contents.
@@ -65,112 +70,168 @@ __device__ __forceinline__ uint64_t slot_key_now(const Slot *p) {
     return k;
 }
 
-// returns the slot index (global) and the element's rank inside its group
-__device__ __forceinline__ uint32_t insert_one(const BuildArgs &a, uint32_t l, uint64_t key, uint32_t id,
-                                               uint32_t &rank) {
-    const uint64_t base = (uint64_t)l * (a.cap + 1);
-    Slot *region = a.slots + base;
-    if (key == kEmptyKey) {
-        // slots start as all-ones: the count field holds (group size - 1), wrapping from ~0
-        rank = atomicAdd(&region[a.cap].cntm1, 1u) + 1u;
-        if (rank == 0) region[a.cap].val = id;
-        return (uint32_t)(base + a.cap);
-    }
-    uint64_t h = slot_index(key, a.cap);
-    for (;;) {
-        Slot *p = region + h;
-        uint64_t cur = slot_key_now(p);
-        if (cur == kEmptyKey) {
-            uint64_t old_lo, old_hi;
-            slot_cas(p, ~0ULL, ~0ULL, key, (uint64_t)id, old_lo, old_hi);   // {key, val = id, cnt-1 = 0}
-            if (old_lo == kEmptyKey) { rank = 0; return (uint32_t)(base + h); }
-            cur = old_lo;
-        }
-        if (cur == key) {
-            rank = atomicAdd(&p->cntm1, 1u) + 1u;
-            return (uint32_t)(base + h);
-        }
-        h = h + 1 == a.cap ? 0 : h + 1;
-    }
-}
-
+// Every thread walks its own stream of (row, column) items as a small state machine: one
+// loop iteration = at most one probe step (one bucket fetch + one atomic) of the thread's
+// current item, and a thread whose item is finished moves on to its next item without
+// waiting for the other lanes.  A warp therefore pays (about) the AVERAGE probe length per
+// item instead of the longest probe sequence among its 32 lanes, which is what a
+// per-item loop costs under SIMT when every step is a DRAM / L2-atomic round trip.
+// Buckets are the two slots of one 32-byte sector.  The kernel is bound by the L2 atomic
+// rate (tools/micro/atom_bench.cu: ~50 G atomics/s whatever the width), so a step is
+// exactly one atomic and nothing is loaded beforehand.
 __global__ void __launch_bounds__(kBuildRows)
 table_insert_kernel(BuildArgs a) {
+    __shared__ unsigned int s_count[2];
     const int lane = threadIdx.x & 31;
     const uint32_t chunks = (a.rows + kBuildRows - 1) / kBuildRows;
     const uint32_t colgroups = (a.n + kBuildCols - 1) / kBuildCols;
     const uint64_t units = (uint64_t)chunks * colgroups;
-    for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t cg = (uint32_t)(u / chunks);
-        const uint32_t row = (uint32_t)(u % chunks) * kBuildRows + threadIdx.x;
-        const uint32_t l0 = cg * kBuildCols;
-        const bool live = row < a.rows;
-        uint64_t keys[kBuildCols];
+    const uint64_t nb = a.cap >> 1;
+    const uint64_t stride = region_stride(a.cap);
+    const size_t seg0 = (size_t)blockIdx.x * a.seg_cap;
+    if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
+    __syncthreads();
+
+    uint64_t u = blockIdx.x;              // next unit to load
+    uint64_t nk[kBuildCols];              // its keys, prefetched
+    auto prefetch = [&](uint64_t uu) {
+        const uint32_t row = (uint32_t)(uu % chunks) * kBuildRows + threadIdx.x;
+        const uint32_t l0 = (uint32_t)(uu / chunks) * kBuildCols;
 #pragma unroll
         for (int j = 0; j < kBuildCols; ++j)
-            keys[j] = (live && l0 + j < a.n) ? __ldg(a.sk + (size_t)row * a.n + l0 + j) : 0;
+            nk[j] = (uu < units && row < a.rows && l0 + j < a.n) ? __ldg(a.sk + (size_t)row * a.n + l0 + j) : kEmptyKey;
+    };
+    prefetch(u);
+    uint64_t keys[kBuildCols];
+    uint32_t row = 0, l0 = 0;
+    int j = kBuildCols;
+    bool finished = false, active = false;
+    uint64_t key = 0, b = 0;
+    int sub = 0;
+    Slot *region = a.slots;
+
+    for (;;) {
+        uint32_t rank = 0, s = 0;
+        bool completed = false;
+        if (!active && !finished) {
+            if (j == kBuildCols) {
+                if (u >= units) finished = true;
+                else {
 #pragma unroll
-        for (int j = 0; j < kBuildCols; ++j) {
-            uint32_t rank = 0, s = 0;
-            if (live && l0 + j < a.n) s = insert_one(a, l0 + j, keys[j], row, rank);
-            // warp-aggregated append of the members that were not first in their group
-            const uint32_t m = __ballot_sync(0xffffffffu, rank >= 1);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                uint32_t b = 0;
-                if (lane == leader) b = atomicAdd(a.counters + 1, (unsigned int)__popc(m));
-                b = __shfl_sync(0xffffffffu, b, leader);
-                if (rank >= 1) {
-                    const uint32_t pos = b + __popc(m & ((1u << lane) - 1));
-                    a.m_slot[pos] = s;
-                    a.m_id[pos] = row;
-                    a.m_rank[pos] = rank;
-                    if (rank == 1) a.g_slot[atomicAdd(a.counters + 2, 1u)] = s;
+                    for (int t = 0; t < kBuildCols; ++t) keys[t] = nk[t];
+                    row = (uint32_t)(u % chunks) * kBuildRows + threadIdx.x;
+                    l0 = (uint32_t)(u / chunks) * kBuildCols;
+                    u += gridDim.x;
+                    prefetch(u);
+                    j = 0;
+                }
+            }
+            if (!finished) {
+                key = j == 0 ? keys[0] : j == 1 ? keys[1] : j == 2 ? keys[2] : keys[3];
+                const uint32_t l = l0 + j;
+                ++j;
+                if (row < a.rows && l < a.n) {
+                    region = a.slots + (uint64_t)l * stride;
+                    if (key == kEmptyKey) {
+                        // slots start as all-ones: the count field holds (group size - 1), wrapping from ~0
+                        rank = atomicAdd(&region[a.cap].cntm1, 1u) + 1u;
+                        if (rank == 0) region[a.cap].val = row;
+                        s = (uint32_t)((uint64_t)l * stride + a.cap);
+                        completed = true;
+                    } else {
+                        b = slot_index(key, nb);
+                        sub = 0;
+                        active = true;
+                    }
                 }
             }
         }
+        if (active) {
+            // no look before the leap: the compare-and-swap itself returns what the slot holds, so an
+            // item costs one L2 atomic when its slot is free (the common case at load <= 0.5)
+            Slot *p = region + 2 * b + sub;
+            uint64_t old_lo, old_hi;
+            slot_cas(p, ~0ULL, ~0ULL, key, (uint64_t)row, old_lo, old_hi);   // {key, val = id, cnt-1 = 0}
+            if (old_lo == kEmptyKey) {
+                rank = 0;
+                completed = true;
+            } else if (old_lo == key) {
+                rank = atomicAdd(&p->cntm1, 1u) + 1u;
+                completed = true;
+            } else {
+                sub ^= 1;
+                if (sub == 0) b = b + 1 == nb ? 0 : b + 1;
+            }
+            if (completed) {
+                s = (uint32_t)(p - a.slots);
+                active = false;
+            }
+        }
+        // warp-aggregated append of the members that were not first in their group
+        const uint32_t m = __ballot_sync(0xffffffffu, completed && rank >= 1);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&s_count[0], (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (completed && rank >= 1) {
+                const size_t pos = seg0 + base + __popc(m & ((1u << lane) - 1));
+                a.m_slot[pos] = s;
+                a.m_id[pos] = row;
+                a.m_rank[pos] = rank;
+                if (rank == 1) a.g_slot[seg0 + atomicAdd(&s_count[1], 1u)] = s;
+            }
+        }
+        if (__all_sync(0xffffffffu, finished && !active)) break;
     }
+    __syncthreads();
+    if (threadIdx.x < 2) a.seg_count[2 * blockIdx.x + threadIdx.x] = s_count[threadIdx.x];
 }
 
 // groups of two or more: allocate the id range, move the inlined first id into it
 __global__ void __launch_bounds__(256)
 table_groups_kernel(BuildArgs a) {
     const int lane = threadIdx.x & 31;
-    const uint32_t groups = a.counters[2];
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t rounds = (groups + stride - 1) / stride;
-    uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint32_t r = 0; r < rounds; ++r, g += stride) {   // whole warps stay in the loop for the shuffles
-        uint32_t need = 0, s = 0;
-        if (g < groups) {
-            s = a.g_slot[g];
-            need = a.slots[s].cntm1 + 1u;
-        }
-        uint32_t incl = need;
+    for (uint32_t seg = blockIdx.x; seg < a.segments; seg += gridDim.x) {
+        const uint32_t groups = a.seg_count[2 * seg + 1];
+        const uint32_t *g_slot = a.g_slot + (size_t)seg * a.seg_cap;
+        const uint32_t rounds = (groups + blockDim.x - 1) / blockDim.x;
+        uint32_t g = threadIdx.x;
+        for (uint32_t r = 0; r < rounds; ++r, g += blockDim.x) {   // whole warps stay in the loop for the shuffles
+            uint32_t need = 0, s = 0;
+            if (g < groups) {
+                s = g_slot[g];
+                need = a.slots[s].cntm1 + 1u;
+            }
+            uint32_t incl = need;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (total) {
-            if (lane == 31) base = atomicAdd(a.counters, total);
-            base = __shfl_sync(0xffffffffu, base, 31);
-        }
-        if (need) {
-            const uint32_t b = base + incl - need;
-            a.ids[b] = a.slots[s].val;
-            a.slots[s].val = b;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (total) {
+                if (lane == 31) base = atomicAdd(a.counters, total);
+                base = __shfl_sync(0xffffffffu, base, 31);
+            }
+            if (need) {
+                const uint32_t b = base + incl - need;
+                a.ids[b] = a.slots[s].val;
+                a.slots[s].val = b;
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(256)
 table_fill_kernel(BuildArgs a) {
-    const uint32_t members = a.counters[1];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < members; i += gridDim.x * blockDim.x)
-        a.ids[a.slots[a.m_slot[i]].val + a.m_rank[i]] = a.m_id[i];
+    for (uint32_t seg = blockIdx.x; seg < a.segments; seg += gridDim.x) {
+        const uint32_t members = a.seg_count[2 * seg];
+        const size_t seg0 = (size_t)seg * a.seg_cap;
+        for (uint32_t i = threadIdx.x; i < members; i += blockDim.x)
+            a.ids[a.slots[a.m_slot[seg0 + i]].val + a.m_rank[seg0 + i]] = a.m_id[seg0 + i];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -188,35 +249,44 @@ int build_tables(nsmh_ctx *c) {
     cudaStream_t s = c->stream;
     const uint32_t n = c->n, rows = c->table_reads;
     T.built = false;
-    const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);   // load factor <= 0.5
-    const uint64_t nslots = (uint64_t)n * (cap + 1);
+    const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);   // even; load factor <= 0.5
+    const uint64_t nslots = (uint64_t)n * region_stride(cap);
     const uint64_t items = (uint64_t)rows * n;
     if (nslots >= (1ULL << 32) || items >= (1ULL << 32))
         return fail(NSMH_EINVAL, "build: reads*n too large for 32-bit slot indices");
     T.cap = cap;
     T.table_reads = rows;
     const size_t ni = (size_t)(items ? items : 1);
+    // persistent grid: exactly the blocks that are resident together, so that consecutive work
+    // units (same hash functions) really run at the same time and their regions stay in L2
+    int occ = 0;
+    NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_insert_kernel, kBuildRows, 0));
+    const uint64_t units = (uint64_t)((rows + kBuildRows - 1) / kBuildRows) * ((n + kBuildCols - 1) / kBuildCols);
+    const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(units, (uint64_t)c->num_sms * (occ > 0 ? occ : 1)));
+    const uint32_t seg_cap = (uint32_t)((units + blocks - 1) / blocks) * kBuildRows * kBuildCols;
+    const size_t nseg = (size_t)blocks * seg_cap;
     NSMH_TRY(T.slots.ensure(nslots * sizeof(Slot), s));
     NSMH_TRY(T.ids.ensure(ni * sizeof(uint32_t), s));
-    NSMH_TRY(c->build_multi.ensure(ni * 4 * sizeof(uint32_t), s));
-    NSMH_TRY(c->build_tmp.ensure(64, s));
+    NSMH_TRY(c->build_multi.ensure(std::max<size_t>(nseg, 1) * 4 * sizeof(uint32_t), s));
+    NSMH_TRY(c->build_tmp.ensure((8 + 2 * (size_t)blocks) * sizeof(unsigned int), s));
     NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), s));
-    NSMH_CK(cudaMemsetAsync(c->build_tmp.p, 0, 4 * sizeof(unsigned int), s));
+    NSMH_CK(cudaMemsetAsync(c->build_tmp.p, 0, 8 * sizeof(unsigned int), s));
     if (items) {
         BuildArgs a;
         a.sk = c->table_sketches;
         a.slots = T.slots.as<Slot>();
         a.ids = T.ids.as<uint32_t>();
         a.m_slot = c->build_multi.as<uint32_t>();
-        a.m_id = a.m_slot + ni;
-        a.m_rank = a.m_id + ni;
-        a.g_slot = a.m_rank + ni;
+        a.m_id = a.m_slot + nseg;
+        a.m_rank = a.m_id + nseg;
+        a.g_slot = a.m_rank + nseg;
         a.counters = c->build_tmp.as<unsigned int>();
+        a.seg_count = a.counters + 8;
         a.cap = cap;
         a.rows = rows;
         a.n = n;
-        const uint64_t units = (uint64_t)((rows + kBuildRows - 1) / kBuildRows) * ((n + kBuildCols - 1) / kBuildCols);
-        const int blocks = (int)std::min<uint64_t>(units, (uint64_t)c->num_sms * 8);
+        a.seg_cap = seg_cap;
+        a.segments = blocks;
         table_insert_kernel<<<blocks, kBuildRows, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
         table_groups_kernel<<<c->num_sms * 2, 256, 0, s>>>(a);
@@ -237,7 +307,7 @@ int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out) {
     NSMH_TRY(c->build_tmp.ensure(64, s));
     uint32_t *d = c->build_tmp.as<uint32_t>() + 4;
     NSMH_CK(cudaMemsetAsync(d, 0, sizeof(uint32_t), s));
-    table_count_keys_kernel<<<c->num_sms, 256, 0, s>>>(T.slots.as<Slot>() + (uint64_t)j * (T.cap + 1),
+    table_count_keys_kernel<<<c->num_sms, 256, 0, s>>>(T.slots.as<Slot>() + (uint64_t)j * region_stride(T.cap),
                                                        T.cap + 1, d);
     ++c->launches;
     NSMH_CK(cudaGetLastError());
