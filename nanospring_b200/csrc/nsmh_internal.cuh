@@ -136,12 +136,10 @@ struct nsmh_ctx {
     int num_sms = 148;
 
     nsmh::DevBuf d_rand;        // u64 [n]
-    nsmh::DevBuf d_ftab_hit;    // u8 [kFilterTabSize]     1 = some hash targets this prefix
     nsmh::DevBuf d_ftab_first;  // u8 [kFilterTabSize]     first hash of the chain
     nsmh::DevBuf d_ftab_next;   // u8 [(kFilterMaxBits+1)*n] next hash in chain, 0xFF = end
     nsmh::DevBuf d_ftab_hit3;   // u8 [kFilter3TabSize]    3 hit bits per (b+4)-bit window
     int lambda_log2 = nsmh::kFilterLambdaLog2;
-    int sketch_variant = 0;     // 0: 3-position lookups + dense hit rounds, 1: first version (A/B runs)
     uint32_t tile_words = nsmh::kTileWords;
 
     nsmh::ReadSet reads;

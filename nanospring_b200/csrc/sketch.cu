@@ -23,10 +23,15 @@
 //    answers three consecutive positions) and touches the 64-bit path only for
 //    the ~n*lambda positions per read that hit, lambda = 2^lambda_log2 .. twice
 //    that being the expected k-mers per bucket (b = floor(log2 #kmers) - lambda_log2).
-//    Hits of a 512-position block are compacted and processed 32 at a time so all
-//    lanes stay busy.  A (read, hash) pair whose bucket stayed empty (probability
-//    ~e^-lambda on random sequence, certain on e.g. homopolymers) is rescanned
-//    exhaustively by sketch_fixup_kernel, which makes the result unconditional.
+//    A warp owns a tile (<= 1024 packed words of one read): the words arrive in
+//    shared memory through ONE bulk asynchronous copy (cp.async.bulk + mbarrier),
+//    phase 1 turns them into one 32-position hit mask per lane and step, and in
+//    phase 2 every lane walks the hits of its own masks, so no compaction is
+//    needed and only the imbalance between lanes is lost.  A (read, hash) pair
+//    whose bucket stayed empty (probability ~e^-lambda on random sequence, certain
+//    on e.g. homopolymers) is rescanned exhaustively by sketch_fixup_kernel, which
+//    makes the result unconditional.
+#include <algorithm>
 #include <cstdlib>
 
 #include "nsmh_internal.cuh"
@@ -40,7 +45,7 @@ struct SketchArgs {
     const uint32_t *tile_start; // [n_reads+1] exclusive scan of tiles per read
     const uint32_t *tile_read;  // [num_tiles] read of every tile (nullptr: binary search)
     const uint64_t *rnd;        // [n]
-    const uint8_t *ftab_hit, *ftab_first, *ftab_next, *ftab_hit3;
+    const uint8_t *ftab_first, *ftab_next, *ftab_hit3;
     unsigned long long *counters;   // [0] fix-ups
     uint32_t n_reads, k, n;
     int lambda_log2;
@@ -64,7 +69,8 @@ sketch_init_kernel(SketchArgs a, uint32_t *__restrict__ tile_cnt) {
             uint32_t tiles = 0;
             if (len >= a.k) {
                 uint64_t nk = len - a.k + 1;
-                uint64_t w0 = b0 / kWordBases, w1 = (b0 + nk - 1) / kWordBases;
+                // tiles start on a 4-word (16-byte) boundary: the bulk copies need it
+                uint64_t w0 = (b0 / kWordBases) & ~3ULL, w1 = (b0 + nk - 1) / kWordBases;
                 tiles = (uint32_t)((w1 - w0 + a.tile_words) / a.tile_words);
             }
             tile_cnt[i] = tiles;
@@ -101,7 +107,7 @@ __device__ __forceinline__ TileGeom tile_geom(const SketchArgs &a, uint32_t tile
     g.read = a.tile_read ? a.tile_read[tile] : find_read_of_tile(a.tile_start, a.n_reads, tile);
     g.rb = a.off[g.read];
     g.nk = a.off[g.read + 1] - g.rb - a.k + 1;
-    uint64_t w0 = g.rb / kWordBases, w1 = (g.rb + g.nk - 1) / kWordBases;
+    uint64_t w0 = (g.rb / kWordBases) & ~3ULL, w1 = (g.rb + g.nk - 1) / kWordBases;
     g.w_begin = w0 + (uint64_t)(tile - a.tile_start[g.read]) * a.tile_words;
     g.w_end = g.w_begin + a.tile_words < w1 + 1 ? g.w_begin + a.tile_words : w1 + 1;
     return g;
@@ -131,206 +137,159 @@ __device__ __forceinline__ uint64_t kmer_at(uint32_t w0, uint32_t w1, uint32_t w
     return (((uint64_t)h32 << 32) | l32) >> kshift;
 }
 
-// ---- filter kernel: 3 positions per lookup, dense hit rounds ---------------------
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+// ---- bulk copy + mbarrier (sm_90+/sm_100a PTX) -------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+// shared memory of the filter kernel: block-wide tables, then one private area per warp
+struct FilterSmem {
+    uint32_t stage_words;    // per warp: staged packed words (tile_words + 8)
+    uint32_t mask_words;     // per warp: hit masks (tile_words / 2)
+    size_t tab_bytes, warp_bytes;
+    __host__ __device__ FilterSmem(uint32_t n, uint32_t tile_words) {
+        stage_words = tile_words + 8;
+        mask_words = tile_words / 2;
+        size_t t = kFilter3TabSize + (2 << kFilter3MaxBits) + (size_t)(kFilterMaxBits + 1) * n + (size_t)n * 8 + 8;
+        tab_bytes = (t + 15) & ~(size_t)15;
+        warp_bytes = ((size_t)stage_words * 4 + (size_t)mask_words * 4 + (size_t)n * 16 + 16 + 15) & ~(size_t)15;
+    }
+};
+
+// ---- filter kernel ------------------------------------------------------------------
+// a.tile_words is a multiple of 64: in every step a lane owns two adjacent words = 32 positions.
+__global__ void __launch_bounds__(768)
 sketch_filter_kernel(SketchArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
+    const FilterSmem L(a.n, a.tile_words);
     uint8_t *s_hit3 = smem;                                   // kFilter3TabSize
     uint8_t *s_first = s_hit3 + kFilter3TabSize;              // 2^(kFilter3MaxBits+1)
-    ulonglong2 *s_min = reinterpret_cast<ulonglong2 *>(s_first + (2 << kFilter3MaxBits));   // WARPS * n pairs
-    uint64_t *s_rlo = reinterpret_cast<uint64_t *>(s_min + (size_t)WARPS * a.n);            // n
-    uint16_t *s_list = reinterpret_cast<uint16_t *>(s_rlo + a.n);                           // WARPS * 512
-    uint8_t *s_next = reinterpret_cast<uint8_t *>(s_list + WARPS * 512);
+    uint8_t *s_next = s_first + (2 << kFilter3MaxBits);       // (kFilterMaxBits+1) * n
+    uint64_t *s_rlo = reinterpret_cast<uint64_t *>(smem + ((kFilter3TabSize + (2 << kFilter3MaxBits) +
+                                                            (size_t)(kFilterMaxBits + 1) * a.n + 7) & ~(size_t)7));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    uint8_t *mine = smem + L.tab_bytes + (size_t)warp * L.warp_bytes;
+    uint32_t *sw = reinterpret_cast<uint32_t *>(mine);                      // staged words
+    uint32_t *own = sw + L.stage_words;                                     // hit masks, [step][lane]
+    ulonglong2 *my_min = reinterpret_cast<ulonglong2 *>(own + L.mask_words);   // {rand[l] & mask, running minimum}
+    uint64_t *bar = reinterpret_cast<uint64_t *>(my_min + a.n);
 
     const uint64_t mask = kmer_mask(a.k);
     {
         const uint4 *g3 = reinterpret_cast<const uint4 *>(a.ftab_hit3);
         const uint4 *gf = reinterpret_cast<const uint4 *>(a.ftab_first);
         uint4 *s3 = reinterpret_cast<uint4 *>(s_hit3), *sf = reinterpret_cast<uint4 *>(s_first);
-        for (int t = threadIdx.x; t < kFilter3TabSize / 16; t += WARPS * 32) s3[t] = g3[t];
-        for (int t = threadIdx.x; t < (2 << kFilter3MaxBits) / 16; t += WARPS * 32) sf[t] = gf[t];
-        for (uint32_t t = threadIdx.x; t < (kFilterMaxBits + 1) * a.n; t += WARPS * 32)
-            s_next[t] = a.ftab_next[t];
-        for (uint32_t t = threadIdx.x; t < a.n; t += WARPS * 32) s_rlo[t] = a.rnd[t] & mask;
+        for (int t = threadIdx.x; t < kFilter3TabSize / 16; t += blockDim.x) s3[t] = g3[t];
+        for (int t = threadIdx.x; t < (2 << kFilter3MaxBits) / 16; t += blockDim.x) sf[t] = gf[t];
+        for (uint32_t t = threadIdx.x; t < (kFilterMaxBits + 1) * a.n; t += blockDim.x) s_next[t] = a.ftab_next[t];
+        for (uint32_t t = threadIdx.x; t < a.n; t += blockDim.x) s_rlo[t] = a.rnd[t] & mask;
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            fence_proxy_async();
+        }
     }
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    ulonglong2 *my_min = s_min + (size_t)warp * a.n;
-    uint16_t *my_list = s_list + warp * 512;
     const uint32_t num_tiles = a.tile_start[a.n_reads];
     const int kshift = 64 - 2 * (int)a.k;
+    uint32_t phase = 0;
 
-    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < num_tiles; tile += gridDim.x * WARPS) {
+    for (uint32_t tile = blockIdx.x * warps + warp; tile < num_tiles; tile += gridDim.x * warps) {
         const TileGeom g = tile_geom(a, tile);
+        const uint32_t nw = (uint32_t)(g.w_end - g.w_begin);
+        // ---- stage the tile: words [w_begin, w_end + 3) rounded up to 16 bytes, one bulk copy ----
+        __syncwarp();                       // everybody is done with the previous tile's words
+        if (lane == 0) {
+            const uint32_t bytes = ((nw + 3 + 3) & ~3u) * 4;
+            fence_proxy_async();
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(sw, a.W + g.w_begin, bytes, bar);
+        }
         const int b = filter_bits(g.nk, a.lambda_log2, kFilter3MaxBits, a.k);
         const int rshift3 = 32 - (b + 4);       // window of b+4 bits answers positions j, j+1, j+2
         const int rshift = 32 - b;
         const uint8_t *nxt = s_next + (size_t)b * a.n;
-
         for (uint32_t l = lane; l < a.n; l += 32) my_min[l] = make_ulonglong2(s_rlo[l], ~0ULL);
-        __syncwarp();
+        // valid k-mer starts of the tile, relative to its first base
+        const uint64_t t0 = g.w_begin * kWordBases;
+        const uint32_t lo_pos = g.rb > t0 ? (uint32_t)(g.rb - t0) : 0u;
+        const uint32_t hi_pos = (uint32_t)min((uint64_t)nw * kWordBases, g.rb + g.nk - t0);
+        const uint32_t steps = (nw + 63) / 64;
+        while (!mbar_try_wait(bar, phase)) { }
+        phase ^= 1;
 
-        // software pipeline: the words of the next 512-position block are in flight while
-        // this one is scanned
-        uint32_t n0 = 0, n1 = 0, n2 = 0;
-        if (g.w_begin + lane < g.w_end) {
-            n0 = __ldg(a.W + g.w_begin + lane);
-            n1 = __ldg(a.W + g.w_begin + lane + 1);
-            n2 = __ldg(a.W + g.w_begin + lane + 2);
-        }
-        for (uint64_t wb = g.w_begin; wb < g.w_end; wb += 32) {
-            const uint64_t w = wb + lane;
-            const uint32_t w0 = n0, w1 = n1, w2 = n2;
-            n0 = n1 = n2 = 0;
-            if (w + 32 < g.w_end) {
-                n0 = __ldg(a.W + w + 32);
-                n1 = __ldg(a.W + w + 33);
-                n2 = __ldg(a.W + w + 34);
-            }
-            int lo = 0, hi = 0;
-            if (w < g.w_end) valid_range(g, w, lo, hi);
-            // phase 1: six lookups cover positions 0..17; bits beyond 15 are dropped
-            uint32_t hits = 0;
+        // ---- phase 1: 32 positions per lane and step -> hit mask (bit 31-q = position q) ----
+        for (uint32_t it = 0; it < steps; ++it) {
+            const uint32_t i0 = it * 64 + 2 * lane;
+            const uint2 w01 = *reinterpret_cast<const uint2 *>(sw + i0);
+            const uint32_t w0 = w01.x, w1 = w01.y, w2 = sw[i0 + 2];
+            uint32_t hi = 0, lo = 0;
 #pragma unroll
-            for (int t = 0; t < 6; ++t) {
-                uint32_t v = t ? __funnelshift_l(w1, w0, 6 * t) : w0;
-                uint32_t idx = __funnelshift_rc(v, 1u, rshift3);   // (1<<(b+4)) | window
-                hits = hits * 8 + s_hit3[idx];
+            for (int t = 0; t < 5; ++t) {          // positions 0..14
+                const uint32_t v = t ? __funnelshift_l(w1, w0, 6 * t) : w0;
+                hi = hi * 8 + s_hit3[__funnelshift_rc(v, 1u, rshift3)];   // (1<<(b+4)) | window
             }
-            hits = (hits >> 2) & (0xFFFFu >> lo) & (0xFFFFu << (16 - hi)) & 0xFFFFu;
-
-            // phase 2: compact the block's hits, then 32 per round with every lane busy
-            const uint32_t cnt = __popc(hits);
-            uint32_t incl = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+            for (int t = 5; t < 11; ++t) {         // positions 15..32
+                const uint32_t v = t == 5 ? __funnelshift_l(w1, w0, 30) : __funnelshift_l(w2, w1, 6 * t - 32);
+                lo = lo * 8 + s_hit3[__funnelshift_rc(v, 1u, rshift3)];
             }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            if (total == 0) continue;
-            uint32_t pos = incl - cnt;
-            while (hits) {
-                const int top = 31 - __clz(hits);
-                hits ^= 1u << top;
-                my_list[pos++] = (uint16_t)((lane << 4) | (15 - top));
+            uint32_t m = (hi << 17) | (lo >> 1);
+            const uint32_t pb = i0 * kWordBases;
+            if (pb < lo_pos || pb + 32 > hi_pos) {     // read / tile edges
+                const uint32_t first = lo_pos > pb ? lo_pos - pb : 0u;          // valid q in [first, last)
+                const uint32_t last = hi_pos > pb ? min(hi_pos - pb, 32u) : 0u;
+                const uint32_t keep_hi = first >= 32 ? 0u : 0xFFFFFFFFu >> first;
+                const uint32_t keep_lo = last == 0 ? 0u : 0xFFFFFFFFu << (32 - last);
+                m &= keep_hi & keep_lo;
             }
-            __syncwarp();
-            for (uint32_t e0 = 0; e0 < total; e0 += 32) {
-                const uint32_t e = e0 + lane;
-                const uint32_t ent = e < total ? my_list[e] : 0u;
-                const int src = ent >> 4, j = ent & 15;
-                const uint32_t a0 = __shfl_sync(0xffffffffu, w0, src);
-                const uint32_t a1 = __shfl_sync(0xffffffffu, w1, src);
-                const uint32_t a2 = __shfl_sync(0xffffffffu, w2, src);
-                if (e < total) {
-                    uint32_t h32;
-                    const uint64_t x = kmer_at(a0, a1, a2, j, kshift, h32);
-                    uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)];
-                    do {
-                        const ulonglong2 rm = my_min[l];        // {rand[l] & mask, running minimum}
-                        const uint32_t ln = nxt[l];
-                        const uint64_t y = x ^ rm.x;
-                        if (y < rm.y) atomicMin(&my_min[l].y, (unsigned long long)y);
-                        l = ln;
-                    } while (l != 0xFFu);
-                }
-            }
-            __syncwarp();
+            own[it * 32 + lane] = m;
         }
-        __syncwarp();
-        for (uint32_t l = lane; l < a.n; l += 32) {
-            uint64_t v = my_min[l].y;
-            if (v != ~0ULL)
-                atomicMin(reinterpret_cast<unsigned long long *>(a.sk + (size_t)g.read * a.n + l),
-                          (a.rnd[l] & ~mask) | v);
-        }
-        __syncwarp();
-    }
-}
 
-// ---- first version of the filter kernel (one lookup per position, hits handled
-//      inline by the lane that found them); kept for A/B measurements -------------
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
-sketch_filter1_kernel(SketchArgs a) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    uint8_t *s_hit = smem;
-    uint8_t *s_first = s_hit + kFilterTabSize;
-    uint64_t *s_rlo = reinterpret_cast<uint64_t *>(s_first + kFilterTabSize);
-    uint64_t *s_min = s_rlo + a.n;
-    uint8_t *s_next = reinterpret_cast<uint8_t *>(s_min + (size_t)WARPS * a.n);
-
-    const uint64_t mask = kmer_mask(a.k);
-    {
-        const uint4 *gh = reinterpret_cast<const uint4 *>(a.ftab_hit);
-        const uint4 *gf = reinterpret_cast<const uint4 *>(a.ftab_first);
-        uint4 *sh = reinterpret_cast<uint4 *>(s_hit), *sf = reinterpret_cast<uint4 *>(s_first);
-        for (int t = threadIdx.x; t < kFilterTabSize / 16; t += WARPS * 32) {
-            sh[t] = gh[t];
-            sf[t] = gf[t];
-        }
-        for (uint32_t t = threadIdx.x; t < (kFilterMaxBits + 1) * a.n; t += WARPS * 32)
-            s_next[t] = a.ftab_next[t];
-        for (uint32_t t = threadIdx.x; t < a.n; t += WARPS * 32) s_rlo[t] = a.rnd[t] & mask;
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint64_t *my_min = s_min + (size_t)warp * a.n;
-    const uint32_t num_tiles = a.tile_start[a.n_reads];
-    const int kshift = 64 - 2 * (int)a.k;
-
-    for (uint32_t tile = blockIdx.x * WARPS + warp; tile < num_tiles; tile += gridDim.x * WARPS) {
-        const TileGeom g = tile_geom(a, tile);
-        const int b = filter_bits(g.nk, a.lambda_log2, kFilterMaxBits, a.k);
-        const int rshift = 32 - b;
-        const uint8_t *nxt = s_next + (size_t)b * a.n;
-
-        for (uint32_t l = lane; l < a.n; l += 32) my_min[l] = ~0ULL;
-        __syncwarp();
-
-        for (uint64_t wb = g.w_begin; wb < g.w_end; wb += 32) {
-            const uint64_t w = wb + lane;
-            uint32_t w0 = 0, w1 = 0, w2 = 0;
-            int lo = 0, hi = 0;
-            if (w < g.w_end) {
-                w0 = __ldg(a.W + w);
-                w1 = __ldg(a.W + w + 1);
-                w2 = __ldg(a.W + w + 2);
-                valid_range(g, w, lo, hi);
-            }
-            uint32_t hits = 0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                uint32_t v = j ? __funnelshift_l(w1, w0, 2 * j) : w0;
-                uint32_t idx = __funnelshift_rc(v, 1u, rshift);   // (1<<b) | top b bits
-                hits = hits * 2 + s_hit[idx];
-            }
-            hits &= (0xFFFFu >> lo) & (0xFFFFu << (16 - hi)) & 0xFFFFu;
-            while (hits) {
-                const int top = 31 - __clz(hits);
-                hits ^= 1u << top;
+        // ---- phase 2: every lane walks its own hits ----
+        {
+            uint32_t c = 0;
+            uint32_t m = own[lane];
+            for (;;) {
+                while (m == 0 && ++c < steps) m = own[c * 32 + lane];
+                if (m == 0) break;
+                const int q = __clz(m);
+                m &= ~(0x80000000u >> q);
+                const uint32_t wi = c * 64 + 2 * lane + (q >> 4);
                 uint32_t h32;
-                const uint64_t x = kmer_at(w0, w1, w2, 15 - top, kshift, h32);
+                const uint64_t x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], q & 15, kshift, h32);
                 uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)];
                 do {
-                    uint64_t y = x ^ s_rlo[l];
-                    if (y < my_min[l]) atomicMin(reinterpret_cast<unsigned long long *>(my_min + l), y);
-                    l = nxt[l];
+                    const ulonglong2 rm = my_min[l];
+                    const uint32_t ln = nxt[l];
+                    const uint64_t y = x ^ rm.x;
+                    if (y < rm.y) atomicMin(&my_min[l].y, (unsigned long long)y);
+                    l = ln;
                 } while (l != 0xFFu);
             }
         }
         __syncwarp();
         for (uint32_t l = lane; l < a.n; l += 32) {
-            uint64_t v = my_min[l];
+            const uint64_t v = my_min[l].y;
             if (v != ~0ULL)
                 atomicMin(reinterpret_cast<unsigned long long *>(a.sk + (size_t)g.read * a.n + l),
                           (a.rnd[l] & ~mask) | v);
         }
-        __syncwarp();
     }
 }
 
@@ -478,13 +437,9 @@ int build_filter_tables(nsmh_ctx *c) {
     if (e && *e) c->lambda_log2 = atoi(e) < 0 ? 0 : (atoi(e) > 8 ? 8 : atoi(e));
     e = getenv("NSMH_TILE_WORDS");
     if (e && *e && atoi(e) >= 32) c->tile_words = (uint32_t)atoi(e);
-    e = getenv("NSMH_SKETCH_VARIANT");
-    if (e && *e) c->sketch_variant = atoi(e) ? 1 : 0;
-    NSMH_TRY(c->d_ftab_hit.ensure(hit.size(), c->stream));
     NSMH_TRY(c->d_ftab_first.ensure(first.size(), c->stream));
     NSMH_TRY(c->d_ftab_next.ensure(next.size(), c->stream));
     NSMH_TRY(c->d_ftab_hit3.ensure(hit3.size(), c->stream));
-    NSMH_CK(cudaMemcpyAsync(c->d_ftab_hit.p, hit.data(), hit.size(), cudaMemcpyHostToDevice, c->stream));
     NSMH_CK(cudaMemcpyAsync(c->d_ftab_first.p, first.data(), first.size(), cudaMemcpyHostToDevice, c->stream));
     NSMH_CK(cudaMemcpyAsync(c->d_ftab_next.p, next.data(), next.size(), cudaMemcpyHostToDevice, c->stream));
     NSMH_CK(cudaMemcpyAsync(c->d_ftab_hit3.p, hit3.data(), hit3.size(), cudaMemcpyHostToDevice, c->stream));
@@ -496,13 +451,11 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
                  DevBuf &cub_tmp, int mode, cudaStream_t s, uint32_t *launches, cudaEvent_t ev0,
                  cudaEvent_t ev1) {
     if (rs.num_reads == 0) return NSMH_OK;
-    constexpr int WARPS = 8;
     SketchArgs a;
     a.off = rs.d_offsets();
     a.W = rs.packed.as<uint32_t>();
     a.sk = d_sketches;
     a.rnd = c->d_rand.as<uint64_t>();
-    a.ftab_hit = c->d_ftab_hit.as<uint8_t>();
     a.ftab_first = c->d_ftab_first.as<uint8_t>();
     a.ftab_next = c->d_ftab_next.as<uint8_t>();
     a.ftab_hit3 = c->d_ftab_hit3.as<uint8_t>();
@@ -511,12 +464,14 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     a.k = c->k;
     a.n = c->n;
     a.lambda_log2 = c->lambda_log2;
-    a.tile_words = c->tile_words;
+    a.tile_words = (c->tile_words + 63) & ~63u;     // the filter kernel takes 64 words per step
+    if (a.tile_words > 4096) a.tile_words = 4096;
 
     // tile_start: [0..n_reads] exclusive scan, followed by the per-read counts
     // upper bound on the number of tiles: ceil(words_i / T) <= words_i / T + 1 per read, and the
     // reads' word ranges overlap by at most one word each
-    const size_t max_tiles = (size_t)((rs.num_words + rs.num_reads) / c->tile_words) + rs.num_reads + 1;
+    // (a read's word range is widened by at most 4 words: shared boundary word + 16-byte alignment)
+    const size_t max_tiles = (size_t)((rs.num_words + 4 * (uint64_t)rs.num_reads) / a.tile_words) + rs.num_reads + 1;
     NSMH_TRY(tile_start.ensure((((size_t)rs.num_reads + 1) * 2 + max_tiles) * sizeof(uint32_t), s));
     uint32_t *cnt = tile_start.as<uint32_t>() + rs.num_reads + 1;
     uint32_t *ts = tile_start.as<uint32_t>();
@@ -543,26 +498,18 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     if (mode == 0) {
         static bool attr_set = false;
         if (!attr_set) {
-            NSMH_CK(cudaFuncSetAttribute(sketch_filter_kernel<WARPS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            NSMH_CK(cudaFuncSetAttribute(sketch_filter1_kernel<WARPS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            NSMH_CK(cudaFuncSetAttribute(sketch_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             attr_set = true;
         }
-        const size_t common = (size_t)c->n * 8 + (size_t)WARPS * c->n * 8 + (size_t)(kFilterMaxBits + 1) * c->n + 16;
-        int occ = 0;
-        if (c->sketch_variant == 0) {
-            const size_t smem = kFilter3TabSize + (2 << kFilter3MaxBits) + common + (size_t)WARPS * c->n * 8 +
-                                WARPS * 512 * sizeof(uint16_t);
-            NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_filter_kernel<WARPS>, WARPS * 32, smem));
-            if (occ < 1) return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
-            sketch_filter_kernel<WARPS><<<c->num_sms * occ, WARPS * 32, smem, s>>>(a);
-        } else {
-            const size_t smem = 2 * (size_t)kFilterTabSize + common;
-            NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_filter1_kernel<WARPS>, WARPS * 32, smem));
-            if (occ < 1) return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
-            sketch_filter1_kernel<WARPS><<<c->num_sms * occ, WARPS * 32, smem, s>>>(a);
-        }
+        // one block per SM, as many warps as the shared memory holds (each warp owns a tile)
+        const FilterSmem L(c->n, a.tile_words);
+        const size_t budget = 226 * 1024;
+        if (L.tab_bytes + 8 * L.warp_bytes > budget)
+            return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
+        int warps = (int)std::min<size_t>(24, (budget - L.tab_bytes) / L.warp_bytes);
+        warps &= ~3;
+        const size_t smem = L.tab_bytes + (size_t)warps * L.warp_bytes;
+        sketch_filter_kernel<<<c->num_sms, warps * 32, smem, s>>>(a);
         ++*launches;
         NSMH_CK(cudaGetLastError());
         if (ev1) NSMH_CK(cudaEventRecord(ev1, s));
