@@ -40,7 +40,7 @@ struct DevBuf {
 
 // ------------------------------------------------------------- constants --
 constexpr int kWordBases = 16;          // bases per packed u32 word, first base in bits 31..30
-constexpr int kTileWords = 1024;        // default words (16384 k-mer start positions) per sketch tile
+constexpr int kTileWords = 832;         // default words (13312 k-mer start positions) per sketch tile: 32 warps per SM fit
 constexpr int kFilterMaxBits = 12;      // largest prefix width b of the sketch filter tables
 constexpr int kFilterTabSize = 1 << (kFilterMaxBits + 1);  // table for b lives at [2^b, 2^(b+1))
 constexpr int kFilterLambdaLog2 = 3;    // default: b = floor(log2(#kmers)) - 3  => 8..16 k-mers expected per bucket

@@ -47,6 +47,7 @@ struct SketchArgs {
     const uint64_t *rnd;        // [n]
     const uint8_t *ftab_first, *ftab_next, *ftab_hit3;
     unsigned long long *counters;   // [0] fix-ups
+    unsigned int *tile_queue;       // next tile to hand out (filter kernel: warps take tiles dynamically)
     uint32_t n_reads, k, n;
     int lambda_log2;
     uint32_t tile_words;        // words (16 k-mer starts each) per tile
@@ -173,7 +174,7 @@ struct FilterSmem {
 
 // ---- filter kernel ------------------------------------------------------------------
 // a.tile_words is a multiple of 64: in every step a lane owns two adjacent words = 32 positions.
-__global__ void __launch_bounds__(768)
+__global__ void __launch_bounds__(1024)
 sketch_filter_kernel(SketchArgs a) {
     extern __shared__ __align__(16) uint8_t smem[];
     const FilterSmem L(a.n, a.tile_words);
@@ -182,7 +183,7 @@ sketch_filter_kernel(SketchArgs a) {
     uint8_t *s_next = s_first + (2 << kFilter3MaxBits);       // (kFilterMaxBits+1) * n
     uint64_t *s_rlo = reinterpret_cast<uint64_t *>(smem + ((kFilter3TabSize + (2 << kFilter3MaxBits) +
                                                             (size_t)(kFilterMaxBits + 1) * a.n + 7) & ~(size_t)7));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *mine = smem + L.tab_bytes + (size_t)warp * L.warp_bytes;
     uint32_t *sw = reinterpret_cast<uint32_t *>(mine);                      // staged words
     uint32_t *own = sw + L.stage_words;                                     // hit masks, [step][lane]
@@ -209,7 +210,15 @@ sketch_filter_kernel(SketchArgs a) {
     const int kshift = 64 - 2 * (int)a.k;
     uint32_t phase = 0;
 
-    for (uint32_t tile = blockIdx.x * warps + warp; tile < num_tiles; tile += gridDim.x * warps) {
+    // Tiles are handed out dynamically (their sizes differ by orders of magnitude, e.g. with
+    // ultra-long reads).  The next index is requested while the current tile is processed,
+    // so the atomic's latency is never waited for.
+    uint32_t my_next = 0;
+    if (lane == 0) my_next = atomicAdd(a.tile_queue, 1u);
+    for (;;) {
+        const uint32_t tile = __shfl_sync(0xffffffffu, my_next, 0);
+        if (tile >= num_tiles) break;
+        if (lane == 0) my_next = atomicAdd(a.tile_queue, 1u);
         const TileGeom g = tile_geom(a, tile);
         const uint32_t nw = (uint32_t)(g.w_end - g.w_begin);
         // ---- stage the tile: words [w_begin, w_end + 3) rounded up to 16 bytes, one bulk copy ----
@@ -472,13 +481,15 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     // reads' word ranges overlap by at most one word each
     // (a read's word range is widened by at most 4 words: shared boundary word + 16-byte alignment)
     const size_t max_tiles = (size_t)((rs.num_words + 4 * (uint64_t)rs.num_reads) / a.tile_words) + rs.num_reads + 1;
-    NSMH_TRY(tile_start.ensure((((size_t)rs.num_reads + 1) * 2 + max_tiles) * sizeof(uint32_t), s));
+    NSMH_TRY(tile_start.ensure((((size_t)rs.num_reads + 1) * 2 + max_tiles + 1) * sizeof(uint32_t), s));
     uint32_t *cnt = tile_start.as<uint32_t>() + rs.num_reads + 1;
     uint32_t *ts = tile_start.as<uint32_t>();
     uint32_t *tile_read = cnt + rs.num_reads + 1;
     a.tile_start = ts;
     a.tile_read = tile_read;
+    a.tile_queue = tile_read + max_tiles;      // per call: concurrent online queries have their own
     NSMH_CK(cudaMemsetAsync(cnt + rs.num_reads, 0, sizeof(uint32_t), s));
+    NSMH_CK(cudaMemsetAsync(a.tile_queue, 0, sizeof(uint32_t), s));
     const uint64_t total = (uint64_t)rs.num_reads * c->n;
     int blocks = (int)((total + 255) / 256 < (uint64_t)c->num_sms * 8 ? (total + 255) / 256
                                                                        : (uint64_t)c->num_sms * 8);
@@ -506,7 +517,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         const size_t budget = 226 * 1024;
         if (L.tab_bytes + 8 * L.warp_bytes > budget)
             return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
-        int warps = (int)std::min<size_t>(24, (budget - L.tab_bytes) / L.warp_bytes);
+        int warps = (int)std::min<size_t>(32, (budget - L.tab_bytes) / L.warp_bytes);
         warps &= ~3;
         const size_t smem = L.tab_bytes + (size_t)warps * L.warp_bytes;
         sketch_filter_kernel<<<c->num_sms, warps * 32, smem, s>>>(a);
