@@ -41,6 +41,10 @@ struct ListRef {
 
 // The n tables, probed for a batch of query sketches.  probe_items_kernel resolves every
 // (query, hash) item and stores {val, group size}; everything downstream reads those.
+__device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+
 struct ProbeSrc {
     const uint64_t *qsk;     // [nq][n]
     const Slot *slots;
@@ -48,11 +52,45 @@ struct ProbeSrc {
     uint32_t *pval, *pcnt;   // [nq][n] probe results: the id / the start in ids, the group size
     uint64_t cap;
     uint32_t n;
+    // Probing is split in two so that the (random, DRAM-latency) bucket loads of several lists
+    // are in flight together: begin() issues the 32-byte load of the home bucket (both slots of
+    // one sector), finish() resolves the probe and only rarely has to move to the next bucket.
+    struct Pending {
+        uint64_t key, b;
+        uint64_t sa, sb, sc, sd;    // slot = {key, val | (cnt-1) << 32}, twice
+        uint32_t j;
+    };
+    __device__ __forceinline__ uint32_t subs() const { return n; }
+    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
+        Pending p;
+        p.j = j;
+        p.key = __ldg(qsk + (size_t)q * n + j);
+        p.b = p.key == kEmptyKey ? (cap >> 1) : slot_index(p.key, cap >> 1);   // key ~0 lives in the extra slot
+        ldg256(slots + (uint64_t)j * region_stride(cap) + 2 * p.b, p.sa, p.sb, p.sc, p.sd);
+        return p;
+    }
+    // group size (0 = absent) and val (the id itself for a group of one, else the start in ids)
+    __device__ __forceinline__ ListRef finish(Pending p) const {
+        const Slot *region = slots + (uint64_t)p.j * region_stride(cap);
+        const uint64_t nb = cap >> 1;
+        uint64_t hit = 0;
+        bool found = false;
+        for (;;) {
+            if (p.key == kEmptyKey || p.sa == p.key) { hit = p.sb; found = true; break; }
+            if (p.sa == kEmptyKey) break;
+            if (p.sc == p.key) { hit = p.sd; found = true; break; }
+            if (p.sc == kEmptyKey) break;
+            p.b = p.b + 1 == nb ? 0 : p.b + 1;
+            ldg256(region + 2 * p.b, p.sa, p.sb, p.sc, p.sd);
+        }
+        ListRef r;
+        r.c = found ? (uint32_t)(hit >> 32) + 1u : 0u;     // untouched extra slot: 0xFFFFFFFF + 1 = 0
+        r.one = (uint32_t)hit;
+        r.ptr = r.c == 1 ? nullptr : ids + r.one;
+        return r;
+    }
+    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
 };
-
-__device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-}
 
 constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
 constexpr int kProbeRows = 256;    // queries per block = threads per block
@@ -579,7 +617,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     const size_t smem = (size_t)kLookupWarps * kWarpWords * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) {
-        NSMH_CK(cudaFuncSetAttribute(count_kernel<StoredSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        NSMH_CK(cudaFuncSetAttribute(count_kernel<ProbeSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NSMH_CK(cudaFuncSetAttribute(count_kernel<PartsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
@@ -670,10 +708,19 @@ static int probe_all(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32
     return NSMH_OK;
 }
 
-// Query nq device-resident sketches [nq][n] against the tables.
+// Query nq device-resident sketches [nq][n] against the tables: probing is fused into the
+// counting kernel (no probe results in HBM).
 int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s) {
-    StoredSrc src;
-    NSMH_TRY(probe_all(c, ws, d_qsketch, nq, s, src));
+    Tables &T = c->tables;
+    if (!T.built) return fail(NSMH_ESTATE, "query: tables not built (call nsmh_build)");
+    ProbeSrc src;
+    src.qsk = d_qsketch;
+    src.slots = T.slots.as<Slot>();
+    src.ids = T.ids.as<uint32_t>();
+    src.pval = nullptr;
+    src.pcnt = nullptr;
+    src.cap = T.cap;
+    src.n = c->n;
     return count_and_emit(c, ws, src, c->n, nq, s);
 }
 
