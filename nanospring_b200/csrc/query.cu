@@ -106,12 +106,13 @@ __global__ void __launch_bounds__(kProbeRows, 4)
 probe_items_kernel(ProbeSrc src, uint32_t nq) {
     const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
     const uint32_t colgroups = (src.n + kProbeCols - 1) / kProbeCols;
-    const uint64_t units = (uint64_t)chunks * colgroups;
+    const uint32_t units = chunks * colgroups;      // nq * n < 2^32 (probe_all)
     const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
     const bool vec = (src.n & 3) == 0;      // rows are sector aligned
-    for (uint64_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t q = (uint32_t)(u % chunks) * kProbeRows + threadIdx.x;
-        const uint32_t l0 = (uint32_t)(u / chunks) * kProbeCols;
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const uint32_t cg = u / chunks;
+        const uint32_t q = (u - cg * chunks) * kProbeRows + threadIdx.x;
+        const uint32_t l0 = cg * kProbeCols;
         if (q >= nq) continue;
         const size_t t0 = (size_t)q * src.n + l0;
         uint64_t key[kProbeCols];

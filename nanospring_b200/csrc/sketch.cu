@@ -58,15 +58,16 @@ __device__ __forceinline__ uint64_t kmer_mask(uint32_t k) { return (1ULL << (2 *
 // ---- row init + tile counts ---------------------------------------------------
 __global__ void __launch_bounds__(256)
 sketch_init_kernel(SketchArgs a, uint32_t *__restrict__ tile_cnt) {
-    const uint64_t total = (uint64_t)a.n_reads * a.n;
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total;
-         t += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t i = (uint32_t)(t / a.n);
-        uint32_t l = (uint32_t)(t - (uint64_t)i * a.n);
-        uint64_t b0 = a.off[i], len = a.off[i + 1] - b0;
+    // one warp per read: rows are written with coalesced stores, no per-element division
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.n_reads; i += warps) {
+        const uint64_t b0 = a.off[i], len = a.off[i + 1] - b0;
         // ReadFilter.cpp:119-124: untouched (zero) when len-k+1 < 0, all-ones otherwise
-        a.sk[t] = (len + 1 < a.k) ? 0ULL : ~0ULL;
-        if (l == 0) {
+        const uint64_t v = (len + 1 < a.k) ? 0ULL : ~0ULL;
+        uint64_t *row = a.sk + (size_t)i * a.n;
+        for (uint32_t l = lane; l < a.n; l += 32) row[l] = v;
+        if (lane == 0) {
             uint32_t tiles = 0;
             if (len >= a.k) {
                 uint64_t nk = len - a.k + 1;
@@ -490,9 +491,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     a.tile_queue = tile_read + max_tiles;      // per call: concurrent online queries have their own
     NSMH_CK(cudaMemsetAsync(cnt + rs.num_reads, 0, sizeof(uint32_t), s));
     NSMH_CK(cudaMemsetAsync(a.tile_queue, 0, sizeof(uint32_t), s));
-    const uint64_t total = (uint64_t)rs.num_reads * c->n;
-    int blocks = (int)((total + 255) / 256 < (uint64_t)c->num_sms * 8 ? (total + 255) / 256
-                                                                       : (uint64_t)c->num_sms * 8);
+    const int blocks = (int)std::min<uint64_t>(((uint64_t)rs.num_reads + 7) / 8, (uint64_t)c->num_sms * 8);
     sketch_init_kernel<<<blocks, 256, 0, s>>>(a, cnt);
     ++*launches;
     NSMH_CK(cudaGetLastError());

@@ -64,125 +64,118 @@ __device__ __forceinline__ void slot_cas(Slot *p, uint64_t exp_lo, uint64_t exp_
         : "memory");
 }
 
+// both slots of a bucket as they are now (256-bit L2-coherent load)
+__device__ __forceinline__ void bucket_now(const Slot *p, uint64_t &k0, uint64_t &v0, uint64_t &k1, uint64_t &v1) {
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(k0), "=l"(v0), "=l"(k1), "=l"(v1) : "l"(p) : "memory");
+}
+
 __device__ __forceinline__ uint64_t slot_key_now(const Slot *p) {
     uint64_t k;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(k) : "l"(&p->key) : "memory");
     return k;
 }
 
-// Every thread walks its own stream of (row, column) items as a small state machine: one
-// loop iteration = at most one probe step (one bucket fetch + one atomic) of the thread's
-// current item, and a thread whose item is finished moves on to its next item without
-// waiting for the other lanes.  A warp therefore pays (about) the AVERAGE probe length per
-// item instead of the longest probe sequence among its 32 lanes, which is what a
-// per-item loop costs under SIMT when every step is a DRAM / L2-atomic round trip.
-// Buckets are the two slots of one 32-byte sector.  The kernel is bound by the L2 atomic
-// rate (tools/micro/atom_bench.cu: ~50 G atomics/s whatever the width), so a step is
-// exactly one atomic and nothing is loaded beforehand.
+// A block takes a unit of 256 rows x 4 adjacent columns; a thread owns the 4 keys of one row
+// (one 32-byte sector of the sketch matrix) and works through them as a small state machine:
+// one loop iteration = one compare-and-swap of the thread's current key, and a thread whose
+// key is placed moves on to its next key without waiting for the other lanes.  A warp
+// therefore pays the longest SUM of probe steps over 4 keys among its lanes, not 4 times the
+// longest probe sequence, and the loop body stays small (the kernel is bound by the L2
+// atomic rate, ~50 G atomics/s whatever their width: tools/micro/atom_bench.cu).
+// Buckets are the two slots of one 32-byte sector.
 __global__ void __launch_bounds__(kBuildRows)
 table_insert_kernel(BuildArgs a) {
     __shared__ unsigned int s_count[2];
     const int lane = threadIdx.x & 31;
     const uint32_t chunks = (a.rows + kBuildRows - 1) / kBuildRows;
     const uint32_t colgroups = (a.n + kBuildCols - 1) / kBuildCols;
-    const uint64_t units = (uint64_t)chunks * colgroups;
+    const uint32_t units = chunks * colgroups;     // < 2^32: checked by build_tables
     const uint64_t nb = a.cap >> 1;
     const uint64_t stride = region_stride(a.cap);
     const size_t seg0 = (size_t)blockIdx.x * a.seg_cap;
     if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
     __syncthreads();
 
-    uint64_t u = blockIdx.x;              // next unit to load
-    uint64_t nk[kBuildCols];              // its keys, prefetched
-    auto prefetch = [&](uint64_t uu) {
-        const uint32_t row = (uint32_t)(uu % chunks) * kBuildRows + threadIdx.x;
-        const uint32_t l0 = (uint32_t)(uu / chunks) * kBuildCols;
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const uint32_t cg = u / chunks;
+        const uint32_t row = (u - cg * chunks) * kBuildRows + threadIdx.x;
+        const uint32_t l0 = cg * kBuildCols;
+        const uint32_t nj = row < a.rows ? min((uint32_t)kBuildCols, a.n - l0) : 0u;   // keys of this thread
+        uint64_t keys[kBuildCols];
 #pragma unroll
         for (int j = 0; j < kBuildCols; ++j)
-            nk[j] = (uu < units && row < a.rows && l0 + j < a.n) ? __ldg(a.sk + (size_t)row * a.n + l0 + j) : kEmptyKey;
-    };
-    prefetch(u);
-    uint64_t keys[kBuildCols];
-    uint32_t row = 0, l0 = 0;
-    int j = kBuildCols;
-    bool finished = false, active = false;
-    uint64_t key = 0, b = 0;
-    int sub = 0;
-    Slot *region = a.slots;
-
-    for (;;) {
-        uint32_t rank = 0, s = 0;
-        bool completed = false;
-        if (!active && !finished) {
-            if (j == kBuildCols) {
-                if (u >= units) finished = true;
-                else {
-#pragma unroll
-                    for (int t = 0; t < kBuildCols; ++t) keys[t] = nk[t];
-                    row = (uint32_t)(u % chunks) * kBuildRows + threadIdx.x;
-                    l0 = (uint32_t)(u / chunks) * kBuildCols;
-                    u += gridDim.x;
-                    prefetch(u);
-                    j = 0;
+            keys[j] = (uint32_t)j < nj ? __ldg(a.sk + (size_t)row * a.n + l0 + j) : 0;
+        uint32_t j = 0;
+        bool fresh = true;        // the current key has not been probed yet
+        uint64_t key = 0, b = 0;
+        Slot *region = a.slots;
+        for (;;) {
+            uint32_t rank = 0, s = 0;
+            bool completed = false;
+            if (j < nj) {
+                if (fresh) {
+                    key = j == 0 ? keys[0] : j == 1 ? keys[1] : j == 2 ? keys[2] : keys[3];
+                    region = a.slots + (uint64_t)(l0 + j) * stride;
+                    b = slot_index(key, nb);
+                    fresh = false;
                 }
-            }
-            if (!finished) {
-                key = j == 0 ? keys[0] : j == 1 ? keys[1] : j == 2 ? keys[2] : keys[3];
-                const uint32_t l = l0 + j;
-                ++j;
-                if (row < a.rows && l < a.n) {
-                    region = a.slots + (uint64_t)l * stride;
-                    if (key == kEmptyKey) {
-                        // slots start as all-ones: the count field holds (group size - 1), wrapping from ~0
-                        rank = atomicAdd(&region[a.cap].cntm1, 1u) + 1u;
-                        if (rank == 0) region[a.cap].val = row;
-                        s = (uint32_t)((uint64_t)l * stride + a.cap);
-                        completed = true;
+                Slot *p;
+                if (key == kEmptyKey) {
+                    // the extra slot; slots start as all-ones: the count field holds
+                    // (group size - 1), wrapping from ~0
+                    p = region + a.cap;
+                    rank = atomicAdd(&p->cntm1, 1u) + 1u;
+                    if (rank == 0) p->val = row;
+                    completed = true;
+                } else {
+                    // peek at the bucket (one 32-byte load, L2-coherent), then one atomic on the slot
+                    // that holds the key or is the first free one.  The peek may be stale; the
+                    // compare-and-swap decides.  (A load that misses L2 followed by an atomic that
+                    // hits is faster than an atomic that misses: tools/micro/atom_bench.cu.)
+                    uint64_t k0, v0, k1, v1;
+                    bucket_now(region + 2 * b, k0, v0, k1, v1);
+                    const int t = (k0 == key || k0 == kEmptyKey) ? 0 : (k1 == key || k1 == kEmptyKey) ? 1 : 2;
+                    p = region + 2 * b + (t & 1);
+                    if (t == 2) {
+                        b = b + 1 == nb ? 0 : b + 1;
                     } else {
-                        b = slot_index(key, nb);
-                        sub = 0;
-                        active = true;
+                        uint64_t cur = t ? k1 : k0;
+                        if (cur == kEmptyKey) {
+                            uint64_t old_hi;
+                            slot_cas(p, ~0ULL, ~0ULL, key, (uint64_t)row, cur, old_hi);   // {key, val = id, cnt-1 = 0}
+                            if (cur == kEmptyKey) completed = true;                  // rank 0: first of its group
+                        }
+                        if (!completed && cur == key) {
+                            rank = atomicAdd(&p->cntm1, 1u) + 1u;
+                            completed = true;
+                        }
+                        // otherwise another key took the slot meanwhile: look again
                     }
                 }
+                if (completed) {
+                    s = (uint32_t)(p - a.slots);
+                    ++j;
+                    fresh = true;
+                }
             }
+            // warp-aggregated append of the members that were not first in their group
+            const uint32_t m = __ballot_sync(0xffffffffu, completed && rank >= 1);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&s_count[0], (unsigned int)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (completed && rank >= 1) {
+                    const size_t pos = seg0 + base + __popc(m & ((1u << lane) - 1));
+                    a.m_slot[pos] = s;
+                    a.m_id[pos] = row;
+                    a.m_rank[pos] = rank;
+                    if (rank == 1) a.g_slot[seg0 + atomicAdd(&s_count[1], 1u)] = s;
+                }
+            }
+            if (__all_sync(0xffffffffu, j >= nj)) break;
         }
-        if (active) {
-            // no look before the leap: the compare-and-swap itself returns what the slot holds, so an
-            // item costs one L2 atomic when its slot is free (the common case at load <= 0.5)
-            Slot *p = region + 2 * b + sub;
-            uint64_t old_lo, old_hi;
-            slot_cas(p, ~0ULL, ~0ULL, key, (uint64_t)row, old_lo, old_hi);   // {key, val = id, cnt-1 = 0}
-            if (old_lo == kEmptyKey) {
-                rank = 0;
-                completed = true;
-            } else if (old_lo == key) {
-                rank = atomicAdd(&p->cntm1, 1u) + 1u;
-                completed = true;
-            } else {
-                sub ^= 1;
-                if (sub == 0) b = b + 1 == nb ? 0 : b + 1;
-            }
-            if (completed) {
-                s = (uint32_t)(p - a.slots);
-                active = false;
-            }
-        }
-        // warp-aggregated append of the members that were not first in their group
-        const uint32_t m = __ballot_sync(0xffffffffu, completed && rank >= 1);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(&s_count[0], (unsigned int)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (completed && rank >= 1) {
-                const size_t pos = seg0 + base + __popc(m & ((1u << lane) - 1));
-                a.m_slot[pos] = s;
-                a.m_id[pos] = row;
-                a.m_rank[pos] = rank;
-                if (rank == 1) a.g_slot[seg0 + atomicAdd(&s_count[1], 1u)] = s;
-            }
-        }
-        if (__all_sync(0xffffffffu, finished && !active)) break;
     }
     __syncthreads();
     if (threadIdx.x < 2) a.seg_count[2 * blockIdx.x + threadIdx.x] = s_count[threadIdx.x];
@@ -252,7 +245,7 @@ int build_tables(nsmh_ctx *c) {
     const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);   // even; load factor <= 0.5
     const uint64_t nslots = (uint64_t)n * region_stride(cap);
     const uint64_t items = (uint64_t)rows * n;
-    if (nslots >= (1ULL << 32) || items >= (1ULL << 32))
+    if (nslots >= (1ULL << 32) || items >= (1ULL << 32) - (1ULL << 22))
         return fail(NSMH_EINVAL, "build: reads*n too large for 32-bit slot indices");
     T.cap = cap;
     T.table_reads = rows;
