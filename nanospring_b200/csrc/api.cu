@@ -180,6 +180,8 @@ int nsmh_create(uint32_t k, uint32_t n, uint32_t thr, const uint64_t *rand_numbe
         for (auto &ev : c->ev)
             if ((e = cudaEventCreate(&ev)) != cudaSuccess) { rc = cuda_fail(e, "event", __FILE__, __LINE__); break; }
         if (rc) break;
+        if ((e = cudaEventCreateWithFlags(&c->ev_order, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(e, "event", __FILE__, __LINE__); break; }
+        if ((e = cudaEventCreateWithFlags(&c->ev_cleared, cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(e, "event", __FILE__, __LINE__); break; }
         // keep freed blocks in the pool: the bench re-runs the same sizes every step
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -223,7 +225,10 @@ int nsmh_destroy(nsmh_handle h) {
         if (h->reads.external_offsets) { h->reads.offsets.p = nullptr; h->reads.offsets.cap = 0; }
         h->reads.release(s);
         if (s) cudaStreamSynchronize(s);
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
         for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
+        if (h->ev_order) cudaEventDestroy(h->ev_order);
+        if (h->ev_cleared) cudaEventDestroy(h->ev_cleared);
         if (h->stream) cudaStreamDestroy(h->stream);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         cudaGetLastError();
@@ -375,6 +380,7 @@ int nsmh_sketch(nsmh_handle c) {
     c->tables.built = false;
     c->bulk_valid = false;
     NSMH_TRY(c->sketches.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream));
+    NSMH_TRY(preclear_tables(c, c->reads.num_reads));
     NSMH_CK(cudaEventRecord(c->ev[2], c->stream));
     NSMH_TRY(sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp,
                           c->sketch_mode, c->stream, &c->launches, c->ev[4], c->ev[5]));

@@ -152,6 +152,9 @@ struct nsmh_ctx {
     const uint64_t *table_sketches = nullptr;   // rows the tables are built from
     uint32_t table_reads = 0, id_base = 0;
     nsmh::Tables tables;
+    cudaEvent_t ev_order = nullptr, ev_cleared = nullptr;
+    uint32_t precleared_rows = 0;   // tables already cleared for this many rows (preclear_tables)
+    void *precleared_ptr = nullptr;
     nsmh::DevBuf build_multi;   // build scratch: members / groups of keys shared by several reads
     nsmh::DevBuf build_tmp;
 
@@ -194,6 +197,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
 
 // ---- table.cu ----------------------------------------------------------------
 int build_tables(nsmh_ctx *c);
+int preclear_tables(nsmh_ctx *c, uint32_t rows);
 int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
 
 // ---- query.cu ----------------------------------------------------------------

@@ -304,55 +304,72 @@ sketch_filter_kernel(SketchArgs a) {
 }
 
 // ---- exact fix-up: (read, hash) pairs that no k-mer matched on the filter prefix ----
-// One warp per read checks the row; every missing hash is recomputed over all k-mers of
-// the read, 512 positions per warp step (coalesced word loads, 16 k-mers per lane).
+// Pass 1 streams the sketch matrix once and lists the entries that still hold the initial
+// all-ones value; pass 2 recomputes each listed entry over all k-mers of its read, one warp
+// per entry, 512 positions per warp step (coalesced word loads, 16 k-mers per lane).
 __global__ void __launch_bounds__(256)
-sketch_fixup_kernel(SketchArgs a) {
+sketch_missing_kernel(SketchArgs a, uint32_t *__restrict__ list, unsigned int *__restrict__ count) {
     const int lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    const uint64_t total = (uint64_t)a.n_reads * a.n;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t rounds = (total + stride - 1) / stride;
+    uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (uint64_t r = 0; r < rounds; ++r, t += stride) {     // whole warps stay in the loop for the ballot
+        const bool miss = t < total && a.sk[t] == ~0ULL;
+        const uint32_t m = __ballot_sync(0xffffffffu, miss);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(count, (unsigned int)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (miss) list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)t;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ count) {
+    __shared__ uint64_t s_best[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint64_t mask = kmer_mask(a.k);
     const int kshift = 64 - 2 * (int)a.k;
-    for (uint32_t i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < a.n_reads; i += warps) {
+    const uint32_t todo = *count;
+    for (uint32_t e = blockIdx.x; e < todo; e += gridDim.x) {      // one block per entry
+        const uint32_t t = list[e];
+        const uint32_t i = t / a.n, lf = t - i * a.n;
         const uint64_t rb = a.off[i], len = a.off[i + 1] - rb;
-        if (len < a.k) continue;
+        if (len < a.k) continue;          // len == k-1: all-ones is the reference's value (ReadFilter.cpp:119-124)
         TileGeom g;
         g.read = i;
         g.rb = rb;
         g.nk = len - a.k + 1;
         g.w_begin = rb / kWordBases;
         g.w_end = (rb + g.nk - 1) / kWordBases + 1;
-        for (uint32_t l0 = 0; l0 < a.n; l0 += 32) {
-            uint32_t l = l0 + lane;
-            bool miss = l < a.n && a.sk[(size_t)i * a.n + l] == ~0ULL;
-            uint32_t todo = __ballot_sync(0xffffffffu, miss);
-            while (todo) {
-                const uint32_t lf = l0 + (__ffs(todo) - 1);
-                todo &= todo - 1;
-                const uint64_t r = a.rnd[lf], rlo = r & mask;
-                uint64_t best = ~0ULL;
-                for (uint64_t wb = g.w_begin; wb < g.w_end; wb += 32) {
-                    const uint64_t w = wb + lane;
-                    if (w >= g.w_end) continue;
-                    int lo, hi;
-                    valid_range(g, w, lo, hi);
-                    const uint32_t w0 = __ldg(a.W + w), w1 = __ldg(a.W + w + 1), w2 = __ldg(a.W + w + 2);
-                    for (int j = lo; j < hi; ++j) {
-                        uint32_t h32;
-                        const uint64_t y = kmer_at(w0, w1, w2, j, kshift, h32) ^ rlo;
-                        best = y < best ? y : best;
-                    }
-                }
-#pragma unroll
-                for (int o = 16; o; o >>= 1) {
-                    uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
-                    best = other < best ? other : best;
-                }
-                if (lane == 0) {
-                    a.sk[(size_t)i * a.n + lf] = (r & ~mask) | best;
-                    atomicAdd(a.counters, 1ULL);
-                }
+        const uint64_t r = a.rnd[lf], rlo = r & mask;
+        uint64_t best = ~0ULL;
+        for (uint64_t w = g.w_begin + threadIdx.x; w < g.w_end; w += blockDim.x) {
+            int lo, hi;
+            valid_range(g, w, lo, hi);
+            const uint32_t w0 = __ldg(a.W + w), w1 = __ldg(a.W + w + 1), w2 = __ldg(a.W + w + 2);
+            for (int j = lo; j < hi; ++j) {
+                uint32_t h32;
+                const uint64_t y = kmer_at(w0, w1, w2, j, kshift, h32) ^ rlo;
+                best = y < best ? y : best;
             }
         }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other < best ? other : best;
+        }
+        if (lane == 0) s_best[warp] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) best = s_best[w] < best ? s_best[w] : best;
+            a.sk[t] = (r & ~mask) | best;
+            atomicAdd(a.counters, 1ULL);
+        }
+        __syncthreads();
     }
 }
 
@@ -482,7 +499,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     // reads' word ranges overlap by at most one word each
     // (a read's word range is widened by at most 4 words: shared boundary word + 16-byte alignment)
     const size_t max_tiles = (size_t)((rs.num_words + 4 * (uint64_t)rs.num_reads) / a.tile_words) + rs.num_reads + 1;
-    NSMH_TRY(tile_start.ensure((((size_t)rs.num_reads + 1) * 2 + max_tiles + 1) * sizeof(uint32_t), s));
+    NSMH_TRY(tile_start.ensure((((size_t)rs.num_reads + 1) * 2 + max_tiles + 2) * sizeof(uint32_t), s));
     uint32_t *cnt = tile_start.as<uint32_t>() + rs.num_reads + 1;
     uint32_t *ts = tile_start.as<uint32_t>();
     uint32_t *tile_read = cnt + rs.num_reads + 1;
@@ -490,14 +507,18 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     a.tile_read = tile_read;
     a.tile_queue = tile_read + max_tiles;      // per call: concurrent online queries have their own
     NSMH_CK(cudaMemsetAsync(cnt + rs.num_reads, 0, sizeof(uint32_t), s));
-    NSMH_CK(cudaMemsetAsync(a.tile_queue, 0, sizeof(uint32_t), s));
+    NSMH_CK(cudaMemsetAsync(a.tile_queue, 0, 2 * sizeof(uint32_t), s));      // + the fix-up list length
     const int blocks = (int)std::min<uint64_t>(((uint64_t)rs.num_reads + 7) / 8, (uint64_t)c->num_sms * 8);
     sketch_init_kernel<<<blocks, 256, 0, s>>>(a, cnt);
     ++*launches;
     NSMH_CK(cudaGetLastError());
     size_t tmp_bytes = 0;
     NSMH_CK(cub_exclusive_sum_u32(nullptr, tmp_bytes, cnt, ts, (size_t)rs.num_reads + 1, s));
-    NSMH_TRY(cub_tmp.ensure(tmp_bytes, s));
+    // the same scratch buffer later holds the fix-up list (u32 per (read, hash) pair at worst)
+    const size_t list_off = (tmp_bytes + 255) & ~(size_t)255;
+    if ((uint64_t)rs.num_reads * c->n >= (1ULL << 32))
+        return fail(NSMH_EINVAL, "sketch: reads*n too large for 32-bit pair indices");
+    NSMH_TRY(cub_tmp.ensure(list_off + (size_t)rs.num_reads * c->n * sizeof(uint32_t) + 16, s));
     NSMH_CK(cub_exclusive_sum_u32(cub_tmp.p, tmp_bytes, cnt, ts, (size_t)rs.num_reads + 1, s));
     sketch_tile_map_kernel<<<(rs.num_reads + 255) / 256, 256, 0, s>>>(ts, rs.num_reads, tile_read);
     *launches += 3;
@@ -523,8 +544,11 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         ++*launches;
         NSMH_CK(cudaGetLastError());
         if (ev1) NSMH_CK(cudaEventRecord(ev1, s));
-        sketch_fixup_kernel<<<c->num_sms * 8, 256, 0, s>>>(a);
-        ++*launches;
+        uint32_t *miss_list = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(cub_tmp.p) + list_off);
+        unsigned int *miss_count = a.tile_queue + 1;
+        sketch_missing_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+        sketch_fixup_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+        *launches += 2;
         NSMH_CK(cudaGetLastError());
     } else {
         int occ = 0;

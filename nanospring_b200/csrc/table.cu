@@ -237,11 +237,33 @@ table_count_keys_kernel(const Slot *__restrict__ slots, uint64_t nslots, uint32_
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
 }
 
+// Clear the tables for `rows` reads on the copy stream, so that the (bandwidth-bound) memset
+// overlaps whatever the main stream does next (nsmh_sketch calls this before sketching: the
+// tables do not depend on the sketches until the first insert).
+int preclear_tables(nsmh_ctx *c, uint32_t rows) {
+    Tables &T = c->tables;
+    // an earlier clear may still run on the copy stream: nothing below may free the buffer under it
+    if (c->precleared_rows) NSMH_CK(cudaStreamWaitEvent(c->stream, c->ev_cleared, 0));
+    c->precleared_rows = 0;
+    const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);
+    const uint64_t nslots = (uint64_t)c->n * region_stride(cap);
+    if (rows == 0 || nslots >= (1ULL << 32)) return NSMH_OK;      // build_tables reports the error
+    NSMH_TRY(T.slots.ensure(nslots * sizeof(Slot), c->stream));
+    NSMH_CK(cudaEventRecord(c->ev_order, c->stream));              // allocation + earlier readers
+    NSMH_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
+    NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), c->copy_stream));
+    NSMH_CK(cudaEventRecord(c->ev_cleared, c->copy_stream));
+    c->precleared_rows = rows;
+    c->precleared_ptr = T.slots.p;
+    return NSMH_OK;
+}
+
 int build_tables(nsmh_ctx *c) {
     Tables &T = c->tables;
     cudaStream_t s = c->stream;
     const uint32_t n = c->n, rows = c->table_reads;
     T.built = false;
+    if (c->precleared_rows) NSMH_CK(cudaStreamWaitEvent(s, c->ev_cleared, 0));   // see preclear_tables
     const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);   // even; load factor <= 0.5
     const uint64_t nslots = (uint64_t)n * region_stride(cap);
     const uint64_t items = (uint64_t)rows * n;
@@ -262,7 +284,9 @@ int build_tables(nsmh_ctx *c) {
     NSMH_TRY(T.ids.ensure(ni * sizeof(uint32_t), s));
     NSMH_TRY(c->build_multi.ensure(std::max<size_t>(nseg, 1) * 4 * sizeof(uint32_t), s));
     NSMH_TRY(c->build_tmp.ensure((8 + 2 * (size_t)blocks) * sizeof(unsigned int), s));
-    NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), s));
+    if (!(c->precleared_rows == rows && c->precleared_ptr == T.slots.p))         // else: cleared during nsmh_sketch
+        NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), s));
+    c->precleared_rows = 0;
     NSMH_CK(cudaMemsetAsync(c->build_tmp.p, 0, 8 * sizeof(unsigned int), s));
     if (items) {
         BuildArgs a;
