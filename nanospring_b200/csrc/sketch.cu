@@ -327,14 +327,35 @@ sketch_missing_kernel(SketchArgs a, uint32_t *__restrict__ list, unsigned int *_
     }
 }
 
+// min over the k-mers starting in word w (positions [lo, hi)) of (k-mer ^ rlo), full 64 bits
+__device__ __forceinline__ uint64_t word_min64(const uint32_t *__restrict__ W, uint64_t w, int lo, int hi,
+                                               int kshift, uint64_t rlo) {
+    const uint32_t w0 = __ldg(W + w), w1 = __ldg(W + w + 1), w2 = __ldg(W + w + 2);
+    uint64_t best = ~0ULL;
+    for (int j = lo; j < hi; ++j) {
+        uint32_t h32;
+        const uint64_t y = kmer_at(w0, w1, w2, j, kshift, h32) ^ rlo;
+        best = y < best ? y : best;
+    }
+    return best;
+}
+
+// One warp per listed entry.  The scan works on the leading 32 bits of y = k-mer ^ rlo only
+// (one funnel shift, one xor, one 32-bit min per position): y32 is a prefix of y, so the
+// 64-bit minimum lies in a word whose 32-bit minimum equals the global one.  Every lane
+// remembers the word of its own minimum; the winning words are then redone in 64 bits.  If a
+// lane saw its minimum in two different words (a 32-bit tie, probability ~2^-32 per pair) the
+// entry falls back to a plain 64-bit scan, so the result is exact in every case.
 __global__ void __launch_bounds__(256)
 sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ count) {
-    __shared__ uint64_t s_best[8];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const uint64_t mask = kmer_mask(a.k);
     const int kshift = 64 - 2 * (int)a.k;
+    const int s_lo = 2 * (int)a.k > 32 ? 2 * (int)a.k - 32 : 0;      // y32 = y >> s_lo
+    const int sh = 2 * (int)a.k >= 32 ? 0 : 32 - 2 * (int)a.k;       // window >> sh = leading bits of the k-mer
     const uint32_t todo = *count;
-    for (uint32_t e = blockIdx.x; e < todo; e += gridDim.x) {      // one block per entry
+    for (uint32_t e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < todo; e += warps) {
         const uint32_t t = list[e];
         const uint32_t i = t / a.n, lf = t - i * a.n;
         const uint64_t rb = a.off[i], len = a.off[i + 1] - rb;
@@ -346,30 +367,67 @@ sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsig
         g.w_begin = rb / kWordBases;
         g.w_end = (rb + g.nk - 1) / kWordBases + 1;
         const uint64_t r = a.rnd[lf], rlo = r & mask;
-        uint64_t best = ~0ULL;
-        for (uint64_t w = g.w_begin + threadIdx.x; w < g.w_end; w += blockDim.x) {
-            int lo, hi;
-            valid_range(g, w, lo, hi);
-            const uint32_t w0 = __ldg(a.W + w), w1 = __ldg(a.W + w + 1), w2 = __ldg(a.W + w + 2);
-            for (int j = lo; j < hi; ++j) {
-                uint32_t h32;
-                const uint64_t y = kmer_at(w0, w1, w2, j, kshift, h32) ^ rlo;
-                best = y < best ? y : best;
+        const uint32_t t32 = (uint32_t)(rlo >> s_lo);
+        uint32_t m = 0xFFFFFFFFu;
+        uint64_t mw = 0;
+        bool has = false, tie = false;
+        // four words per lane and step, all loads first: the scan is a chain of L2 round trips
+        for (uint64_t wb = g.w_begin + lane; wb < g.w_end; wb += 128) {
+            uint32_t w0[4], w1[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t w = wb + 32 * u;
+                const bool in = w < g.w_end;
+                w0[u] = in ? __ldg(a.W + w) : 0u;
+                w1[u] = in ? __ldg(a.W + w + 1) : 0u;
             }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint64_t w = wb + 32 * u;
+                if (w >= g.w_end) break;
+                int lo, hi;
+                valid_range(g, w, lo, hi);
+                if (lo >= hi) continue;
+                uint32_t local = 0xFFFFFFFFu;
+                if (lo == 0 && hi == kWordBases) {
+#pragma unroll
+                    for (int j = 0; j < kWordBases; ++j) {
+                        const uint32_t x = j ? __funnelshift_l(w1[u], w0[u], 2 * j) : w0[u];
+                        local = min(local, (x >> sh) ^ t32);
+                    }
+                } else {
+                    for (int j = lo; j < hi; ++j) local = min(local, (__funnelshift_l(w1[u], w0[u], 2 * j) >> sh) ^ t32);
+                }
+                if (!has || local < m) { m = local; mw = w; tie = false; has = true; }
+                else if (local == m) tie = true;
+            }
+        }
+        uint32_t gm = has ? m : 0xFFFFFFFFu;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) gm = min(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        const bool cand = has && m == gm;
+        uint64_t best = ~0ULL;
+        if (__any_sync(0xffffffffu, cand && tie)) {
+            for (uint64_t w = g.w_begin + lane; w < g.w_end; w += 32) {
+                int lo, hi;
+                valid_range(g, w, lo, hi);
+                const uint64_t v = word_min64(a.W, w, lo, hi, kshift, rlo);
+                best = v < best ? v : best;
+            }
+        } else if (cand) {
+            int lo, hi;
+            valid_range(g, mw, lo, hi);
+            best = word_min64(a.W, mw, lo, hi, kshift, rlo);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
-            uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
+            const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
             best = other < best ? other : best;
         }
-        if (lane == 0) s_best[warp] = best;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < 8; ++w) best = s_best[w] < best ? s_best[w] : best;
+        if (lane == 0) {
             a.sk[t] = (r & ~mask) | best;
             atomicAdd(a.counters, 1ULL);
         }
-        __syncthreads();
     }
 }
 
@@ -538,7 +596,6 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         if (L.tab_bytes + 8 * L.warp_bytes > budget)
             return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
         int warps = (int)std::min<size_t>(32, (budget - L.tab_bytes) / L.warp_bytes);
-        warps &= ~3;
         const size_t smem = L.tab_bytes + (size_t)warps * L.warp_bytes;
         sketch_filter_kernel<<<c->num_sms, warps * 32, smem, s>>>(a);
         ++*launches;
