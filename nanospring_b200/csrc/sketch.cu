@@ -551,6 +551,10 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     a.lambda_log2 = c->lambda_log2;
     a.tile_words = (c->tile_words + 63) & ~63u;     // the filter kernel takes 64 words per step
     if (a.tile_words > 4096) a.tile_words = 4096;
+    // ... and keeps a tile per warp in shared memory: at least 8 warps per SM must fit
+    const size_t smem_budget = 226 * 1024;
+    while (a.tile_words > 64 && FilterSmem(c->n, a.tile_words).tab_bytes + 8 * FilterSmem(c->n, a.tile_words).warp_bytes > smem_budget)
+        a.tile_words = ((a.tile_words / 2) + 63) & ~63u;
 
     // tile_start: [0..n_reads] exclusive scan, followed by the per-read counts
     // upper bound on the number of tiles: ceil(words_i / T) <= words_i / T + 1 per read, and the
@@ -592,7 +596,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         }
         // one block per SM, as many warps as the shared memory holds (each warp owns a tile)
         const FilterSmem L(c->n, a.tile_words);
-        const size_t budget = 226 * 1024;
+        const size_t budget = smem_budget;
         if (L.tab_bytes + 8 * L.warp_bytes > budget)
             return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
         int warps = (int)std::min<size_t>(32, (budget - L.tab_bytes) / L.warp_bytes);

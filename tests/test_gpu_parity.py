@@ -250,3 +250,148 @@ def test_large_roundtrip_properties():
     fwd = set(zip(owner.tolist(), ids.tolist()))
     assert all((j, i) in fwd for (i, j) in fwd)                        # symmetric
     f.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# Tests aimed at the internals of the sm_100a kernels (tile staging, filter levels, fix-up,
+# bucketed tables, the three lookup paths).  All of them compare with the oracle bit for bit.
+def _mk_reads(seqs):
+    return ReadData.from_reads(seqs)
+
+
+def _random_seq(rng, n):
+    return rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n).tobytes()
+
+
+@pytest.mark.parametrize("tile_words", [64, 128, 640, 4096])
+def test_tile_sizes_and_alignment(orc, monkeypatch, tile_words):
+    """Tiles start on 16-byte boundaries of the packed stream and are staged with one bulk copy:
+    reads that start at every word offset, lengths around the tile size, many tiles per read."""
+    monkeypatch.setenv("NSMH_TILE_WORDS", str(tile_words))
+    k, n, thr = 23, 60, 6
+    rng = np.random.default_rng(11)
+    tile_bases = tile_words * 16
+    lens = [1, 5, 17, 40, 63, 64, 65, 100]                     # shift the following reads through all alignments
+    for d in (-65, -17, -1, 0, 1, 15, 16, 17, 63, 64):
+        lens += [tile_bases + k - 1 + d, 3, 2 * tile_bases + d, 29]
+    lens += [5 * tile_bases + 7, 12345]
+    seqs = [_random_seq(rng, L) for L in lens]
+    rd = _mk_reads(seqs)
+    rnd = ns.rand_from_seed(5, n)
+    f = make_filter(k, n, thr, rnd)
+    f.initialize(rd)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    bad = np.argwhere(f.sketches() != want)
+    assert bad.size == 0, f"tile_words {tile_words}: sketch differs at {bad[:3].tolist()}"
+    f.close()
+
+
+@pytest.mark.parametrize("lam", [0, 1, 2, 3, 5, 8])
+def test_filter_level_does_not_change_results(orc, monkeypatch, lam):
+    """The prefix filter is an exact shortcut at every level: few expected k-mers per bucket
+    (lam 0: 1..2, a third of the (read, hash) pairs go through the fix-up kernels) or many."""
+    monkeypatch.setenv("NSMH_LAMBDA_LOG2", str(lam))
+    k, n = 21, 64
+    lengths = ns.synth_lengths(400, 4000, seed=8)
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=300_000, genome_seed=2, read_seed=3))
+    rnd = ns.rand_from_seed(99, n)
+    f = make_filter(k, n, 6, rnd)
+    f.load(rd)
+    f.sketch()
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    assert (f.sketches() == want).all()
+    if lam == 0:
+        assert f.stats()["sketch_fixups"] > 1000          # the fix-up path really ran
+    f.close()
+
+
+@pytest.mark.parametrize("k", [9, 16, 17, 31])
+def test_fixup_with_repeats_and_ties(orc, monkeypatch, k):
+    """Fix-up scan on 32-bit prefixes: reads made of one unit repeated at a period of 32 packed
+    words put equal k-mers into different words of the SAME lane (the tie fallback), plus
+    homopolymers / dinucleotide repeats where no bucket of the filter is hit."""
+    monkeypatch.setenv("NSMH_LAMBDA_LOG2", "0")
+    rng = np.random.default_rng(k)
+    unit = _random_seq(rng, 512)
+    seqs = [unit * 4, unit * 7 + b"ACGT", b"G" + unit * 3, b"A" * 3000, b"AC" * 2000, b"ACG" * 1500,
+            _random_seq(rng, 5000), unit[:300] * 9]
+    rd = _mk_reads(seqs)
+    n = 40
+    rnd = ns.rand_from_seed(1234, n)
+    f = make_filter(k, n, 3, rnd)
+    f.initialize(rd)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    bad = np.argwhere(f.sketches() != want)
+    assert bad.size == 0, f"k {k}: sketch differs at {bad[:3].tolist()}"
+    T = orc.build_tables(want)
+    assert_csr_equal(f.queryAll(False), T.query_all(rd.bases, rd.offsets, want, k, rnd, 3, 0), "fwd")
+    f.close()
+
+
+@pytest.mark.parametrize("thr", [1, 6, 60])
+def test_lookup_paths_small_sort_heavy(orc, thr):
+    """Families of identical reads of size 1, 3 (counting table in shared memory), 10 (bitonic
+    sort path: 600 gathered ids) and 30 (global path: 1800 ids), plus near-duplicates that share
+    only some slots; every table group of two or more members goes through the member lists."""
+    k, n = 23, 60
+    rng = np.random.default_rng(3)
+    seqs = []
+    for copies in (1, 3, 10, 30, 1, 3):
+        s = _random_seq(rng, 3000)
+        seqs += [s] * copies
+        m = bytearray(s)
+        for p in range(0, 3000, 150):                      # a mutated relative: shares some minima only
+            m[p] = ord("A") if m[p] != ord("A") else ord("C")
+        seqs.append(bytes(m))
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[i] for i in order]
+    rd = _mk_reads(seqs)
+    rnd = ns.rand_from_seed(42, n)
+    f = make_filter(k, n, thr, rnd)
+    f.initialize(rd)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    assert (f.sketches() == want).all()
+    T = orc.build_tables(want)
+    for j in (0, n - 1):
+        assert f.tableNumKeys(j) == T.num_keys(j)
+    got = f.queryAll(False)
+    assert_csr_equal(got, T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 0), f"thr {thr}")
+    assert int(np.diff(got[0].astype(np.int64)).max()) >= 30
+    f.close()
+
+
+def test_many_results_per_query(orc):
+    """thr = 1 at high coverage: dozens of result ids per query (shuffle sort of <= 32 results,
+    shared-memory sort beyond), gathered-id counts on both sides of the counting-table limit."""
+    lengths = ns.synth_lengths(1200, 900, seed=15)
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=12_000, genome_seed=4, read_seed=5,
+                                                      p_ins=0.0, p_del=0.0, p_sub=0.005))
+    k, n = 15, 24
+    rnd = ns.rand_from_seed(7, n)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    T = orc.build_tables(want)
+    for thr in (1, 2, 5):
+        f = make_filter(k, n, thr, rnd)
+        f.initialize(rd)
+        got = f.queryAll(False)
+        assert_csr_equal(got, T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 0), f"thr {thr}")
+        if thr == 1:
+            assert int(np.diff(got[0].astype(np.int64)).max()) > 64
+        f.close()
+
+
+def test_rebuild_and_requery_same_handle(orc):
+    """A handle is reused for a second, different read set (tables are pre-cleared on the copy
+    stream while the new reads are sketched): no state of the first set may leak."""
+    k, n, thr = 23, 60, 6
+    rnd = ns.rand_from_seed(20261017, n)
+    f = make_filter(k, n, thr, rnd)
+    for seed, count in ((1, 900), (2, 300), (3, 1500)):
+        lengths = ns.synth_lengths(count, 2500, seed=seed)
+        rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=150_000, genome_seed=seed, read_seed=seed + 10))
+        f.initialize(rd)
+        want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+        assert (f.sketches() == want).all()
+        T = orc.build_tables(want)
+        assert_csr_equal(f.queryAll(False), T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 0), f"set {seed}")
+    f.close()
