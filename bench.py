@@ -9,8 +9,9 @@ One "step" = one pass of the hot path over one batch of synthetic reads:
 Workload at N=1 = BASELINE.json configs[1]: 100 000 synthetic nanopore-like reads, ~10 kb
 mean (mixed-gamma lengths), 10 % error (3 % ins, 3 % del, 4 % sub), 50 % reverse strand,
 random 50 Mb genome, k=23, n=60, overlap-sketch-thr=6.  At N>1 every rank owns one such
-shard (weak scaling); sketches are all-gathered over NCCL and every rank builds the full
-tables and queries its own shard.
+shard (weak scaling); the tables are partitioned by hash function across the ranks and the
+two exchanges (sketch columns to the table owners, probe results back to the read owners) are
+stores into NVLink peer memory issued by the producing kernels (csrc/multigpu.cu).
 
 `value`  : device-resident Gbases/s (ASCII reads already in HBM when the clock starts).
 `e2e`    : the same metric through the public API with HOST buffers: pinned ASCII reads are
@@ -176,8 +177,10 @@ def main():
     ap.add_argument("--sketch-mode", type=int, default=0, help="0 filtered kernel, 1 brute force")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
-    ap.add_argument("--multi", default="auto", choices=["auto", "replicated", "partitioned"],
-                    help="N>1: all-gather sketches + full tables per rank, or tables partitioned by hash function")
+    ap.add_argument("--multi", default="auto", choices=["auto", "peer", "replicated", "partitioned"],
+                    help="N>1: tables partitioned by hash function with exchanges over NVLink peer memory inside the "
+                         "kernels (peer, default), the same with NCCL all-to-alls (partitioned), or NCCL all-gather "
+                         "of the sketches + full tables on every rank (replicated)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "nsmh" else args.warmup
 
@@ -226,8 +229,12 @@ def main():
     f.sketchMode = args.sketch_mode
     f._create()
     rows_per_rank = [READS_PER_GPU] * world
-    multi = args.multi if args.multi != "auto" else "partitioned"
-    pf = shard.PartitionedFilter(f, rank, world) if (world > 1 and multi == "partitioned") else None
+    multi = args.multi if args.multi != "auto" else "peer"
+    pf = None
+    if world > 1 and multi == "partitioned":
+        pf = shard.PartitionedFilter(f, rank, world)
+    elif world > 1 and multi == "peer":
+        pf = shard.PeerPartitionedFilter(f, rank, world, rows_per_rank)
     ext = torch.cuda.ExternalStream(f.stream(), device=local_rank)
     keep = {}
 
@@ -334,6 +341,8 @@ def main():
 
     if dist is not None:
         dist.barrier()
+    if isinstance(pf, shard.PeerPartitionedFilter):
+        pf.shutdown()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()

@@ -121,6 +121,37 @@ int nsmh_probe_lists(nsmh_handle h, const uint64_t *d_sketches, uint32_t num_que
 int nsmh_count_lists(nsmh_handle h, uint32_t num_queries, uint32_t parts, const uint64_t *const *d_offsets,
                      const uint32_t *const *d_ids, uint64_t *total_ids);
 
+/* ---- multi-GPU, native: one process per GPU, exchanges over NVLink peer memory -------------
+ * The reference has no distributed path (ReadFilter.cpp:31-44 is one OpenMP loop over the
+ * reads, :163-165 one over the tables); this is the only exchange the path needs.  Rank g owns
+ * the tables of a contiguous block of hash functions for ALL reads of all ranks:
+ *   sketch (local reads) -> every rank STORES its sketch columns straight into the owners'
+ *   memory -> flag barrier -> owners build their tables and probe them for every read,
+ *   storing {id | group start, group size} straight into the memory of the rank that owns
+ *   the read -> flag barrier -> every rank thresholds its own reads (group ids are read from
+ *   the owner's memory on demand).  No host round trip between the stages, no NCCL call.
+ * Results are bit-identical to one GPU holding all reads (global read id = rows of the lower
+ * ranks + local id).  The work per rank is constant under weak scaling.
+ *
+ * Usage (all ranks): nsmh_mg_init -> exchange the tokens by any means (e.g. an all-gather of
+ * NSMH_MG_TOKEN_BYTES bytes) -> nsmh_mg_connect -> per batch: nsmh_load_reads_* , nsmh_sketch,
+ * nsmh_mg_run, nsmh_query_all_result / _device_ptrs.  rows_per_rank[r] = reads of rank r; the
+ * batch loaded on this rank must have exactly rows_per_rank[rank] reads.  world <= 16.
+ * Every rank must call nsmh_mg_run the same number of times; a peer that never arrives makes
+ * the call fail with NSMH_ECUDA after a timeout instead of hanging the GPU. */
+#define NSMH_MG_MAX_RANKS 16
+#define NSMH_MG_TOKEN_BYTES 256
+int nsmh_mg_init(nsmh_handle h, uint32_t rank, uint32_t world, const uint32_t *rows_per_rank,
+                 void *token_out /* NSMH_MG_TOKEN_BYTES */);
+int nsmh_mg_connect(nsmh_handle h, const void *tokens /* world * NSMH_MG_TOKEN_BYTES, rank order */);
+int nsmh_mg_run(nsmh_handle h, uint64_t *total_ids);
+/* Device time of the stages of the last nsmh_mg_run, ms: scatter columns, barrier, build owned
+ * tables, probe + store to peers, barrier, count. */
+int nsmh_mg_stage_ms(nsmh_handle h, float *out /* [6] */);
+/* Detach from the peers and free the exchange memory (also done by nsmh_destroy).  All ranks
+ * must have finished their last nsmh_mg_run before any rank calls this. */
+int nsmh_mg_shutdown(nsmh_handle h);
+
 /* ---- online query: ReadFilter::getFilteredReads(const std::string&, std::vector<read_t>&)
  *      (ReadFilter.h:24-25, ReadFilter.cpp:85-97).  Thread-safe, re-entrant. -------------
  * Writes min(count, cap) ids to out and the full count to *count; returns NSMH_ERANGE

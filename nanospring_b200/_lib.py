@@ -9,6 +9,7 @@ ROOT = os.path.dirname(PKG)
 LIB_PATH = os.path.join(PKG, "libnsmh.so")
 HEADER = os.path.join(ROOT, "include", "nsmh.h")
 
+MG_TOKEN_BYTES, MG_MAX_RANKS = 256, 16
 NSMH_OK, NSMH_EINVAL, NSMH_ECUDA, NSMH_ESTATE, NSMH_ENOMEM, NSMH_ERANGE = 0, -1, -2, -3, -4, -5
 
 u64p = C.POINTER(C.c_uint64)
@@ -65,6 +66,11 @@ _SIGS = {
     "nsmh_query_all_device_ptrs": [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)],
     "nsmh_probe_lists": [C.c_void_p, C.c_void_p, C.c_uint32, u64p],
     "nsmh_count_lists": [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), u64p],
+    "nsmh_mg_init": [C.c_void_p, C.c_uint32, C.c_uint32, u32p, C.c_void_p],
+    "nsmh_mg_connect": [C.c_void_p, C.c_void_p],
+    "nsmh_mg_run": [C.c_void_p, u64p],
+    "nsmh_mg_stage_ms": [C.c_void_p, C.POINTER(C.c_float)],
+    "nsmh_mg_shutdown": [C.c_void_p],
     "nsmh_query_string": [C.c_void_p, C.c_char_p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)],
     "nsmh_query_strings": [C.c_void_p, C.c_void_p, u64p, C.c_uint32, u64p, u32p, C.c_size_t],
     "nsmh_query_sketches": [C.c_void_p, u64p, C.c_uint32, u64p, u32p, C.c_size_t],

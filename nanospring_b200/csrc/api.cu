@@ -30,6 +30,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 
 int DevBuf::ensure(size_t bytes, cudaStream_t s, size_t keep) {
     if (bytes <= cap && p) return NSMH_OK;
+    if (borrowed) return fail(NSMH_ENOMEM, "internal: a borrowed device buffer is too small");
     size_t want = bytes + bytes / 8 + 256;
     void *np = nullptr;
     NSMH_CK(cudaMallocAsync(&np, want, s));
@@ -43,7 +44,8 @@ int DevBuf::ensure(size_t bytes, cudaStream_t s, size_t keep) {
 }
 
 void DevBuf::release(cudaStream_t s) {
-    if (p) cudaFreeAsync(p, s);
+    if (p && !borrowed) cudaFreeAsync(p, s);
+    borrowed = false;
     p = nullptr;
     cap = 0;
 }
@@ -209,6 +211,7 @@ int nsmh_destroy(nsmh_handle h) {
     {
         DeviceGuard guard(h->device);
         if (h->stream) cudaStreamSynchronize(h->stream);
+        mg_destroy(h);
         for (QueryWs *ws : h->pool) {
             if (ws->stream) cudaStreamSynchronize(ws->stream);
             free_ws(*ws, ws->stream);
@@ -229,7 +232,7 @@ int nsmh_destroy(nsmh_handle h) {
         for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
         if (h->ev_order) cudaEventDestroy(h->ev_order);
         if (h->ev_cleared) cudaEventDestroy(h->ev_cleared);
-        if (h->stream) cudaStreamDestroy(h->stream);
+        if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         cudaGetLastError();
     }
@@ -380,7 +383,9 @@ int nsmh_sketch(nsmh_handle c) {
     c->tables.built = false;
     c->bulk_valid = false;
     NSMH_TRY(c->sketches.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream));
-    NSMH_TRY(preclear_tables(c, c->reads.num_reads));
+    // the tables that the next build fills are cleared on the copy stream while the reads are sketched
+    if (c->mg && c->mg_sub()) NSMH_TRY(preclear_tables(c->mg_sub(), c->mg_total_rows()));
+    else NSMH_TRY(preclear_tables(c, c->reads.num_reads));
     NSMH_CK(cudaEventRecord(c->ev[2], c->stream));
     NSMH_TRY(sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp,
                           c->sketch_mode, c->stream, &c->launches, c->ev[4], c->ev[5]));

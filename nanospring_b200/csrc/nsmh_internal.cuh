@@ -32,6 +32,7 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool borrowed = false;      // storage owned by somebody else (e.g. the peer-visible arena): never grown or freed
     // keep > 0: preserve the first `keep` bytes when the buffer has to grow
     int ensure(size_t bytes, cudaStream_t s, size_t keep = 0);
     void release(cudaStream_t s);
@@ -124,6 +125,8 @@ struct QueryWs {
     uint32_t launches = 0;
 };
 
+struct MgState;
+
 } // namespace nsmh
 
 struct nsmh_ctx {
@@ -165,6 +168,11 @@ struct nsmh_ctx {
 
     nsmh_stats stats = {};
     uint32_t launches = 0;
+
+    bool owns_stream = true;    // false: `stream` belongs to the parent context (multi-GPU sub-context)
+    nsmh::MgState *mg = nullptr;   // multigpu.cu: tables partitioned by hash function across ranks
+    nsmh_ctx *mg_sub() const;      // the context of the tables this rank owns (nullptr before nsmh_mg_connect)
+    uint32_t mg_total_rows() const;
 };
 
 namespace nsmh {
@@ -206,5 +214,25 @@ int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, u
 int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s);
 int count_lists_device(nsmh_ctx *c, QueryWs &ws, uint32_t nq, uint32_t parts, const uint64_t *const *d_offsets,
                        const uint32_t *const *d_ids, cudaStream_t s);
+
+// ---- multi-GPU over peer memory (query.cu kernels, multigpu.cu orchestration) ----
+constexpr int kMgMaxRanks = NSMH_MG_MAX_RANKS;
+// Where the probe results of the tables owned by this rank go: the read's owner, through peer memory.
+struct PeerDst {
+    uint32_t *pval[kMgMaxRanks], *pcnt[kMgMaxRanks];   // [rows_r][n_total] in rank r's arena
+    uint32_t row_end[kMgMaxRanks];                     // global row index one past rank r's rows
+    uint32_t world, n_total, col0;                     // col0: first hash function this rank owns
+};
+// Probe results stored locally by the table owners + where the owners keep their group ids.
+struct PeerLists {
+    const uint32_t *pval, *pcnt;            // [nq][n] local
+    const uint32_t *ids[kMgMaxRanks];       // ids array of the rank that owns the hash function
+    uint32_t col_end[kMgMaxRanks];          // hash functions [col_end[r-1], col_end[r]) belong to rank r
+    uint32_t world, n;
+};
+int probe_to_peers_device(nsmh_ctx *sub, const uint64_t *d_qsketch, uint32_t nq, const PeerDst &dst,
+                          cudaStream_t s, uint32_t *launches);
+int count_peer_lists_device(nsmh_ctx *c, QueryWs &ws, const PeerLists &src, uint32_t nq, cudaStream_t s);
+void mg_destroy(nsmh_ctx *c);
 
 } // namespace nsmh

@@ -153,6 +153,64 @@ probe_items_kernel(ProbeSrc src, uint32_t nq) {
     }
 }
 
+// The same probe, for the tables this rank owns (src.n of the n_total hash functions, starting at
+// dst.col0) and the reads of ALL ranks (q = global row).  The results are stored straight into
+// the memory of the rank that owns read q (peer mapping over NVLink), at [local row][col0 + j].
+__global__ void __launch_bounds__(kProbeRows, 4)
+probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
+    const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
+    const uint32_t colgroups = (src.n + kProbeCols - 1) / kProbeCols;
+    const uint32_t units = chunks * colgroups;
+    const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
+    const bool vec_in = (src.n & 3) == 0;
+    const bool vec_out = ((dst.n_total | dst.col0) & 3) == 0 && vec_in;
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        const uint32_t cg = u / chunks;
+        const uint32_t q = (u - cg * chunks) * kProbeRows + threadIdx.x;
+        const uint32_t l0 = cg * kProbeCols;
+        if (q >= nq) continue;
+        const size_t t0 = (size_t)q * src.n + l0;
+        uint64_t key[kProbeCols];
+        if (vec_in) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
+        else {
+#pragma unroll
+            for (int j = 0; j < kProbeCols; ++j) key[j] = l0 + j < src.n ? __ldg(src.qsk + t0 + j) : 0;
+        }
+        uint64_t b[kProbeCols], sa[kProbeCols], sb[kProbeCols], sc[kProbeCols], sd[kProbeCols];
+#pragma unroll
+        for (int j = 0; j < kProbeCols; ++j) {
+            b[j] = key[j] == kEmptyKey ? nb : slot_index(key[j], nb);
+            const uint32_t l = min(l0 + j, src.n - 1);
+            ldg256(src.slots + (uint64_t)l * rstride + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
+        }
+        uint32_t val[kProbeCols], cnt[kProbeCols];
+#pragma unroll
+        for (int j = 0; j < kProbeCols; ++j) {
+            const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
+            for (;;) {
+                if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
+                if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
+                if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
+                ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
+            }
+        }
+        uint32_t o = 0;                                   // owner of read q
+        while (o + 1 < dst.world && q >= dst.row_end[o]) ++o;
+        const uint32_t lq = q - (o ? dst.row_end[o - 1] : 0u);
+        const size_t d0 = (size_t)lq * dst.n_total + dst.col0 + l0;
+        if (vec_out) {
+            *reinterpret_cast<uint4 *>(dst.pval[o] + d0) = make_uint4(val[0], val[1], val[2], val[3]);
+            *reinterpret_cast<uint4 *>(dst.pcnt[o] + d0) = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kProbeCols; ++j)
+                if (l0 + j < src.n) { dst.pval[o][d0 + j] = val[j]; dst.pcnt[o][d0 + j] = cnt[j]; }
+        }
+    }
+}
+
 // id lists from stored probe results
 struct StoredSrc {
     const uint32_t *pval, *pcnt;   // [nq][n]
@@ -199,6 +257,37 @@ struct PartsSrc {
         r.ptr = ids[p.j] + p.o0;
         r.c = (uint32_t)(p.o1 - p.o0);
         r.one = 0;
+        return r;
+    }
+    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
+};
+
+// Multi-GPU (multigpu.cu): the probe results of every (query, hash) were stored here by the
+// rank that owns the hash function's table; the ids of groups with two or more members stay
+// in the owner's memory and are read through the NVLink peer mapping.
+struct PeerSrc {
+    PeerLists L;
+    struct Pending {
+        uint32_t val, c, j;
+    };
+    __device__ __forceinline__ uint32_t subs() const { return L.n; }
+    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
+        Pending p;
+        p.j = j;
+        p.val = __ldg(L.pval + (size_t)q * L.n + j);
+        p.c = __ldg(L.pcnt + (size_t)q * L.n + j);
+        return p;
+    }
+    __device__ __forceinline__ ListRef finish(Pending p) const {
+        ListRef r;
+        r.c = p.c;
+        r.one = p.val;
+        r.ptr = nullptr;
+        if (p.c > 1) {
+            uint32_t o = 0;
+            while (o + 1 < L.world && p.j >= L.col_end[o]) ++o;
+            r.ptr = L.ids[o] + p.val;
+        }
         return r;
     }
     __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
@@ -616,12 +705,8 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
         NSMH_TRY(ws.tmp_ids.ensure((size_t)nq * 16 * sizeof(uint32_t), s));
 
     const size_t smem = (size_t)kLookupWarps * kWarpWords * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        NSMH_CK(cudaFuncSetAttribute(count_kernel<ProbeSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        NSMH_CK(cudaFuncSetAttribute(count_kernel<PartsSrc>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    // function attributes are per device: set on every call (cheap) rather than once per process
+    NSMH_CK(cudaFuncSetAttribute(count_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CountArgs a;
     a.qcount = ws.qcount.as<uint32_t>();
     a.qpos = ws.qpos.as<uint64_t>();
@@ -770,6 +855,37 @@ probe_write_kernel(StoredSrc src, uint32_t nq, const uint64_t *__restrict__ out_
             base += __shfl_sync(0xffffffffu, incl, 31);
         }
     }
+}
+
+// ---------------------------------------------------------------- multi-GPU --
+int probe_to_peers_device(nsmh_ctx *sub, const uint64_t *d_qsketch, uint32_t nq, const PeerDst &dst,
+                          cudaStream_t s, uint32_t *launches) {
+    Tables &T = sub->tables;
+    if (!T.built) return fail(NSMH_ESTATE, "mg: owned tables not built");
+    if ((uint64_t)nq * sub->n >= (1ULL << 32)) return fail(NSMH_EINVAL, "mg: reads*n too large for 32-bit item indices");
+    if (nq == 0) return NSMH_OK;
+    ProbeSrc src;
+    src.qsk = d_qsketch;
+    src.slots = T.slots.as<Slot>();
+    src.ids = T.ids.as<uint32_t>();
+    src.pval = nullptr;
+    src.pcnt = nullptr;
+    src.cap = T.cap;
+    src.n = sub->n;
+    const uint64_t units = (uint64_t)((nq + kProbeRows - 1) / kProbeRows) * ((sub->n + kProbeCols - 1) / kProbeCols);
+    int occ = 0;
+    NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_to_peers_kernel, kProbeRows, 0));
+    const int blocks = (int)std::min<uint64_t>(units, (uint64_t)sub->num_sms * (occ > 0 ? occ : 1));
+    probe_to_peers_kernel<<<blocks, kProbeRows, 0, s>>>(src, nq, dst);
+    ++*launches;
+    NSMH_CK(cudaGetLastError());
+    return NSMH_OK;
+}
+
+int count_peer_lists_device(nsmh_ctx *c, QueryWs &ws, const PeerLists &lists, uint32_t nq, cudaStream_t s) {
+    PeerSrc src;
+    src.L = lists;
+    return count_and_emit(c, ws, src, lists.n, nq, s);
 }
 
 int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s) {

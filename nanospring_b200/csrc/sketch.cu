@@ -589,11 +589,8 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     if (mode == 0 && c->n > 255) mode = 1;   // chain tables index hashes with one byte
     if (ev0) NSMH_CK(cudaEventRecord(ev0, s));
     if (mode == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            NSMH_CK(cudaFuncSetAttribute(sketch_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            attr_set = true;
-        }
+        // per-device attribute: set on every call (cheap) rather than once per process
+        NSMH_CK(cudaFuncSetAttribute(sketch_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // one block per SM, as many warps as the shared memory holds (each warp owns a tile)
         const FilterSmem L(c->n, a.tile_words);
         const size_t budget = smem_budget;

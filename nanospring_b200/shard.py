@@ -1,10 +1,16 @@
 """Multi-GPU plumbing for the read-overlap stage: one process per GPU, reads sharded by
-bases, sketches all-gathered (NCCL over NVLink; gloo on CPU for the tests), every rank
-builds the full tables and queries its own shard.
+bases.  Three strategies, all bit-identical to one GPU:
+
+  PeerPartitionedFilter  (default) tables partitioned by hash function, both exchanges done by
+                         the producing kernels as stores into NVLink peer memory, flag barriers
+                         on the device (csrc/multigpu.cu, nsmh_mg_*); torch.distributed only
+                         carries the 256-byte setup tokens.
+  PartitionedFilter      the same partitioning with NCCL all-to-alls driven from the host.
+  gather_and_build       SURVEY's baseline: NCCL all-gather of the sketch rows, every rank
+                         builds the full tables (cost grows with the global read count).
 
 The reference has no distributed path (single process, OpenMP: ReadFilter.cpp:31-44 is a
-loop over reads, ReadFilter.cpp:163-165 a loop over tables), so this module defines the
-only exchange step the path has: one all-gather of [reads][n] u64 sketch rows.
+loop over reads, ReadFilter.cpp:163-165 a loop over tables).
 """
 import numpy as np
 
@@ -203,3 +209,55 @@ class PartitionedFilter:
         ids = np.zeros(max(total, 1), dtype=np.uint32)
         check(lib().nsmh_query_all_result(self.f._h, off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p)))
         return off, ids[:total]
+
+
+# ------------------------------------------------------------------------------------------
+class PeerPartitionedFilter:
+    """Tables partitioned by hash function; exchanges over NVLink peer memory inside the kernels
+    (include/nsmh.h, nsmh_mg_*).  `group` is only used once, to exchange the setup tokens."""
+
+    def __init__(self, local_filter, rank, world, rows_per_rank, group=None):
+        import ctypes as C
+        from ._lib import MG_TOKEN_BYTES, check, lib, u32p
+        self.C = C
+        self.f = local_filter
+        self.rank, self.world = rank, world
+        rows = np.ascontiguousarray(np.asarray(rows_per_rank, dtype=np.uint32))
+        if rows.size != world:
+            raise ValueError("rows_per_rank must have one entry per rank")
+        token = (C.c_uint8 * MG_TOKEN_BYTES)()
+        check(lib().nsmh_mg_init(self.f._h, rank, world, rows.ctypes.data_as(u32p), token))
+        tokens = [None] * world
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_gather_object(tokens, bytes(token), group=group)
+        else:
+            tokens[0] = bytes(token)
+        blob = b"".join(tokens)
+        check(lib().nsmh_mg_connect(self.f._h, blob))
+        self.last_ms = {}
+
+    def run(self, n_local=None, rows_per_rank=None):
+        """After self.f.sketch(): scatter columns, build owned tables, probe, count.  Returns the
+        number of candidate ids of the local reads; the CSR stays on the device."""
+        from ._lib import check, lib
+        C = self.C
+        total = C.c_uint64(0)
+        check(lib().nsmh_mg_run(self.f._h, C.byref(total)))
+        ms = (C.c_float * 6)()
+        check(lib().nsmh_mg_stage_ms(self.f._h, ms))
+        self.last_ms = dict(zip(("scatter_columns", "barrier_1", "build_owned_tables", "probe_to_peers",
+                                 "barrier_2", "count"), [float(x) for x in ms]))
+        return total.value
+
+    def result(self, n_local, total):
+        """CSR (offsets u64[n_local+1], ids u32[total]) of the local reads, global read ids."""
+        from ._lib import check, lib, u32p, u64p
+        off = np.zeros(n_local + 1, dtype=np.uint64)
+        ids = np.zeros(max(total, 1), dtype=np.uint32)
+        check(lib().nsmh_query_all_result(self.f._h, off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p)))
+        return off, ids[:total]
+
+    def shutdown(self):
+        from ._lib import check, lib
+        check(lib().nsmh_mg_shutdown(self.f._h))

@@ -51,11 +51,24 @@ def main():
     ptotal = pf.run(hi - lo, rows)
     poff, pids = pf.result(hi - lo, ptotal)
     same = bool((poff == off).all() and pids.size == ids.size and (pids == ids).all())
+    # third strategy (the default): the same partitioning, exchanges over NVLink peer memory
+    # inside the kernels, device-side flag barriers (csrc/multigpu.cu); run twice (epochs)
+    peer = shard.PeerPartitionedFilter(f, rank, world, rows)
+    same_peer = True
+    for _ in range(2):
+        f.sketch()
+        qtotal = peer.run()
+        qoff, qids = peer.result(hi - lo, qtotal)
+        same_peer &= bool((qoff == off).all() and qids.size == ids.size and (qids == ids).all())
+    dist.barrier()
+    peer.shutdown()
     flags = [None] * world
-    dist.all_gather_object(flags, same)
-    ok = all(flags)
+    dist.all_gather_object(flags, (same, same_peer))
+    ok = all(a and b for a, b in flags)
     if rank == 0:
-        print(f"partitioned tables == replicated tables on every rank: {ok}", flush=True)
+        print(f"partitioned tables (NCCL) == replicated tables on every rank: {all(a for a, _ in flags)}", flush=True)
+        print(f"partitioned tables (peer memory) == replicated tables on every rank: {all(b for _, b in flags)} "
+              f"stages ms {dict((k2, round(v, 3)) for k2, v in peer.last_ms.items())}", flush=True)
     if rank == 0:
         counts = np.concatenate([p[0] for p in pieces])
         all_ids = np.concatenate([p[1] for p in pieces])
