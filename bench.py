@@ -308,6 +308,12 @@ def main():
 
     if pf is not None:
         phases["partitioned_stage_ms"] = {k2: round(v, 3) for k2, v in pf.last_ms.items()}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, [round(v, 3) for v in pf.last_ms.values()])
+        if rank == 0:
+            log("stage ms per rank " + " ".join(pf.last_ms.keys()))
+            for r, v in enumerate(per_rank):
+                log(f"  rank {r}: {v}")
 
     # ---- e2e: host buffers in, CSR out ----
     for _ in range(0 if args.no_e2e else 2):

@@ -36,7 +36,8 @@ constexpr uint64_t kMgMagic = 0x4e534d48504d4731ULL;   // "NSMHPMG1"
 struct MgToken {
     cudaIpcMemHandle_t handle;       // 64 bytes
     uint64_t magic;
-    uint64_t off_m, off_pval, off_pcnt, off_ids, off_flags, arena_bytes;
+    uint64_t off_m, off_pr, off_ids, off_inbox, off_flags, arena_bytes;
+    uint32_t inbox_cap, pad0;
     uint32_t rank, world, n_total, col0, ncols, rows, total_rows;
     int32_t device;
 };
@@ -89,8 +90,26 @@ mg_scatter_columns_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_
     }
 }
 
+// The same when every rank owns a multiple of 4 hash functions: a thread moves 4 adjacent
+// columns of one row = one 32-byte sector in (256-bit load) and one out (256-bit store).
+__global__ void __launch_bounds__(256)
+mg_scatter_columns4_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_t n, ScatterArgs a) {
+    const uint32_t groups = n >> 2;
+    const uint64_t total = (uint64_t)rows * groups, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
+        const uint32_t i = (uint32_t)(t / groups), j = (uint32_t)(t - (uint64_t)i * groups) << 2;
+        uint64_t v0, v1, v2, v3;
+        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(S + t * 4));
+        uint32_t o = 0;
+        while (o + 1 < a.world && j >= a.col_end[o]) ++o;
+        const uint32_t cb = o ? a.col_end[o - 1] : 0u, nc = a.col_end[o] - cb;
+        uint64_t *d = a.m[o] + (size_t)(a.row0 + i) * nc + (j - cb);
+        asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(d), "l"(v0), "l"(v1), "l"(v2), "l"(v3) : "memory");
+    }
+}
+
 struct BarrierArgs {
-    uint32_t *flags[kMgMaxRanks];     // flags block of every rank: [2][kMgMaxRanks] epochs + [1] error
+    uint32_t *flags[kMgMaxRanks];     // flags block of every rank: [2][kMgMaxRanks] epochs, [1] error, [kMgMaxRanks] inbox cursors
     uint32_t world, rank;
     uint64_t timeout_ns;
 };
@@ -199,14 +218,20 @@ int nsmh_mg_init(nsmh_handle c, uint32_t rank, uint32_t world, const uint32_t *r
         const size_t local = std::max<size_t>((size_t)m->rows[rank] * m->n_total, 1);
         size_t off = 0;
         t.off_m = off;      off = align256(off + items * sizeof(uint64_t));
-        t.off_pval = off;   off = align256(off + local * sizeof(uint32_t));
-        t.off_pcnt = off;   off = align256(off + local * sizeof(uint32_t));
+        t.off_pr = off;     off = align256(off + local * sizeof(uint64_t));
         t.off_ids = off;    off = align256(off + items * sizeof(uint32_t));
-        t.off_flags = off;  off = align256(off + (2 * kMgMaxRanks + 8) * sizeof(uint32_t));
+        // inbox: one segment per source rank, room for 2 ids per (local read, hash of that rank)
+        uint32_t max_cols = 0;
+        for (uint32_t r = 0; r < world; ++r) max_cols = std::max(max_cols, m->col_end[r] - (r ? m->col_end[r - 1] : 0u));
+        t.inbox_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2ull * m->rows[rank] * max_cols, 64), 1ull << 30);
+        const char *ic = getenv("NSMH_MG_INBOX_CAP");        // tests: force the overflow path
+        if (ic && *ic && atoll(ic) > 0) t.inbox_cap = (uint32_t)std::min<long long>(atoll(ic), 1ll << 30);
+        t.off_inbox = off;  off = align256(off + (size_t)world * t.inbox_cap * sizeof(uint32_t));
+        t.off_flags = off;  off = align256(off + (3 * kMgMaxRanks + 8) * sizeof(uint32_t));
         t.arena_bytes = off;
         cudaError_t ce = cudaMalloc(reinterpret_cast<void **>(&m->arena), off);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "cudaMalloc(arena)", __FILE__, __LINE__); break; }
-        if ((ce = cudaMemset(m->arena + t.off_flags, 0, (2 * kMgMaxRanks + 8) * sizeof(uint32_t))) != cudaSuccess) { rc = cuda_fail(ce, "memset", __FILE__, __LINE__); break; }
+        if ((ce = cudaMemset(m->arena + t.off_flags, 0, (3 * kMgMaxRanks + 8) * sizeof(uint32_t))) != cudaSuccess) { rc = cuda_fail(ce, "memset", __FILE__, __LINE__); break; }
         if ((ce = cudaIpcGetMemHandle(&t.handle, m->arena)) != cudaSuccess) { rc = cuda_fail(ce, "cudaIpcGetMemHandle", __FILE__, __LINE__); break; }
         t.magic = kMgMagic;
         t.rank = rank;
@@ -305,8 +330,9 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
         ba.flags[r] = in ? reinterpret_cast<uint32_t *>(base + m->peers[r].off_flags) : nullptr;
         sa.m[r] = in ? reinterpret_cast<uint64_t *>(base + m->peers[r].off_m) : nullptr;
         sa.col_end[r] = in ? m->col_end[r] : 0u;
-        pd.pval[r] = in ? reinterpret_cast<uint32_t *>(base + m->peers[r].off_pval) : nullptr;
-        pd.pcnt[r] = in ? reinterpret_cast<uint32_t *>(base + m->peers[r].off_pcnt) : nullptr;
+        pd.pr[r] = in ? reinterpret_cast<uint64_t *>(base + m->peers[r].off_pr) : nullptr;
+        pd.inbox[r] = in ? reinterpret_cast<uint32_t *>(base + m->peers[r].off_inbox) + (size_t)m->rank * m->peers[r].inbox_cap : nullptr;
+        pd.inbox_cap[r] = in ? m->peers[r].inbox_cap : 0u;
         pd.row_end[r] = in ? m->row_end[r] : 0u;
         pl.ids[r] = in ? reinterpret_cast<const uint32_t *>(base + m->peers[r].off_ids) : nullptr;
         pl.col_end[r] = in ? m->col_end[r] : 0u;
@@ -315,17 +341,29 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
     ba.rank = m->rank;
     ba.timeout_ns = m->timeout_ns;
     sa.row0 = m->rank ? m->row_end[m->rank - 1] : 0u;
-    pd.n_total = m->n_total;
     pd.col0 = m->col0;
-    pl.pval = reinterpret_cast<const uint32_t *>(m->arena + m->self.off_pval);
-    pl.pcnt = reinterpret_cast<const uint32_t *>(m->arena + m->self.off_pcnt);
+    pd.ncols = m->ncols;
+    pl.pr = reinterpret_cast<const uint64_t *>(m->arena + m->self.off_pr);
     pl.n = m->n_total;
+    pl.rows = rows;
+    pl.inbox = reinterpret_cast<const uint32_t *>(m->arena + m->self.off_inbox);
+    pl.inbox_cap = m->self.inbox_cap;
+    uint32_t *cursors = reinterpret_cast<uint32_t *>(m->arena + m->self.off_flags) + 2 * kMgMaxRanks + 8;
+    pd.cursor = cursors;
+    NSMH_CK(cudaMemsetAsync(cursors, 0, kMgMaxRanks * sizeof(uint32_t), s));
     uint64_t *M = reinterpret_cast<uint64_t *>(m->arena + m->self.off_m);
 
     NSMH_CK(cudaEventRecord(m->ev[0], s));
     if (rows) {
-        const int blocks = (int)std::min<uint64_t>(((uint64_t)rows + 7) / 8, (uint64_t)c->num_sms * 8);
-        mg_scatter_columns_kernel<<<blocks, 256, 0, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
+        bool by4 = (c->n & 3) == 0;
+        for (uint32_t r = 0; r < m->world; ++r) by4 = by4 && (m->col_end[r] & 3) == 0;
+        if (by4) {
+            const int blocks = (int)std::min<uint64_t>(((uint64_t)rows * (c->n >> 2) + 255) / 256, (uint64_t)c->num_sms * 8);
+            mg_scatter_columns4_kernel<<<blocks, 256, 0, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
+        } else {
+            const int blocks = (int)std::min<uint64_t>(((uint64_t)rows + 7) / 8, (uint64_t)c->num_sms * 8);
+            mg_scatter_columns_kernel<<<blocks, 256, 0, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
+        }
         ++c->launches;
         NSMH_CK(cudaGetLastError());
     }

@@ -46,6 +46,36 @@ def test_world_of_one_equals_plain_path_and_oracle(k, n, thr):
     assert (off0 == woff).all() and (ids0 == wids).all()
 
 
+@pytest.mark.parametrize("inbox_cap", [None, "48"])
+def test_groups_of_every_size_inbox_and_remote_paths(inbox_cap, monkeypatch):
+    """Duplicated reads give groups of 2..100 members in every table: small groups travel through
+    the inbox, groups above kInboxMaxGroup (32) and everything beyond the inbox capacity are read
+    from the owner's ids array; all of it must agree with the plain single-GPU path."""
+    import nanospring_b200 as ns
+    from nanospring_b200 import shard
+    if inbox_cap:
+        monkeypatch.setenv("NSMH_MG_INBOX_CAP", inbox_cap)
+    k, n, thr = 23, 60, 6
+    rnd = ns.rand_from_seed(9, n)
+    base = ns.synth_reads_host(ns.synth_lengths(40, 1500, seed=8), ns.synth_params(genome_len=100_000))
+    reads = []
+    for i in range(40):
+        reads += [base.getRead(i)] * (1 + (i * 7) % 100 if i % 3 == 0 else 1 + i % 4)
+    rd = ns.ReadData.from_reads(reads)
+    f = ns.MinHashReadFilter(device=0)
+    f.k, f.n, f.overlapSketchThreshold, f.randNumbers = k, n, thr, rnd
+    f.initialize(rd)
+    off0, ids0 = f.queryAll(False)
+    assert int(np.diff(off0.astype(np.int64)).max()) > 32
+    peer = shard.PeerPartitionedFilter(f, 0, 1, [rd.numReads])
+    f.sketch()
+    total = peer.run()
+    off, ids = peer.result(rd.numReads, total)
+    assert (off == off0).all() and (ids == ids0).all()
+    peer.shutdown()
+    f.close()
+
+
 def test_mg_argument_checks():
     import ctypes as C
     import nanospring_b200 as ns
