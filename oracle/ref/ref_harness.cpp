@@ -203,6 +203,12 @@ void nsref_destroy(void *h) {
     delete static_cast<Ctx *>(h);
 }
 
+// The objects behind a handle, as the reference's callers hold them (Consensus.h:31-41:
+// `ReadData *rD; ReadFilter *rF;`): for tests that run the reference's own consensus stage
+// against this filter (tests/cpp/consensus_dropin_test.cpp).
+void *nsref_read_filter(void *h) { return static_cast<ReadFilter *>(&static_cast<Ctx *>(h)->rF); }
+void *nsref_read_data(void *h) { return &static_cast<Ctx *>(h)->rD; }
+
 // Public static helpers, for the known-answer tests of SURVEY section 8(c).
 uint64_t nsref_kmer_to_int(const char *s, size_t len) {
     return MinHashReadFilter::kMerToInt(std::string(s, len));
