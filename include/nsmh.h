@@ -109,6 +109,23 @@ int nsmh_query_all_result(nsmh_handle h, uint64_t *offsets /* [num_reads+1] host
                           uint32_t *ids /* [total_ids] host */);
 int nsmh_query_all_device_ptrs(nsmh_handle h, uint64_t **d_offsets, uint32_t **d_ids);
 
+/* ---- candidate pre-filters of the consensus builder, on the device ----------------------
+ * flags[i] of loaded read i:
+ *   NSMH_FLAG_REPETITIVE  Consensus::checkRepetitive(i) (Consensus.cpp:405-424): for some shift
+ *                         s in 1..6 more than 0.7*len positions j have read[j] == read[(j+s) % len];
+ *                         this is isRepetitive[i] of Consensus::initialize (Consensus.cpp:426-442)
+ *   NSMH_FLAG_SHORT       len < 32, the length gate of addRelatedReads (Consensus.cpp:213)
+ * Computed from the packed reads on the first call after a load (one pass over 0.25 B/base).
+ * nsmh_query_all_drop removes from the bulk CSR of the last nsmh_query_all every candidate id
+ * whose flags intersect drop_mask - what the caller does one id at a time at
+ * Consensus.cpp:204-216 - so that they never leave the device.  Single-GPU bulk results only
+ * (candidate ids must be ids of the loaded reads). */
+#define NSMH_FLAG_REPETITIVE 1u
+#define NSMH_FLAG_SHORT 2u
+int nsmh_read_flags(nsmh_handle h, uint8_t *out /* [num_reads] host, may be NULL */);
+int nsmh_read_flags_device_ptr(nsmh_handle h, uint8_t **d_flags);
+int nsmh_query_all_drop(nsmh_handle h, uint32_t drop_mask, uint64_t *total_ids);
+
 /* ---- multi-GPU building blocks (tables partitioned by hash function across ranks) -----
  * nsmh_probe_lists: probe this handle's n tables for num_queries device-resident sketches
  * [num_queries][n] and gather the id lists WITHOUT counting: CSR of concatenated lists

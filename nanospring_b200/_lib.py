@@ -11,6 +11,7 @@ HEADER = os.path.join(ROOT, "include", "nsmh.h")
 
 MG_TOKEN_BYTES, MG_MAX_RANKS = 256, 16
 NSMH_OK, NSMH_EINVAL, NSMH_ECUDA, NSMH_ESTATE, NSMH_ENOMEM, NSMH_ERANGE = 0, -1, -2, -3, -4, -5
+FLAG_REPETITIVE, FLAG_SHORT = 1, 2
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -54,6 +55,9 @@ _SIGS = {
     "nsmh_load_reads_ascii_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64],
     "nsmh_load_reads_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
     "nsmh_num_reads": [C.c_void_p, u32p, u64p],
+    "nsmh_read_flags": [C.c_void_p, u8p],
+    "nsmh_read_flags_device_ptr": [C.c_void_p, C.POINTER(C.c_void_p)],
+    "nsmh_query_all_drop": [C.c_void_p, C.c_uint32, u64p],
     "nsmh_sketch": [C.c_void_p],
     "nsmh_set_sketch_mode": [C.c_void_p, C.c_int],
     "nsmh_get_sketches": [C.c_void_p, u64p],

@@ -124,6 +124,18 @@ public:
         resRev.assign(ids.begin() + out_off[1], ids.begin() + out_off[2]);
     }
 
+    /** The candidate pre-filters of the consensus builder, computed on the device from the packed
+     *  reads: flags[i] & NSMH_FLAG_REPETITIVE == Consensus::checkRepetitive(i), i.e. isRepetitive[i]
+     *  of Consensus::initialize (Consensus.cpp:405-442); flags[i] & NSMH_FLAG_SHORT == the
+     *  `size() < 32` gate of addRelatedReads (Consensus.cpp:213).  Valid after initialize(). */
+    void readFlags(std::vector<uint8_t> &flags) {
+        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::readFlags before initialize");
+        uint32_t numReads = 0;
+        check(nsmh_num_reads(h_, &numReads, nullptr));
+        flags.assign(numReads, 0);
+        check(nsmh_read_flags(h_, flags.data()));
+    }
+
     /** Generates a sequence of n kMer_t random numbers (ReadFilter.cpp:49-63). */
     void generateRandomNumbers(size_t count) {
         std::random_device rd;

@@ -222,7 +222,7 @@ int nsmh_destroy(nsmh_handle h) {
         cudaStream_t s = h->stream;
         free_ws(h->bulk, s);
         DevBuf *bufs[] = {&h->d_rand, &h->d_ftab_first, &h->d_ftab_next, &h->sketches,
-                          &h->tile_start, &h->counters, &h->build_multi, &h->build_tmp,
+                          &h->tile_start, &h->read_flags, &h->counters, &h->build_multi, &h->build_tmp,
                           &h->tables.slots, &h->tables.ids};
         for (DevBuf *b : bufs) b->release(s);
         if (h->reads.external_offsets) { h->reads.offsets.p = nullptr; h->reads.offsets.cap = 0; }
@@ -257,6 +257,7 @@ static int set_offsets_host(nsmh_ctx *c, const uint64_t *offsets, uint32_t num_r
 
 static void invalidate(nsmh_ctx *c) {
     c->reads_loaded = false;
+    c->flags_valid = false;
     c->sketched = false;
     c->tables.built = false;
     c->bulk_valid = false;
@@ -506,6 +507,43 @@ int nsmh_query_all_device_ptrs(nsmh_handle c, uint64_t **d_offsets, uint32_t **d
     if (!c->bulk_valid) return fail(NSMH_ESTATE, "query_all_device_ptrs: no bulk query result");
     if (d_offsets) *d_offsets = c->bulk.out_off.as<uint64_t>();
     if (d_ids) *d_ids = c->bulk.out_ids.as<uint32_t>();
+    return NSMH_OK;
+}
+
+// ------------------------------------------------- caller-side pre-filters --
+static int ensure_flags(nsmh_ctx *c) {
+    if (!c->reads_loaded) return fail(NSMH_ESTATE, "read_flags: no reads loaded");
+    if (c->flags_valid) return NSMH_OK;
+    NSMH_TRY(compute_read_flags(c));
+    c->flags_valid = true;
+    return NSMH_OK;
+}
+
+int nsmh_read_flags(nsmh_handle c, uint8_t *out) {
+    CTX_GUARD(c);
+    NSMH_TRY(ensure_flags(c));
+    if (out && c->reads.num_reads)
+        NSMH_CK(cudaMemcpyAsync(out, c->read_flags.p, c->reads.num_reads, cudaMemcpyDeviceToHost, c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    return NSMH_OK;
+}
+
+int nsmh_read_flags_device_ptr(nsmh_handle c, uint8_t **d_flags) {
+    CTX_GUARD(c);
+    if (!d_flags) return fail(NSMH_EINVAL, "read_flags_device_ptr: null output");
+    NSMH_TRY(ensure_flags(c));
+    *d_flags = c->read_flags.as<uint8_t>();
+    return NSMH_OK;
+}
+
+int nsmh_query_all_drop(nsmh_handle c, uint32_t drop_mask, uint64_t *total_ids) {
+    CTX_GUARD(c);
+    if (!c->bulk_valid) return fail(NSMH_ESTATE, "query_all_drop: no bulk query result");
+    if (c->mg || c->id_base != 0 || c->table_reads != c->reads.num_reads)
+        return fail(NSMH_ESTATE, "query_all_drop: candidate ids are not ids of the loaded reads (multi-GPU result)");
+    NSMH_TRY(ensure_flags(c));
+    if (drop_mask) NSMH_TRY(drop_flagged_candidates(c, c->bulk, drop_mask, c->stream));
+    if (total_ids) *total_ids = c->bulk.last_total;
     return NSMH_OK;
 }
 

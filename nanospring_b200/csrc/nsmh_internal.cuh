@@ -150,6 +150,8 @@ struct nsmh_ctx {
     nsmh::DevBuf sketches;      // u64 [num_reads*n]
     bool sketched = false;
     nsmh::DevBuf tile_start;    // u32 [num_reads+1]
+    nsmh::DevBuf read_flags;    // u8 [num_reads]  NSMH_FLAG_* (prefilter.cu), valid when flags_valid
+    bool flags_valid = false;
     nsmh::DevBuf counters;      // u64 [8] device counters (fix-ups ...)
 
     const uint64_t *table_sketches = nullptr;   // rows the tables are built from
@@ -214,6 +216,10 @@ int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, u
 int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s);
 int count_lists_device(nsmh_ctx *c, QueryWs &ws, uint32_t nq, uint32_t parts, const uint64_t *const *d_offsets,
                        const uint32_t *const *d_ids, cudaStream_t s);
+
+// ---- prefilter.cu --------------------------------------------------------------
+int compute_read_flags(nsmh_ctx *c);
+int drop_flagged_candidates(nsmh_ctx *c, QueryWs &ws, uint32_t drop, cudaStream_t s);
 
 // ---- multi-GPU over peer memory (query.cu kernels, multigpu.cu orchestration) ----
 constexpr int kMgMaxRanks = NSMH_MG_MAX_RANKS;

@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 from . import _lib
-from ._lib import NSMH_ERANGE, NsmhError, SynthParams, Stats, check, lib, u32p, u64p
+from ._lib import NSMH_ERANGE, NsmhError, SynthParams, Stats, check, lib, u32p, u64p, u8p
 
 
 def rand_from_seed(seed, n):
@@ -204,6 +204,27 @@ class MinHashReadFilter:
         Returns (offsets u64[N+1], ids u32[total]) or just the total when fetch=False."""
         total = C.c_uint64(0)
         check(lib().nsmh_query_all(self._h, int(bool(reverseComplement)), C.byref(total)))
+        if not fetch:
+            return total.value
+        N = self.numReads()
+        off = np.zeros(N + 1, dtype=np.uint64)
+        ids = np.zeros(max(total.value, 1), dtype=np.uint32)
+        check(lib().nsmh_query_all_result(self._h, off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p)))
+        return off, ids[:total.value]
+
+    # -- candidate pre-filters of the consensus builder (csrc/prefilter.cu) ---------
+    def readFlags(self):
+        """u8[numReads]: bit 0 = Consensus::checkRepetitive (Consensus.cpp:405-424, i.e. isRepetitive[]
+        of Consensus::initialize), bit 1 = shorter than 32 bases (Consensus.cpp:213)."""
+        out = np.zeros(max(self.numReads(), 1), dtype=np.uint8)
+        check(lib().nsmh_read_flags(self._h, out.ctypes.data_as(u8p)))
+        return out[:self.numReads()]
+
+    def queryAllDrop(self, drop_mask=3, fetch=True):
+        """Drop the candidates whose flags intersect drop_mask from the CSR of the last queryAll, on
+        the device (the `continue`s at Consensus.cpp:204-216)."""
+        total = C.c_uint64(0)
+        check(lib().nsmh_query_all_drop(self._h, int(drop_mask), C.byref(total)))
         if not fetch:
             return total.value
         N = self.numReads()

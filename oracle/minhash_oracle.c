@@ -308,6 +308,29 @@ int orc_query_all(const orc_tables *T, const char *bases, const uint64_t *offset
 void orc_free(void *p) { free(p); }
 
 /* ------------------------------------------------------------------------- */
+/* Candidate pre-filters of the consensus builder.
+ * Consensus::checkRepetitive (src/Consensus.cpp:405-424): the read comes out of the 2-bit
+ * store ("ATCG"[code], dnaToBits.cpp:81-98); for every shift i in 1..6 count the positions j
+ * with read[j] == read[(j+i) % len]; repetitive when a count exceeds 0.7 * (double)len.
+ * The length gate `readStr1.size() < 32` is src/Consensus.cpp:213.
+ * flags[r]: bit 0 repetitive, bit 1 shorter than 32 bases.                 */
+void orc_read_flags(const char *bases, const uint64_t *offsets, uint32_t num_reads, uint8_t *flags) {
+#pragma omp parallel for schedule(dynamic, 64)
+    for (uint32_t r = 0; r < num_reads; ++r) {
+        const char *s = bases + offsets[r];
+        const size_t len = (size_t)(offsets[r + 1] - offsets[r]);
+        int rep = 0;
+        for (size_t i = 1; i <= 6 && !rep; ++i) {
+            size_t same = 0;
+            for (size_t j = 0; j < len; ++j)
+                if (orc_base_to_int(s[j]) == orc_base_to_int(s[(j + i) % len])) ++same;
+            if ((double)same > 0.7 * (double)len) rep = 1;
+        }
+        flags[r] = (uint8_t)(rep | (len < 32 ? 2 : 0));
+    }
+}
+
+/* ------------------------------------------------------------------------- */
 /* FNV-1a-64 over the little-endian bytes of u64 words: the checksum SURVEY.md
  * section 8(c) uses for its golden table.                                    */
 uint64_t orc_fnv1a64_u64(const uint64_t *p, size_t n, uint64_t h) {

@@ -98,6 +98,7 @@ class Oracle:
         L.orc_query_all.argtypes = [C.c_void_p, C.c_void_p, u64p, u64p, C.c_uint32, u64p, C.c_uint32,
                                     C.c_int, u64p, C.POINTER(C.c_void_p)]
         L.orc_free.argtypes = [C.c_void_p]
+        L.orc_read_flags.argtypes = [C.c_void_p, u64p, C.c_uint32, C.c_void_p]
         L.orc_fnv1a64_u64.restype = C.c_uint64
         L.orc_fnv1a64_u64.argtypes = [u64p, C.c_size_t, C.c_uint64]
         L.orc_fnv1a64_csr.restype = C.c_uint64
@@ -162,6 +163,14 @@ class Oracle:
                                 _p(sk, u64p))
         return sk
 
+    def read_flags(self, bases, offsets):
+        """bit 0: Consensus::checkRepetitive (Consensus.cpp:405-424); bit 1: len < 32 (Consensus.cpp:213)."""
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = np.zeros(offsets.size - 1, dtype=np.uint8)
+        self.lib.orc_read_flags(bases.ctypes.data, _p(offsets, u64p), offsets.size - 1, out.ctypes.data)
+        return out
+
     def build_tables(self, sketches):
         sk = np.ascontiguousarray(sketches, dtype=np.uint64)
         N, n = sk.shape
@@ -208,6 +217,44 @@ class OracleTables:
         self.orc.lib.orc_query_all(self.h, bases.ctypes.data, _p(offsets, u64p), _p(sk, u64p), k,
                                    _p(rnd, u64p), thr, int(rc), _p(out_off, u64p), C.byref(ids_ptr))
         return out_off, self._take(ids_ptr.value, int(out_off[-1]))
+
+
+REF_CONS_SO = os.path.join(HERE, "_ref", "libnsref_consensus.so")
+
+
+class RefConsensus:
+    """The reference's own consensus translation unit (oracle/_ref/libnsref_consensus.so):
+    Consensus::initialize / checkRepetitive (Consensus.cpp:405-442)."""
+    _inst = None
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_CONS_SO)
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = cls()
+        return cls._inst
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_CONS_SO)
+        L.nsref_consensus_is_repetitive.argtypes = [C.c_void_p, u64p, C.c_uint32, C.c_int, C.c_void_p]
+        L.nsref_check_repetitive.argtypes = [C.c_char_p, C.c_size_t]
+
+    def is_repetitive(self, bases, offsets, threads=0):
+        bases = np.ascontiguousarray(bases, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        out = np.zeros(offsets.size - 1, dtype=np.uint8)
+        rc = self.lib.nsref_consensus_is_repetitive(bases.ctypes.data, _p(offsets, u64p), offsets.size - 1, threads,
+                                                    out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("reference consensus harness failed")
+        return out
+
+    def check_repetitive(self, s):
+        s = s.encode() if isinstance(s, str) else bytes(s)
+        return bool(self.lib.nsref_check_repetitive(s, len(s)))
 
 
 class RefLib:
