@@ -81,6 +81,28 @@ int nsmh_load_reads_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32
                               uint32_t num_reads);
 int nsmh_num_reads(nsmh_handle h, uint32_t *num_reads, uint64_t *total_bases);
 
+/* ---- FASTQ ingest on the device (replaces ReadData::loadFromFile for
+ *      FASTQ / GZIP input, ReadData.cpp:12-26, 156-221, and the temp-file + mutex getRead,
+ *      ReadData.cpp:225-235).  Record semantics are the reference loader's: lines split at
+ *      '\n' only, record i = lines 4i..4i+3, its second line is the read (any bytes, no
+ *      '\r' stripping, no '@'/'+' checks), a last line without '\n' counts; a text that ends
+ *      inside a header line stores that header's bytes as the last read, as the reference
+ *      does.  The reads end up exactly as after nsmh_load_reads_ascii. ------------------- */
+/* Whole (inflated) FASTQ text in host memory: copied once, parsed and packed on the device. */
+int nsmh_load_fastq(nsmh_handle h, const char *text, size_t bytes);
+/* Same with the text already device-resident (device pointer; read-only, may be freed after). */
+int nsmh_load_fastq_device(nsmh_handle h, const char *d_text, size_t bytes);
+/* ReadData::loadFromFile(path, gzip ? GZIP : FASTQ): the file is read (and inflated with zlib
+ * when gzip != 0, concatenated members included) on the host in pinned chunks that stream to the
+ * device while the next chunk is produced; no temp file is written. */
+int nsmh_load_fastq_file(nsmh_handle h, const char *path, int gzip);
+/* Base offsets of the loaded reads: offsets[i] .. offsets[i+1] = read i, host u64 [num_reads+1]. */
+int nsmh_read_offsets(nsmh_handle h, uint64_t *offsets);
+/* ReadData::getRead for reads first .. first+count-1, concatenated: every base rendered as
+ * "ATCG"[code] from the device's 2-bit store (dnaToBits.cpp:81-98).  out: host buffer of
+ * offsets[first+count] - offsets[first] bytes.  Serialised with the other non-query calls. */
+int nsmh_get_reads_ascii(nsmh_handle h, uint32_t first, uint32_t count, char *out);
+
 /* ---- MinHashReadFilter::initialize() (ReadFilter.cpp:11-47), split in its two stages --- */
 /* Sketch every loaded read: sketches[read][hash], row-major u64, on the device. */
 int nsmh_sketch(nsmh_handle h);
@@ -195,6 +217,9 @@ typedef struct {
     uint64_t sketch_fixups;   /* (read,hash) pairs the exact fix-up pass had to rescan */
     uint64_t query_pairs;     /* gathered (query,id) pairs in the last bulk query */
     uint32_t kernel_launches; /* kernels launched by this handle since creation */
+    float fastq_parse_ms;     /* nsmh_load_fastq*: device time of parse + pack (text already on the device) */
+    float fastq_pack_ms;      /* ... of which the gather-pack kernel */
+    float fastq_load_ms;      /* nsmh_load_fastq / _file: whole call incl. file read, inflate and H2D (host clock) */
 } nsmh_stats;
 int nsmh_get_stats(nsmh_handle h, nsmh_stats *out);
 /* The engine's CUDA stream (cudaStream_t as void*), for event timing by the host program. */

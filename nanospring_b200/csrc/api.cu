@@ -4,7 +4,11 @@
 //   Compressor.cpp:69-76   rF.k/n/overlapSketchThreshold = ...; rF.initialize(rD)
 //   ReadFilter.cpp:11-47   initialize(): sketch all reads, populateHashTables()
 //   Consensus.cpp:189      rF->getFilteredReads(string, results)  (concurrent callers)
+#include <zlib.h>
+
 #include <algorithm>
+#include <chrono>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 
@@ -360,6 +364,189 @@ int nsmh_load_reads_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32
     if (rc) return rc;
     c->reads_loaded = true;
     return NSMH_OK;
+}
+
+// ------------------------------------------------------------ FASTQ ingest --
+// (kernels in fastq.cu)
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+int nsmh_load_fastq_device(nsmh_handle c, const char *d_text, size_t bytes) {
+    CTX_GUARD(c);
+    if (bytes && !d_text) return fail(NSMH_EINVAL, "load_fastq_device: null text");
+    invalidate(c);
+    uint8_t last = 0;
+    if (bytes) {
+        NSMH_CK(cudaMemcpyAsync(&last, d_text + bytes - 1, 1, cudaMemcpyDeviceToHost, c->stream));
+        NSMH_CK(cudaStreamSynchronize(c->stream));
+    }
+    NSMH_TRY(parse_fastq_device(c, reinterpret_cast<const uint8_t *>(d_text), bytes, bytes, last));
+    c->reads_loaded = true;
+    return NSMH_OK;
+}
+
+int nsmh_load_fastq(nsmh_handle c, const char *text, size_t bytes) {
+    CTX_GUARD(c);
+    if (bytes && !text) return fail(NSMH_EINVAL, "load_fastq: null text");
+    const double t0 = now_ms();
+    invalidate(c);
+    DevBuf d_text;
+    NSMH_TRY(d_text.ensure(bytes + 64, c->stream));
+    int rc = NSMH_OK;
+    cudaError_t e = cudaSuccess;
+    if (bytes && (e = cudaMemcpyAsync(d_text.p, text, bytes, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess)
+        rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
+    if (!rc) rc = parse_fastq_device(c, d_text.as<uint8_t>(), bytes, d_text.cap, bytes ? (uint8_t)text[bytes - 1] : 0);
+    d_text.release(c->stream);
+    if (rc) return rc;
+    c->stats.fastq_load_ms = (float)(now_ms() - t0);
+    c->reads_loaded = true;
+    return NSMH_OK;
+}
+
+namespace {
+// Sequential producer of the (inflated) file contents.
+struct TextSource {
+    FILE *f = nullptr;
+    bool gz = false, eof_in = false, done = false, at_boundary = true, z_init = false;
+    z_stream zs;
+    std::vector<uint8_t> in;
+    ~TextSource() {
+        if (z_init) inflateEnd(&zs);
+        if (f) fclose(f);
+    }
+    int open(const char *path, int gzip) {
+        f = fopen(path, "rb");
+        if (!f) return fail(NSMH_EINVAL, std::string("load_fastq_file: cannot open ") + path);
+        gz = gzip != 0;
+        if (gz) {
+            memset(&zs, 0, sizeof zs);
+            if (inflateInit2(&zs, 15 + 32) != Z_OK) return fail(NSMH_ENOMEM, "load_fastq_file: inflateInit2 failed");
+            z_init = true;
+            in.resize(1 << 20);
+        }
+        return NSMH_OK;
+    }
+    // bytes produced into out (0 = end of data), -1 = corrupt / truncated input
+    long fill(uint8_t *out, size_t cap) {
+        if (!gz) return (long)fread(out, 1, cap, f);
+        size_t produced = 0;
+        while (produced < cap && !done) {
+            if (zs.avail_in == 0 && !eof_in) {
+                const size_t got = fread(in.data(), 1, in.size(), f);
+                if (got == 0) eof_in = true;
+                zs.next_in = in.data();
+                zs.avail_in = (uInt)got;
+            }
+            if (zs.avail_in == 0 && eof_in) {
+                if (!at_boundary) return -1;       // the file ends inside a gzip member
+                done = true;
+                break;
+            }
+            zs.next_out = out + produced;
+            zs.avail_out = (uInt)std::min<size_t>(cap - produced, (size_t)INT_MAX);
+            const uInt before = zs.avail_out;
+            at_boundary = false;
+            const int zr = inflate(&zs, Z_NO_FLUSH);
+            produced += before - zs.avail_out;
+            if (zr == Z_STREAM_END) {
+                inflateReset(&zs);                 // a further gzip member may follow
+                at_boundary = true;
+            } else if (zr != Z_OK && zr != Z_BUF_ERROR) {
+                return -1;
+            }
+        }
+        return (long)produced;
+    }
+};
+}  // namespace
+
+int nsmh_load_fastq_file(nsmh_handle c, const char *path, int gzip) {
+    CTX_GUARD(c);
+    if (!path) return fail(NSMH_EINVAL, "load_fastq_file: null path");
+    const double t0 = now_ms();
+    TextSource src;
+    NSMH_TRY(src.open(path, gzip));
+    uint64_t file_size = 0;
+    if (fseek(src.f, 0, SEEK_END) == 0) {
+        const long sz = ftell(src.f);
+        if (sz > 0) file_size = (uint64_t)sz;
+        fseek(src.f, 0, SEEK_SET);
+    }
+    invalidate(c);
+    const size_t chunk = 32u << 20;
+    uint8_t *pin[2] = {nullptr, nullptr};
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    DevBuf d_text;
+    int rc = NSMH_OK;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && !rc; ++i) {
+        if ((e = cudaMallocHost(reinterpret_cast<void **>(&pin[i]), chunk)) != cudaSuccess) rc = cuda_fail(e, "pinned", __FILE__, __LINE__);
+        if (!rc && (e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
+    }
+    if (!rc) rc = d_text.ensure((gzip ? file_size * 4 : file_size) + chunk + 64, c->stream);
+    uint64_t used = 0;
+    int last = 0, bi = 0;
+    bool in_flight[2] = {false, false};
+    while (!rc) {
+        if (in_flight[bi] && (e = cudaEventSynchronize(copied[bi])) != cudaSuccess) { rc = cuda_fail(e, "sync", __FILE__, __LINE__); break; }
+        const long got = src.fill(pin[bi], chunk);     // overlaps the H2D copy of the other buffer
+        if (got < 0) { rc = fail(NSMH_EINVAL, std::string("load_fastq_file: corrupt or truncated gzip data in ") + path); break; }
+        if (got == 0) break;
+        if (used + (uint64_t)got + 64 > d_text.cap)
+            rc = d_text.ensure(std::max<uint64_t>(2 * d_text.cap, used + (uint64_t)got + 64), c->stream, used);
+        if (rc) break;
+        if ((e = cudaMemcpyAsync(d_text.as<uint8_t>() + used, pin[bi], (size_t)got, cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) { rc = cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
+        if ((e = cudaEventRecord(copied[bi], c->stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
+        in_flight[bi] = true;
+        last = pin[bi][got - 1];
+        used += (uint64_t)got;
+        bi ^= 1;
+    }
+    if (!rc) rc = parse_fastq_device(c, d_text.as<uint8_t>(), used, d_text.cap, last);
+    cudaStreamSynchronize(c->stream);
+    d_text.release(c->stream);
+    for (int i = 0; i < 2; ++i) {
+        if (pin[i]) cudaFreeHost(pin[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+    }
+    if (rc) return rc;
+    c->stats.fastq_load_ms = (float)(now_ms() - t0);
+    c->reads_loaded = true;
+    return NSMH_OK;
+}
+
+int nsmh_read_offsets(nsmh_handle c, uint64_t *offsets) {
+    CTX_GUARD(c);
+    if (!c->reads_loaded) return fail(NSMH_ESTATE, "read_offsets: no reads loaded");
+    if (!offsets) return fail(NSMH_EINVAL, "read_offsets: null output");
+    NSMH_CK(cudaMemcpyAsync(offsets, c->reads.offsets.p, ((size_t)c->reads.num_reads + 1) * sizeof(uint64_t),
+                            cudaMemcpyDeviceToHost, c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    return NSMH_OK;
+}
+
+int nsmh_get_reads_ascii(nsmh_handle c, uint32_t first, uint32_t count, char *out) {
+    CTX_GUARD(c);
+    if (!c->reads_loaded) return fail(NSMH_ESTATE, "get_reads_ascii: no reads loaded");
+    if ((uint64_t)first + count > c->reads.num_reads) return fail(NSMH_EINVAL, "get_reads_ascii: read range out of bounds");
+    if (!count) return NSMH_OK;
+    uint64_t be[2] = {0, 0};
+    NSMH_CK(cudaMemcpyAsync(&be[0], c->reads.d_offsets() + first, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    NSMH_CK(cudaMemcpyAsync(&be[1], c->reads.d_offsets() + first + count, sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    const uint64_t nb = be[1] - be[0];
+    if (!nb) return NSMH_OK;
+    if (!out) return fail(NSMH_EINVAL, "get_reads_ascii: null output");
+    DevBuf d;
+    NSMH_TRY(d.ensure(nb + 16, c->stream));
+    int rc = unpack_ascii_device(c, be[0], nb, d.as<uint8_t>(), c->stream);
+    cudaError_t e = cudaSuccess;
+    if (!rc && (e = cudaMemcpyAsync(out, d.p, nb, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) rc = cuda_fail(e, "d2h", __FILE__, __LINE__);
+    if (!rc && (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+    d.release(c->stream);
+    return rc;
 }
 
 int nsmh_num_reads(nsmh_handle c, uint32_t *num_reads, uint64_t *total_bases) {

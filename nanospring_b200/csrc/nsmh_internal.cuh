@@ -199,6 +199,10 @@ int pack_reverse_complement(const ReadSet &src, ReadSet &dst, cudaStream_t s, ui
 int pack_from_dnabitset(ReadSet &rs, const uint8_t *d_src, const uint64_t *d_src_byte_off,
                         cudaStream_t s, uint32_t *launches);
 
+// ---- fastq.cu ----------------------------------------------------------------
+int parse_fastq_device(nsmh_ctx *c, const uint8_t *d_text, uint64_t bytes, uint64_t safe_bytes, int last_byte);
+int unpack_ascii_device(nsmh_ctx *c, uint64_t b0, uint64_t nb, uint8_t *d_out, cudaStream_t s);
+
 // ---- sketch.cu ---------------------------------------------------------------
 int build_filter_tables(nsmh_ctx *c);
 int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &tile_start,

@@ -331,6 +331,70 @@ void orc_read_flags(const char *bases, const uint64_t *offsets, uint32_t num_rea
 }
 
 /* ------------------------------------------------------------------------- */
+/* FASTQ ingest: which bytes of a FASTQ text become the reads.
+ * Restates the record loop of ReadData::loadFromFastqFile_lowmem
+ * (src/ReadData.cpp:177-198; the CLI fixes low_mem = true, src/main.cpp:40):
+ *     while (getline(fin, line)) { getline(fin, line); <line is the read>; getline; getline; }
+ * with std::getline's behaviour restated explicitly: a call succeeds iff at least one
+ * byte (possibly just the '\n') is left; the returned line excludes the '\n'; a last
+ * line without '\n' is returned and sets eofbit; and a call made with eofbit already
+ * set fails WITHOUT clearing its string argument.  The last point is observable: when
+ * the text ends inside a header line (no '\n' after it), the second getline leaves the
+ * header bytes in `line` and they are stored as that record's read (the high-memory
+ * loader, :113-127, reads into a different string there and stores an empty or stale
+ * read instead; that loader is not reachable from the CLI).  No '\r' handling, no
+ * check of '@' / '+': every 4 lines, the second one, any bytes.
+ * start[i]/len[i] = byte range of read i inside text.  Returns the number of reads
+ * (records); only the first `cap` entries are written.                        */
+typedef struct { const char *t; size_t n, pos; int eof; } orc_lines;
+
+/* returns 1 and sets [*b, *e) on success; 0 on failure with [*b,*e) untouched */
+static int orc_getline(orc_lines *L, size_t *b, size_t *e) {
+    if (L->eof) return 0;                       /* sentry fails, string not erased */
+    if (L->pos >= L->n) {                       /* erase(), nothing extracted -> failbit|eofbit */
+        L->eof = 1;
+        *b = *e = L->n;
+        return 0;
+    }
+    const char *nl = memchr(L->t + L->pos, '\n', L->n - L->pos);
+    *b = L->pos;
+    if (nl) {
+        *e = (size_t)(nl - L->t);
+        L->pos = *e + 1;
+    } else {
+        *e = L->n;
+        L->pos = L->n;
+        L->eof = 1;
+    }
+    return 1;
+}
+
+uint64_t orc_fastq_index(const char *text, size_t bytes, uint64_t *start, uint64_t *len, uint64_t cap) {
+    orc_lines L = {text, bytes, 0, 0};
+    size_t b = 0, e = 0, tb, te;
+    uint64_t reads = 0;
+    while (orc_getline(&L, &b, &e)) {           /* header -> line */
+        orc_getline(&L, &b, &e);                /* read -> the same string */
+        if (reads < cap) {
+            start[reads] = b;
+            len[reads] = e - b;
+        }
+        ++reads;
+        tb = te = 0;
+        orc_getline(&L, &tb, &te);              /* '+' line (dropped) */
+        orc_getline(&L, &tb, &te);              /* quality line (dropped) */
+    }
+    return reads;
+}
+
+/* What ReadData::getRead hands back for stored bytes: the 2-bit code of every byte
+ * (src/dnaToBits.cpp:46-71) rendered through "ATCG"[code] (src/dnaToBits.cpp:81-98). */
+void orc_store_roundtrip(const char *in, size_t n, char *out) {
+    static const char tab[4] = {'A', 'T', 'C', 'G'};
+    for (size_t i = 0; i < n; ++i) out[i] = tab[orc_base_to_int(in[i])];
+}
+
+/* ------------------------------------------------------------------------- */
 /* FNV-1a-64 over the little-endian bytes of u64 words: the checksum SURVEY.md
  * section 8(c) uses for its golden table.                                    */
 uint64_t orc_fnv1a64_u64(const uint64_t *p, size_t n, uint64_t h) {

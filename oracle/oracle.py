@@ -18,6 +18,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libnsref.so")
+REF_READDATA_SO = os.path.join(HERE, "_ref", "libnsref_readdata.so")
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -105,6 +106,9 @@ class Oracle:
         L.orc_fnv1a64_csr.argtypes = [u64p, u32p, C.c_uint32]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_fastq_index.restype = C.c_uint64
+        L.orc_fastq_index.argtypes = [C.c_void_p, C.c_size_t, u64p, u64p, C.c_uint64]
+        L.orc_store_roundtrip.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
 
     # -- small helpers -----------------------------------------------------
     def rand_from_seed(self, seed, n):
@@ -151,6 +155,38 @@ class Oracle:
 
     def num_threads(self):
         return int(self.lib.orc_num_threads())
+
+    # -- FASTQ ingest ---------------------------------------
+    def fastq_index(self, text):
+        """(start, len) byte ranges of the reads of a FASTQ text, ReadData.cpp:177-198."""
+        t = np.frombuffer(bytes(text), dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, np.uint8)
+        cap = int((t == 10).sum()) // 4 + 2
+        start = np.zeros(cap, dtype=np.uint64)
+        ln = np.zeros(cap, dtype=np.uint64)
+        n = int(self.lib.orc_fastq_index(t.ctypes.data if t.size else None, t.size, _p(start, u64p), _p(ln, u64p), cap))
+        assert n <= cap
+        return start[:n].copy(), ln[:n].copy()
+
+    def fastq_reads(self, text):
+        """(bases uint8[total], offsets uint64[N+1]): the bytes the loader stores, in file order."""
+        t = np.frombuffer(bytes(text), dtype=np.uint8) if not isinstance(text, np.ndarray) else np.ascontiguousarray(text, np.uint8)
+        start, ln = self.fastq_index(t)
+        offsets = np.zeros(start.size + 1, dtype=np.uint64)
+        offsets[1:] = np.cumsum(ln, dtype=np.uint64)
+        if start.size == 0 or int(offsets[-1]) == 0:
+            return np.zeros(0, np.uint8), offsets
+        # gather: index of every stored byte = its read's start + position inside the read
+        reps = ln.astype(np.int64)
+        src = np.repeat(start.astype(np.int64) - offsets[:-1].astype(np.int64), reps) + np.arange(int(offsets[-1]), dtype=np.int64)
+        return t[src].copy(), offsets
+
+    def store_roundtrip(self, bases):
+        """"ATCG"[code] of every byte: what ReadData::getRead returns (dnaToBits.cpp:46-98)."""
+        b = np.ascontiguousarray(bases, dtype=np.uint8)
+        out = np.zeros(b.size, dtype=np.uint8)
+        if b.size:
+            self.lib.orc_store_roundtrip(b.ctypes.data, b.size, out.ctypes.data)
+        return out
 
     # -- bulk --------------------------------------------------------------
     def sketch_all(self, bases, offsets, k, n, rnd):
@@ -255,6 +291,63 @@ class RefConsensus:
     def check_repetitive(self, s):
         s = s.encode() if isinstance(s, str) else bytes(s)
         return bool(self.lib.nsref_check_repetitive(s, len(s)))
+
+
+class RefReadData:
+    """The reference's own read loader (oracle/_ref/libnsref_readdata.so = unmodified
+    src/ReadData.cpp + src/dnaToBits.cpp, oracle/ref/readdata_harness.cpp)."""
+    _inst = None
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_READDATA_SO)
+
+    @classmethod
+    def get(cls):
+        if cls._inst is None:
+            cls._inst = cls()
+        return cls._inst
+
+    def __init__(self):
+        L = self.lib = C.CDLL(REF_READDATA_SO)
+        L.nsrd_load.restype = C.c_void_p
+        L.nsrd_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_char_p]
+        L.nsrd_num_reads.restype = C.c_uint32
+        L.nsrd_num_reads.argtypes = [C.c_void_p]
+        for f in (L.nsrd_avg_read_len, L.nsrd_max_read_len):
+            f.restype = C.c_uint64
+            f.argtypes = [C.c_void_p]
+        L.nsrd_lengths.argtypes = [C.c_void_p, u64p]
+        L.nsrd_all_reads.argtypes = [C.c_void_p, C.c_void_p]
+        L.nsrd_free.argtypes = [C.c_void_p]
+
+    def load(self, path, gzip_flag, low_mem=True):
+        """ReadData::loadFromFile(path, GZIP|FASTQ, low_mem) then getRead(0..N-1):
+        (bases uint8[total], offsets uint64[N+1], avgReadLen, maxReadLen)."""
+        with tempfile.TemporaryDirectory() as td:
+            h = self.lib.nsrd_load(os.fsencode(path), 2 if gzip_flag else 0, int(bool(low_mem)), os.fsencode(td))
+            if not h:
+                raise RuntimeError("reference ReadData::loadFromFile failed")
+            try:
+                n = int(self.lib.nsrd_num_reads(h))
+                ln = np.zeros(max(n, 1), dtype=np.uint64)
+                self.lib.nsrd_lengths(h, _p(ln, u64p))
+                ln = ln[:n]
+                offsets = np.zeros(n + 1, dtype=np.uint64)
+                offsets[1:] = np.cumsum(ln, dtype=np.uint64)
+                bases = np.zeros(int(offsets[-1]) + 1, dtype=np.uint8)
+                self.lib.nsrd_all_reads(h, bases.ctypes.data)
+                return (bases[:int(offsets[-1])].copy(), offsets, int(self.lib.nsrd_avg_read_len(h)),
+                        int(self.lib.nsrd_max_read_len(h)))
+            finally:
+                self.lib.nsrd_free(h)
+
+    def load_text(self, text, gzip_flag=False, low_mem=True):
+        with tempfile.TemporaryDirectory() as td:
+            p = os.path.join(td, "in.fastq" + (".gz" if gzip_flag else ""))
+            with (gzip.open(p, "wb") if gzip_flag else open(p, "wb")) as f:
+                f.write(bytes(text))
+            return self.load(p, gzip_flag, low_mem)
 
 
 class RefLib:

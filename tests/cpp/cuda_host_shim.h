@@ -1,0 +1,90 @@
+// TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile a kernel header
+// for the HOST and run it in lock step: every lane of a warp is an OS thread, warp collectives
+// (__shfl_up_sync, __reduce_add_sync) meet on a barrier.  One warp runs at a time, so only kernels
+// without block-level cooperation (no __syncthreads / shared memory) can be emulated - which is all
+// that nanospring_b200/csrc/fastq_kernels.cuh contains.
+#pragma once
+#include <stdint.h>
+
+#include <barrier>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(x)
+
+struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
+static thread_local emu_dim3 blockIdx, threadIdx;
+static emu_dim3 gridDim, blockDim;
+
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(uint32_t v) { return __builtin_ffs((int)v); }
+static inline uint32_t __vcmpeq4(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i)
+        if (((a >> (8 * i)) & 0xFF) == ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
+    return r;
+}
+static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31));
+}
+static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
+    return (uint32_t)((((((uint64_t)hi) << 32) | lo) << (sh & 31)) >> 32);
+}
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) {
+    return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+
+struct EmuWarp {
+    std::barrier<> bar{32};
+    uint32_t slot[32];
+};
+static thread_local EmuWarp *emu_warp = nullptr;
+static thread_local int emu_lane = 0;
+
+static inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, int d) {
+    EmuWarp *w = emu_warp;
+    w->slot[emu_lane] = v;
+    w->bar.arrive_and_wait();
+    const uint32_t r = emu_lane >= d ? w->slot[emu_lane - d] : v;
+    w->bar.arrive_and_wait();
+    return r;
+}
+static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
+    EmuWarp *w = emu_warp;
+    w->slot[emu_lane] = v;
+    w->bar.arrive_and_wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r += w->slot[i];
+    w->bar.arrive_and_wait();
+    return r;
+}
+
+// kernel<<<grid, block>>>(...) : body() is the kernel call with its arguments bound
+static inline void emu_launch(unsigned grid, unsigned block, const std::function<void()> &body) {
+    gridDim.x = grid;
+    blockDim.x = block;
+    for (unsigned b = 0; b < grid; ++b)
+        for (unsigned w0 = 0; w0 < block; w0 += 32) {
+            EmuWarp warp;
+            std::vector<std::thread> lanes;
+            for (int l = 0; l < 32; ++l)
+                lanes.emplace_back([&, l] {
+                    emu_warp = &warp;
+                    emu_lane = l;
+                    blockIdx.x = b;
+                    threadIdx.x = w0 + l;
+                    body();
+                });
+            for (auto &t : lanes) t.join();
+        }
+}
