@@ -53,6 +53,11 @@ typedef struct nsmh_ctx *nsmh_handle;
  *      ReadFilter.h:37-42; CLI defaults 23/60/6: main.cpp:57-62) ------------------- */
 int nsmh_create(uint32_t k, uint32_t n, uint32_t overlap_sketch_thr, const uint64_t *rand_numbers,
                 int device, nsmh_handle *out);
+/* Change k / n / threshold / random numbers of an existing handle.  Loaded reads stay on the
+ * device (the reference loads the reads first, Compressor.cpp:60, and configures the filter
+ * afterwards, :69-76); sketches and tables are dropped and must be recomputed. */
+int nsmh_set_params(nsmh_handle h, uint32_t k, uint32_t n, uint32_t overlap_sketch_thr,
+                    const uint64_t *rand_numbers);
 int nsmh_destroy(nsmh_handle h);
 const char *nsmh_last_error(void);
 const char *nsmh_version(void);

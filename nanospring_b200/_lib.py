@@ -28,7 +28,8 @@ class Stats(C.Structure):
     _fields_ = [("h2d_pack_ms", C.c_float), ("pack_ms", C.c_float), ("sketch_ms", C.c_float),
                 ("sketch_main_ms", C.c_float), ("build_ms", C.c_float), ("query_ms", C.c_float),
                 ("sketch_fixups", C.c_uint64), ("query_pairs", C.c_uint64),
-                ("kernel_launches", C.c_uint32)]
+                ("kernel_launches", C.c_uint32), ("fastq_parse_ms", C.c_float), ("fastq_pack_ms", C.c_float),
+                ("fastq_load_ms", C.c_float)]
 
 
 class SynthParams(C.Structure):
@@ -55,6 +56,12 @@ _SIGS = {
     "nsmh_load_reads_ascii_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64],
     "nsmh_load_reads_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
     "nsmh_num_reads": [C.c_void_p, u32p, u64p],
+    "nsmh_set_params": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, u64p],
+    "nsmh_load_fastq": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "nsmh_load_fastq_device": [C.c_void_p, C.c_void_p, C.c_size_t],
+    "nsmh_load_fastq_file": [C.c_void_p, C.c_char_p, C.c_int],
+    "nsmh_read_offsets": [C.c_void_p, u64p],
+    "nsmh_get_reads_ascii": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p],
     "nsmh_read_flags": [C.c_void_p, u8p],
     "nsmh_read_flags_device_ptr": [C.c_void_p, C.POINTER(C.c_void_p)],
     "nsmh_query_all_drop": [C.c_void_p, C.c_uint32, u64p],

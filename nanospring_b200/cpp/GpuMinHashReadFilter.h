@@ -48,6 +48,7 @@ public:
     void initialize(ReadData &rD) override {
         nsmh_destroy(h_);
         h_ = nullptr;
+        hostOffsets_.clear();
         if (randNumbers.size() != n) generateRandomNumbers(n);
         check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
                           device, &h_));
@@ -136,6 +137,45 @@ public:
         check(nsmh_read_flags(h_, flags.data()));
     }
 
+    /** SURVEY 8(f) N2 - ReadData::loadFromFile(fileName, FASTQ|GZIP, low_mem) (ReadData.cpp:12-26,
+     *  156-221) and initialize() in one step, without the host 2-bit store: the file is read (and
+     *  inflated) on the host, records are split and packed by kernels (csrc/fastq.cu), and the packed
+     *  reads are sketched where they are.  No temp file, no getRead() round trip.  getNumReads() /
+     *  getRead() below then serve the reads from the device store. */
+    void initializeFromFile(const char *fileName, ReadData::Filetype filetype) {
+        if (filetype != ReadData::FASTQ && filetype != ReadData::GZIP)
+            throw std::runtime_error("GpuMinHashReadFilter::initializeFromFile: FASTQ or GZIP input only");
+        nsmh_destroy(h_);
+        h_ = nullptr;
+        hostOffsets_.clear();
+        if (randNumbers.size() != n) generateRandomNumbers(n);
+        check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
+                          device, &h_));
+        check(nsmh_load_fastq_file(h_, fileName, filetype == ReadData::GZIP ? 1 : 0));
+        check(nsmh_sketch(h_));
+        check(nsmh_build(h_));
+    }
+
+    /** ReadData::getNumReads (ReadData.cpp:223) of the reads on the device. */
+    read_t getNumReads() {
+        uint32_t numReads = 0;
+        if (h_) check(nsmh_num_reads(h_, &numReads, nullptr));
+        return numReads;
+    }
+
+    /** ReadData::getRead (ReadData.cpp:225-235) from the device's 2-bit store: "ATCG"[code] per base.
+     *  Not re-entrant (a bulk accessor; the reference's own getRead takes a global mutex). */
+    void getRead(read_t readId, std::string &readStr) {
+        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::getRead before initialize");
+        if (hostOffsets_.empty()) {
+            hostOffsets_.resize((size_t)getNumReads() + 1);
+            check(nsmh_read_offsets(h_, hostOffsets_.data()));
+        }
+        if ((size_t)readId + 1 >= hostOffsets_.size()) throw std::runtime_error("GpuMinHashReadFilter::getRead: bad read id");
+        readStr.resize(hostOffsets_[readId + 1] - hostOffsets_[readId]);
+        check(nsmh_get_reads_ascii(h_, readId, 1, readStr.empty() ? nullptr : &readStr[0]));
+    }
+
     /** Generates a sequence of n kMer_t random numbers (ReadFilter.cpp:49-63). */
     void generateRandomNumbers(size_t count) {
         std::random_device rd;
@@ -147,6 +187,7 @@ public:
 
 private:
     nsmh_handle h_ = nullptr;
+    std::vector<uint64_t> hostOffsets_;     // filled by the first getRead()
 
     static void check(int rc) {
         if (rc != NSMH_OK) throw std::runtime_error(std::string("nsmh: ") + nsmh_last_error());

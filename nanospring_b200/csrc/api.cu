@@ -209,6 +209,33 @@ int nsmh_create(uint32_t k, uint32_t n, uint32_t thr, const uint64_t *rand_numbe
     return NSMH_OK;
 }
 
+int nsmh_set_params(nsmh_handle c, uint32_t k, uint32_t n, uint32_t thr, const uint64_t *rand_numbers) {
+    CTX_GUARD(c);
+    if (k < 1 || k > 31) return fail(NSMH_EINVAL, "set_params: k must be in 1..31");
+    if (n < 1) return fail(NSMH_EINVAL, "set_params: n must be >= 1");
+    if (!rand_numbers) return fail(NSMH_EINVAL, "set_params: rand_numbers is null");
+    if (c->mg) return fail(NSMH_ESTATE, "set_params: not allowed once nsmh_mg_init has been called");
+    NSMH_CK(cudaStreamSynchronize(c->stream));
+    NSMH_CK(cudaStreamSynchronize(c->copy_stream));   // a table pre-clear of the old geometry may be in flight
+    // the loaded reads stay; everything derived from the old parameters goes
+    c->sketched = false;
+    c->tables.built = false;
+    c->bulk_valid = false;
+    c->table_sketches = nullptr;
+    c->table_reads = 0;
+    c->id_base = 0;
+    c->precleared_rows = 0;
+    c->precleared_ptr = nullptr;
+    c->k = k;
+    c->n = n;
+    c->thr = thr;
+    c->rand.assign(rand_numbers, rand_numbers + n);
+    NSMH_TRY(c->d_rand.ensure(n * sizeof(uint64_t), c->stream));
+    NSMH_CK(cudaMemcpyAsync(c->d_rand.p, c->rand.data(), n * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    NSMH_TRY(build_filter_tables(c));
+    return NSMH_OK;
+}
+
 int nsmh_destroy(nsmh_handle h) {
     if (!h) return NSMH_OK;
     std::string keep = g_err;

@@ -59,6 +59,95 @@ class ReadData:
         return self.bases[int(self.offsets[i]):int(self.offsets[i + 1])].tobytes()
 
 
+class GpuReadData:
+    """The reference's ReadData with the loader on the device.
+
+    Reference: ReadData::loadFromFile(fileName, FASTQ|GZIP, low_mem) (ReadData.cpp:12-26, 156-221)
+    parses the FASTQ text on one host thread, 2-bit packs every read (DnaBitset) into a temp file and
+    serves getRead() through a mutex + seekg (ReadData.cpp:225-235).  Here the host only reads (and
+    inflates) the file; record splitting, the 2-bit pack and getRead's unpack are kernels
+    (csrc/fastq.cu) and the packed reads stay on the device, where MinHashReadFilter.initialize(rD)
+    sketches them without another copy.  Same public surface: tempDir, avgReadLen, maxReadLen,
+    loadFromFile, getNumReads, getRead."""
+
+    FASTQ, READ, GZIP = 0, 1, 2            # enum Filetype, ReadData.h:23
+
+    def __init__(self, device=0):
+        self.device = device
+        self.tempDir = ""                   # interface parity; no temp file is written
+        self.avgReadLen = 0
+        self.maxReadLen = 0
+        self.numReads = 0
+        self.offsets = np.zeros(1, dtype=np.uint64)
+        self._h = None
+
+    def _handle(self):
+        if self._h is None:
+            h = C.c_void_p()
+            rnd = np.zeros(1, dtype=np.uint64)      # placeholder parameters; the filter sets the real ones
+            check(lib().nsmh_create(23, 1, 1, rnd.ctypes.data_as(u64p), self.device, C.byref(h)))
+            self._h = h
+        return self._h
+
+    def close(self):
+        if self._h is not None:
+            lib().nsmh_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _loaded(self):
+        n = C.c_uint32(0)
+        check(lib().nsmh_num_reads(self._h, C.byref(n), None))
+        self.numReads = n.value
+        self.offsets = np.zeros(self.numReads + 1, dtype=np.uint64)
+        check(lib().nsmh_read_offsets(self._h, self.offsets.ctypes.data_as(u64p)))
+        lens = np.diff(self.offsets.astype(np.int64))
+        self.maxReadLen = int(lens.max()) if lens.size else 0                 # ReadData.cpp:182-183
+        self.avgReadLen = int(lens.sum() // max(self.numReads, 1))             # ReadData.cpp:200
+
+    def loadFromFile(self, fileName, filetype=0, low_mem=False):
+        """low_mem is accepted for signature parity: nothing is spilled to disk either way."""
+        if filetype not in (self.FASTQ, self.GZIP):
+            raise ValueError("GpuReadData: only FASTQ and GZIP inputs (the two the CLI passes, main.cpp:141-145)")
+        check(lib().nsmh_load_fastq_file(self._handle(), os.fsencode(fileName), int(filetype == self.GZIP)))
+        self._loaded()
+
+    def loadFromText(self, text):
+        """The (inflated) FASTQ text as bytes / uint8 array in host memory."""
+        t = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray, memoryview)) else \
+            np.ascontiguousarray(text, dtype=np.uint8)
+        check(lib().nsmh_load_fastq(self._handle(), t.ctypes.data if t.size else None, t.size))
+        self._loaded()
+
+    def loadFromDeviceText(self, d_text_ptr, nbytes):
+        check(lib().nsmh_load_fastq_device(self._handle(), d_text_ptr, nbytes))
+        self._loaded()
+
+    def getNumReads(self):
+        return self.numReads
+
+    def getReads(self, first, count):
+        """Concatenated getRead(first) .. getRead(first+count-1) as one uint8 array."""
+        nb = int(self.offsets[first + count] - self.offsets[first])
+        out = np.zeros(max(nb, 1), dtype=np.uint8)
+        check(lib().nsmh_get_reads_ascii(self._h, first, count, out.ctypes.data))
+        return out[:nb]
+
+    def getRead(self, i):
+        """ReadData::getRead: "ATCG"[code] of every stored base (dnaToBits.cpp:81-98)."""
+        return self.getReads(i, 1).tobytes()
+
+    def stats(self):
+        st = Stats()
+        check(lib().nsmh_get_stats(self._h, C.byref(st)))
+        return {f: getattr(st, f) for f, _ in Stats._fields_}
+
+
 class MinHashReadFilter:
     """Drop-in for the reference's MinHashReadFilter, computing on one B200."""
 
@@ -72,12 +161,15 @@ class MinHashReadFilter:
         self.sketchMode = 0                 # 0 filtered kernel, 1 brute force (same results)
         self._h = None
         self._rd = None
+        self._borrowed = False              # handle owned by a GpuReadData
 
     # -- lifetime ----------------------------------------------------------------
     def close(self):
         if self._h is not None:
-            lib().nsmh_destroy(self._h)
+            if not self._borrowed:
+                lib().nsmh_destroy(self._h)
             self._h = None
+            self._borrowed = False
 
     def __del__(self):
         try:
@@ -136,8 +228,27 @@ class MinHashReadFilter:
     def build(self):
         check(lib().nsmh_build(self._h))
 
+    def _adopt(self, rD):
+        """Reads already packed on the device by GpuReadData: take its handle, set k/n/thr/rand."""
+        self.close()
+        if rD._h is None:
+            raise RuntimeError("GpuReadData: nothing loaded")
+        if self.randNumbers is None:
+            self.generateRandomNumbers(self.n)
+        rnd = np.ascontiguousarray(self.randNumbers, dtype=np.uint64)
+        if rnd.size != self.n:
+            raise ValueError("randNumbers must hold n values")
+        check(lib().nsmh_set_params(rD._h, self.k, self.n, self.overlapSketchThreshold, rnd.ctypes.data_as(u64p)))
+        self._h, self._borrowed, self._rd = rD._h, True, rD
+        check(lib().nsmh_set_sketch_mode(self._h, int(self.sketchMode)))
+
     def initialize(self, rD):
         """ReadFilter.cpp:11-47: sketch every read, then populate the n hash tables."""
+        if isinstance(rD, GpuReadData):
+            self._adopt(rD)
+            self.sketch()
+            self.build()
+            return
         self._create()
         self.load(rD)
         self.sketch()
