@@ -168,6 +168,84 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------
+def ingest_leg(local_rank, d_bases, offsets, steps, hbm_peak):
+    """SURVEY 8(f) N2, reported beside the headline: FASTQ text -> packed reads on the device
+    (csrc/fastq.cu) for the first INGEST_READS reads of the workload, (a) text already in HBM,
+    (b) text in pinned host memory (H2D inside the timed region), and the reference's own loader
+    (oracle/_ref/libnsref_readdata.so, ReadData::loadFromFile low_mem = true) on a bounded sample."""
+    import tempfile
+    import torch
+    import nanospring_b200 as ns
+    INGEST_READS = 25_000
+    n = min(INGEST_READS, offsets.size - 1)
+    L = torch.from_numpy(np.diff(offsets[:n + 1].astype(np.int64))).cuda()
+    nb = int(offsets[n])
+    rec = 2 * L + 6                                       # "@\n" seq "\n+\n" qual "\n"
+    start = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    torch.cumsum(rec, 0, out=start[1:])
+    nbytes = int(start[-1].item())
+    text = torch.full((nbytes + 64,), ord("I"), dtype=torch.uint8, device="cuda")
+    s0 = start[:-1]
+    seq0 = s0 + 2
+    text[s0] = ord("@")
+    text[s0 + 1] = 10
+    off_d = torch.from_numpy(offsets[:n].astype(np.int64)).cuda()
+    idx = torch.repeat_interleave(seq0 - off_d, L) + torch.arange(nb, dtype=torch.int64, device="cuda")
+    text[idx] = d_bases[:nb]
+    del idx
+    text[seq0 + L] = 10
+    text[seq0 + L + 1] = ord("+")
+    text[seq0 + L + 2] = 10
+    text[start[1:] - 1] = 10
+    torch.cuda.synchronize()
+    rd = ns.GpuReadData(device=local_rank)
+    for _ in range(2):
+        rd.loadFromDeviceText(text.data_ptr(), nbytes)
+    assert rd.getNumReads() == n and int(rd.offsets[-1]) == nb, "ingest: wrong read table"
+    ms, pk = [], []
+    for _ in range(steps):
+        rd.loadFromDeviceText(text.data_ptr(), nbytes)
+        st = rd.stats()
+        ms.append(st["fastq_parse_ms"])
+        pk.append(st["fastq_pack_ms"])
+    dev_ms = float(np.mean(ms))
+    alg_bytes = nbytes + nb + nb / 4 + 8 * n             # text once, read lines again, packed words + offsets out
+    h_text = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_text.copy_(text[:nbytes])
+    torch.cuda.synchronize()
+    rd.loadFromText(h_text.numpy())
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rd.loadFromText(h_text.numpy())
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    out = {"workload": f"FASTQ text of the first {n} reads ({nb / 1e9:.3f} Gbases, {nbytes / 1e9:.3f} GB of text)",
+           "device_ms": dev_ms, "device_gbases_per_s": nb / (dev_ms * 1e-3) / 1e9, "pack_kernel_ms": float(np.mean(pk)),
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / (dev_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / (dev_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg_bytes},
+           "e2e_host_text_ms": e2e_ms, "e2e_gbases_per_s": nb / (e2e_ms * 1e-3) / 1e9, "h2d_bytes": nbytes}
+    rd.close()
+    try:
+        from oracle.oracle import RefReadData
+        if RefReadData.available():
+            m = min(n, 2_000)
+            mb = int(start[m].item())
+            with tempfile.TemporaryDirectory() as td:
+                pth = os.path.join(td, "sample.fastq")
+                with open(pth, "wb") as f:
+                    f.write(h_text.numpy()[:mb].tobytes())
+                t0 = time.perf_counter()
+                _, roff, _, _ = RefReadData.get().load(pth, False, True)
+                dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": int(roff[-1]) / dt / 1e9, "unit": "Gbases/s", "cores": 1, "kind": "reference",
+                                   "sample": f"first {m} records ({mb / 1e6:.0f} MB of text): ReadData::loadFromFile "
+                                             f"(FASTQ, low_mem) + getRead of every read", "seconds": dt}
+    except Exception as e:  # noqa: BLE001
+        out["cpu_baseline"] = {"error": str(e)[:200]}
+    del text
+    return out
+
+
+# ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -177,6 +255,7 @@ def main():
     ap.add_argument("--sketch-mode", type=int, default=0, help="0 filtered kernel, 1 brute force")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the FASTQ-ingest side measurement (N=1 only)")
     ap.add_argument("--multi", default="auto", choices=["auto", "peer", "replicated", "partitioned"],
                     help="N>1: tables partitioned by hash function with exchanges over NVLink peer memory inside the "
                          "kernels (peer, default), the same with NCCL all-to-alls (partitioned), or NCCL all-gather "
@@ -231,10 +310,41 @@ def main():
     rows_per_rank = [READS_PER_GPU] * world
     multi = args.multi if args.multi != "auto" else "peer"
     pf = None
-    if world > 1 and multi == "partitioned":
+    multi_note = None
+    if world > 1 and multi == "peer":
+        # Peer-memory path (cudaIpc arenas + device-side flag barriers).  In auto mode one trial step
+        # runs first and all ranks agree on the outcome; if any rank cannot set it up (no P2P access,
+        # IPC refused, a barrier timing out), every rank switches to the NCCL all-gather strategy.
+        ok, why = 1, ""
+        try:
+            pf = shard.PeerPartitionedFilter(f, rank, world, rows_per_rank)
+            f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
+            f.sketch()
+            pf.run(lengths.size, rows_per_rank)
+        except Exception as e:  # noqa: BLE001
+            if args.multi != "auto":
+                raise
+            ok, why = 0, f"{type(e).__name__}: {e}"[:200]
+        if args.multi == "auto":
+            t = torch.tensor([ok], device="cuda", dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                log(f"[rank {rank}] peer-memory path unavailable ({why or 'another rank failed'}); using NCCL all-gather")
+                multi, multi_note = "replicated", "auto: peer-memory path failed its trial step, fell back to NCCL all-gather"
+                try:
+                    if pf is not None:
+                        pf.shutdown()
+                except Exception:  # noqa: BLE001
+                    pass
+                pf = None
+                f.close()
+                f = ns.MinHashReadFilter(device=local_rank)
+                f.k, f.n, f.overlapSketchThreshold = K, NHASH, THR
+                f.randNumbers = ns.rand_from_seed(RAND_SEED, NHASH)
+                f.sketchMode = args.sketch_mode
+                f._create()
+    elif world > 1 and multi == "partitioned":
         pf = shard.PartitionedFilter(f, rank, world)
-    elif world > 1 and multi == "peer":
-        pf = shard.PeerPartitionedFilter(f, rank, world, rows_per_rank)
     ext = torch.cuda.ExternalStream(f.stream(), device=local_rank)
     keep = {}
 
@@ -361,7 +471,7 @@ def main():
         "config": {"workload": workload_name(n_gpus), "k": K, "num_hash": NHASH, "overlap_sketch_thr": THR,
                    "reads_per_gpu": READS_PER_GPU, "bases_per_gpu": total_bases, "mean_read_len": mean_len,
                    "sketch_mode": "filter" if args.sketch_mode == 0 else "brute",
-                   "multi_gpu": ("n/a" if world == 1 else multi),
+                   "multi_gpu": ("n/a" if world == 1 else multi), **({"multi_gpu_note": multi_note} if multi_note else {}),
                    "l2": "inputs larger than L2 (1 GB ASCII + 0.25 GB packed per step vs 126 MB L2)",
                    "step": "pack + sketch + build tables + bulk forward lookup, CSR left on device"},
         "phases_last_step": phases,
@@ -371,6 +481,13 @@ def main():
         "roofline": roofline,
         "clocks": clocks,
     }
+
+    # ---- FASTQ ingest: a side measurement, never part of `value` ----
+    if n_gpus == 1 and not args.no_ingest and not args.no_e2e:
+        try:
+            line["ingest"] = ingest_leg(local_rank, d_bases, offsets, args.steps, hbm_peak)
+        except Exception as e:  # noqa: BLE001
+            line["ingest"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample ----
     if n_gpus == 1 and not args.no_cpu_baseline:
