@@ -38,6 +38,11 @@ READS_PER_GPU = 100_000
 MEAN_LEN = 10_000
 RAND_SEED = 20261017
 GENOME_LEN = 50_000_000
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on exactly this
+# workload (rank-0 shard, k=23 n=60), from the `ncu --set full` capture summarised in
+# profiles/r1_ncu_full_s4_summary.txt.  A recorded figure, not measured by this run.
+NCU_TRAFFIC_BYTES = {"sketch_filter_kernel": 300_792_000 + 38_677_504}
+NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_s4_summary.txt (ncu --set full, one launch)"
 
 
 def log(*a):
@@ -444,9 +449,11 @@ def main():
     # the reference's operation count on the INT32 pipe: (6n+6) lane-ops per base
     int_ops = total_bases * (6 * NHASH + 6)
     int_peak = 148 * 64 * sm_max * 1e6          # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH rt_SMSP=2)
-    roofline = {"bound": "hbm", "kernel": "sketch_filter_kernel" if args.sketch_mode == 0 else "sketch_brute_kernel",
+    dominant = "sketch_filter_kernel" if args.sketch_mode == 0 else "sketch_brute_kernel"
+    roofline = {"bound": "hbm", "kernel": dominant,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": None,
+                "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES.get(dominant) if rank == 0 else None,
+                "traffic_source": NCU_TRAFFIC_SOURCE if dominant in NCU_TRAFFIC_BYTES else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sk_ms,
                 "kernel_gbases_per_s": total_bases / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else None,
                 "int32_reference_count": {"lane_ops_per_base": 6 * NHASH + 6,

@@ -226,13 +226,26 @@ class PeerPartitionedFilter:
         if rows.size != world:
             raise ValueError("rows_per_rank must have one entry per rank")
         token = (C.c_uint8 * MG_TOKEN_BYTES)()
-        check(lib().nsmh_mg_init(self.f._h, rank, world, rows.ctypes.data_as(u32p), token))
+        # A rank whose arena could not be set up still takes part in the token exchange (with an
+        # empty token), so that the ranks never sit in different collectives; all of them then raise.
+        init_error = None
+        try:
+            check(lib().nsmh_mg_init(self.f._h, rank, world, rows.ctypes.data_as(u32p), token))
+        except Exception as e:  # noqa: BLE001
+            init_error = e
+        mine = b"" if init_error is not None else bytes(token)
         tokens = [None] * world
         if world > 1:
             import torch.distributed as dist
-            dist.all_gather_object(tokens, bytes(token), group=group)
+            dist.all_gather_object(tokens, mine, group=group)
         else:
-            tokens[0] = bytes(token)
+            tokens[0] = mine
+        if init_error is not None:
+            raise init_error
+        bad = [r for r, t in enumerate(tokens) if len(t) != MG_TOKEN_BYTES]
+        if bad:
+            lib().nsmh_mg_shutdown(self.f._h)
+            raise RuntimeError(f"nsmh_mg_init failed on rank(s) {bad}")
         blob = b"".join(tokens)
         check(lib().nsmh_mg_connect(self.f._h, blob))
         self.last_ms = {}
