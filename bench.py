@@ -173,19 +173,14 @@ def reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------------------------------
-def ingest_leg(local_rank, d_bases, offsets, steps, hbm_peak):
-    """SURVEY 8(f) N2, reported beside the headline: FASTQ text -> packed reads on the device
-    (csrc/fastq.cu) for the first INGEST_READS reads of the workload, (a) text already in HBM,
-    (b) text in pinned host memory (H2D inside the timed region), and the reference's own loader
-    (oracle/_ref/libnsref_readdata.so, ReadData::loadFromFile low_mem = true) on a bounded sample."""
-    import tempfile
+def fastq_text_device(d_bases, offsets, max_reads):
+    """FASTQ text ("@\n" seq "\n+\n" qual "\n" per record) of the first max_reads reads, built on the device.
+    Returns (text u8 tensor with 64 spare bytes, text bytes, bases, reads, record starts int64[reads+1])."""
     import torch
-    import nanospring_b200 as ns
-    INGEST_READS = 25_000
-    n = min(INGEST_READS, offsets.size - 1)
+    n = min(max_reads, offsets.size - 1)
     L = torch.from_numpy(np.diff(offsets[:n + 1].astype(np.int64))).cuda()
     nb = int(offsets[n])
-    rec = 2 * L + 6                                       # "@\n" seq "\n+\n" qual "\n"
+    rec = 2 * L + 6
     start = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
     torch.cumsum(rec, 0, out=start[1:])
     nbytes = int(start[-1].item())
@@ -203,6 +198,18 @@ def ingest_leg(local_rank, d_bases, offsets, steps, hbm_peak):
     text[seq0 + L + 2] = 10
     text[start[1:] - 1] = 10
     torch.cuda.synchronize()
+    return text, nbytes, nb, n, start
+
+
+def ingest_leg(local_rank, d_bases, offsets, steps, hbm_peak):
+    """SURVEY 8(f) N2, reported beside the headline: FASTQ text -> packed reads on the device
+    (csrc/fastq.cu) for the first INGEST_READS reads of the workload, (a) text already in HBM,
+    (b) text in pinned host memory (H2D inside the timed region), and the reference's own loader
+    (oracle/_ref/libnsref_readdata.so, ReadData::loadFromFile low_mem = true) on a bounded sample."""
+    import tempfile
+    import torch
+    import nanospring_b200 as ns
+    text, nbytes, nb, n, start = fastq_text_device(d_bases, offsets, 25_000)
     rd = ns.GpuReadData(device=local_rank)
     for _ in range(2):
         rd.loadFromDeviceText(text.data_ptr(), nbytes)

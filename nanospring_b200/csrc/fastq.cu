@@ -5,7 +5,7 @@
 //   ReadData::getRead                    (src/ReadData.cpp:225-235): mutex + seekg + unpack per call
 // The inflated text is copied to the device once; everything else happens there:
 //
-//   fastq_count_newlines_kernel   a warp per 512-byte tile, 128-bit loads, byte compares (HBM: text once)
+//   fastq_count_newlines_kernel   a warp per 4 x 512-byte tiles, 128-bit loads, byte compares (HBM: text once)
 //   (CUB exclusive sum over the tile counts)
 //   fastq_write_newlines_kernel   ordered byte positions of all '\n' (only tiles that have one are re-read)
 //   fastq_read_table_kernel       a thread per record: byte range of its second line = the read
@@ -21,6 +21,7 @@
 // start with, a missing second line gives an empty read - except when the text ends inside the
 // header line itself (no '\n' after it), where the reference stores the header bytes as the read.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nsmh_internal.cuh"
 #include "fastq_kernels.cuh"
@@ -56,7 +57,7 @@ int parse_fastq_device(nsmh_ctx *c, const uint8_t *d_text, uint64_t bytes, uint6
     FQ_CK(cudaMemsetAsync(flag.p, 0, sizeof(unsigned long long), s));
     if (!rc) FQ_CK(cudaMemsetAsync(tile_cnt.as<uint32_t>() + ntiles, 0, sizeof(uint32_t), s));
     if (!rc && ntiles) {
-        fastq_count_newlines_kernel<<<grid_warps(ntiles, c->num_sms), 256, 0, s>>>(d_text, bytes, aligned16, ntiles,
+        fastq_count_newlines_kernel<<<grid_warps((ntiles + kFqCountTiles - 1) / kFqCountTiles, c->num_sms), 256, 0, s>>>(d_text, bytes, aligned16, ntiles,
                                                                                   tile_cnt.as<uint32_t>());
         ++c->launches;
         FQ_CK(cudaGetLastError());
@@ -79,7 +80,7 @@ int parse_fastq_device(nsmh_ctx *c, const uint8_t *d_text, uint64_t bytes, uint6
     const uint32_t num_reads = (uint32_t)num_reads64;
     FQ_TRY(nl.ensure(std::max<uint64_t>(newlines, 1) * sizeof(uint64_t), s));
     if (!rc && newlines) {
-        fastq_write_newlines_kernel<<<grid_warps(ntiles, c->num_sms), 256, 0, s>>>(d_text, bytes, aligned16, ntiles,
+        fastq_write_newlines_kernel<<<grid_warps((ntiles + 31) / 32, c->num_sms), 256, 0, s>>>(d_text, bytes, aligned16, ntiles,
                                                                                   tile_base.as<uint64_t>(), nl.as<uint64_t>());
         ++c->launches;
         FQ_CK(cudaGetLastError());
@@ -112,11 +113,25 @@ int parse_fastq_device(nsmh_ctx *c, const uint8_t *d_text, uint64_t bytes, uint6
     }
     FQ_CK(cudaEventRecord(ev[1], s));
     if (!rc && rs.num_words) {
-        const uint64_t chunks = (rs.num_words + 32ull * kFqPackIters - 1) / (32ull * kFqPackIters);
-        fastq_pack_kernel<<<grid_warps(chunks, c->num_sms), 256, 0, s>>>(d_text, safe_bytes, rs.d_offsets(), src.as<uint64_t>(),
-                                                                        num_reads, total_bases, rs.packed.as<uint32_t>());
-        ++c->launches;
-        FQ_CK(cudaGetLastError());
+        // words per lane and chunk: a multiple of kFqPackUnroll (NSMH_FQ_PACK_ITERS: tuning runs only)
+        uint32_t iters = kFqPackIters;
+        const char *ev_iters = getenv("NSMH_FQ_PACK_ITERS");
+        if (ev_iters && *ev_iters && atoi(ev_iters) > 0)
+            iters = (uint32_t)std::min(4096, (atoi(ev_iters) + kFqPackUnroll - 1) / kFqPackUnroll * kFqPackUnroll);
+        const uint64_t chunks = (rs.num_words + 32ull * iters - 1) / (32ull * iters);
+        const char *ev_wide = getenv("NSMH_FQ_PACK_WIDE");       // tuning runs only
+        const bool wide = ev_wide && *ev_wide ? atoi(ev_wide) != 0 : kFqPackWideDefault;
+        auto kernel = wide ? fastq_pack_wide_kernel : fastq_pack_kernel;
+        int occ = 0;
+        FQ_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
+        const uint64_t resident = (uint64_t)c->num_sms * (occ > 0 ? occ : 1);
+        const unsigned blocks = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((chunks + 7) / 8, resident));
+        if (!rc) {
+            kernel<<<blocks, 256, 0, s>>>(d_text, safe_bytes, rs.d_offsets(), src.as<uint64_t>(), num_reads, total_bases,
+                                          rs.packed.as<uint32_t>(), iters);
+            ++c->launches;
+            FQ_CK(cudaGetLastError());
+        }
     }
     FQ_CK(cudaEventRecord(ev[2], s));
     FQ_CK(cudaStreamSynchronize(s));

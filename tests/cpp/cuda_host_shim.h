@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile a kernel header
 // for the HOST and run it in lock step: every lane of a warp is an OS thread, warp collectives
-// (__shfl_up_sync, __reduce_add_sync) meet on a barrier.  One warp runs at a time, so only kernels
+// (__shfl_up_sync, __shfl_sync, __ballot_sync, __reduce_add_sync) meet on a barrier.  One warp runs at a time, so only kernels
 // without block-level cooperation (no __syncthreads / shared memory) can be emulated - which is all
 // that nanospring_b200/csrc/fastq_kernels.cuh contains.
 #pragma once
@@ -34,6 +34,12 @@ static inline uint32_t __vcmpeq4(uint32_t a, uint32_t b) {
         if (((a >> (8 * i)) & 0xFF) == ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
     return r;
 }
+static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
+    const uint64_t src = ((uint64_t)b << 32) | a;              // selector nibbles 0..7 only (no sign replication)
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= (uint32_t)((src >> (8 * ((sel >> (4 * i)) & 7))) & 0xFF) << (8 * i);
+    return r;
+}
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
     return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh & 31));
 }
@@ -47,6 +53,7 @@ static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long 
 struct EmuWarp {
     std::barrier<> bar{32};
     uint32_t slot[32];
+    uint64_t slot64[32];
 };
 static thread_local EmuWarp *emu_warp = nullptr;
 static thread_local int emu_lane = 0;
@@ -56,6 +63,23 @@ static inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, int d) {
     w->slot[emu_lane] = v;
     w->bar.arrive_and_wait();
     const uint32_t r = emu_lane >= d ? w->slot[emu_lane - d] : v;
+    w->bar.arrive_and_wait();
+    return r;
+}
+static inline uint64_t __shfl_sync(uint32_t, uint64_t v, int src) {
+    EmuWarp *w = emu_warp;
+    w->slot64[emu_lane] = v;
+    w->bar.arrive_and_wait();
+    const uint64_t r = w->slot64[src & 31];
+    w->bar.arrive_and_wait();
+    return r;
+}
+static inline uint32_t __ballot_sync(uint32_t, bool pred) {
+    EmuWarp *w = emu_warp;
+    w->slot[emu_lane] = pred ? 1u : 0u;
+    w->bar.arrive_and_wait();
+    uint32_t r = 0;
+    for (int i = 0; i < 32; ++i) r |= w->slot[i] << i;
     w->bar.arrive_and_wait();
     return r;
 }

@@ -13,6 +13,7 @@ from oracle.oracle import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "oracle", "libfastq_emul.so")
+PACK_WIDE = 0
 
 
 @pytest.fixture(scope="module")
@@ -20,14 +21,15 @@ def emul():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "emul"])
     L = C.CDLL(SO)
     u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
-    L.fq_emul_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, u64p, C.c_uint64, u32p, C.c_uint64,
+    L.fq_emul_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_uint32, C.c_int, u64p, C.c_uint64, u32p, C.c_uint64,
                                 u32p, u64p]
     L.fq_emul_unpack.argtypes = [u32p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint]
     return L
 
 
-def run_emul(L, text, misalign=0, grid=2, slack=64):
-    """misalign: byte offset of the text inside a 64-byte aligned buffer; slack: readable bytes behind it."""
+def run_emul(L, text, misalign=0, grid=2, slack=64, pack_iters=0, pack_wide=None):
+    """misalign: byte offset of the text inside a 64-byte aligned buffer; slack: readable bytes behind it;
+    pack_iters: words per lane and chunk of the pack kernel (0 = the library's default)."""
     raw = np.zeros(len(text) + misalign + slack + 64, dtype=np.uint8)
     base = (-raw.ctypes.data) % 64 + misalign
     buf = raw[base:base + len(text) + slack]
@@ -37,7 +39,7 @@ def run_emul(L, text, misalign=0, grid=2, slack=64):
     offsets = np.zeros(nl_cap, dtype=np.uint64)
     words = np.full(len(text) // 16 + 2 + 8, 0, dtype=np.uint32)
     n, nls = C.c_uint32(0), C.c_uint64(0)
-    rc = L.fq_emul_parse(buf.ctypes.data, len(text), len(text) + slack, grid,
+    rc = L.fq_emul_parse(buf.ctypes.data, len(text), len(text) + slack, grid, pack_iters, int(PACK_WIDE if pack_wide is None else pack_wide),
                          offsets.ctypes.data_as(C.POINTER(C.c_uint64)), offsets.size,
                          words.ctypes.data_as(C.POINTER(C.c_uint32)), words.size - 8, C.byref(n), C.byref(nls))
     assert rc == 0
@@ -47,6 +49,10 @@ def run_emul(L, text, misalign=0, grid=2, slack=64):
 
 
 def check(L, orc, text, **kw):
+    """every case runs through both gathers of the pack kernel (32-bit and 128-bit loads)"""
+    if "pack_wide" not in kw:
+        check(L, orc, text, pack_wide=1, **kw)
+        kw["pack_wide"] = 0
     off, words = run_emul(L, text, **kw)
     bases, want_off = orc.fastq_reads(text)
     assert off.size == want_off.size and (off == want_off).all()
@@ -88,3 +94,17 @@ def test_emulated_kernels_many_short_reads(emul):
         L = int(rng.integers(0, 6)) if i % 5 else 0
         recs.append(b"@\n" + rng.choice(np.frombuffer(b"ACGT", np.uint8), size=L).tobytes() + b"\n+\n" + b"I" * L + b"\n")
     check(emul, orc, b"".join(recs))
+
+
+def test_emulated_kernels_long_reads_many_steps(emul):
+    """reads longer than a pack chunk (16 k bases) and a text of several hundred tiles: every warp
+    runs several steps of the 4-tile count loop, the 32-tile newline loop and the unrolled pack loop"""
+    orc = Oracle.get()
+    rng = np.random.default_rng(21)
+    recs = []
+    for L in (40000, 3, 17001, 0, 65, 33000, 16, 9000):
+        seq = rng.choice(np.frombuffer(b"ACGTN", np.uint8), size=L, p=[.24, .24, .24, .24, .04]).tobytes()
+        recs.append(b"@r\n" + seq + b"\n+\n" + b"5" * L + b"\n")
+    text = b"".join(recs)
+    for mis, grid, iters in ((0, 1, 0), (3, 2, 4), (8, 3, 16), (5, 1, 64)):
+        check(emul, orc, text, misalign=mis, grid=grid, pack_iters=iters)
