@@ -119,9 +119,7 @@ int parse_fastq_device(nsmh_ctx *c, const uint8_t *d_text, uint64_t bytes, uint6
         if (ev_iters && *ev_iters && atoi(ev_iters) > 0)
             iters = (uint32_t)std::min(4096, (atoi(ev_iters) + kFqPackUnroll - 1) / kFqPackUnroll * kFqPackUnroll);
         const uint64_t chunks = (rs.num_words + 32ull * iters - 1) / (32ull * iters);
-        const char *ev_wide = getenv("NSMH_FQ_PACK_WIDE");       // tuning runs only
-        const bool wide = ev_wide && *ev_wide ? atoi(ev_wide) != 0 : kFqPackWideDefault;
-        auto kernel = wide ? fastq_pack_wide_kernel : fastq_pack_kernel;
+        auto kernel = fastq_pack_kernel;
         int occ = 0;
         FQ_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0));
         const uint64_t resident = (uint64_t)c->num_sms * (occ > 0 ? occ : 1);

@@ -9,7 +9,6 @@ namespace nsmh {
 constexpr int kFqTileBytes = 512;      // bytes per warp step: 32 lanes x 16
 constexpr int kFqCountTiles = 4;       // tiles per warp step in fastq_count_newlines_kernel
 constexpr int kFqPackIters = 32;       // words per lane and chunk in fastq_pack_kernel (default of its `iters`)
-constexpr bool kFqPackWideDefault = false;   // which gather fastq.cu launches (see fastq_pack_body)
 constexpr int kFqPackUnroll = 4;       // ... of which this many are gathered together (divides iters)
 
 // 4 ASCII bytes (first base in the low byte) -> 2-bit codes (c & 2) | ((c & 4) >> 2) in the TOP byte,
@@ -191,14 +190,13 @@ __device__ __forceinline__ uint32_t fq_read_of_base(const uint64_t *__restrict__
 // handled kFqPackUnroll at a time: first the read cursor is advanced for each of them (rarely more
 // than a compare), then all their loads are issued, then the codes are extracted - 80 bytes in
 // flight per lane instead of 20.
-// WIDE = false: 5 aligned 32-bit loads per word (20 L1 wavefronts per warp and 512 useful bytes);
-// WIDE = true: the two 16-byte blocks that hold the word as 128-bit loads (8 wavefronts) and a
-// select on the word offset inside the first block, which is the same for all lanes in one read.
-template <bool WIDE>
-__device__ __forceinline__ void fastq_pack_body(const uint8_t *__restrict__ text, uint64_t safe_bytes,
-                                                const uint64_t *__restrict__ off, const uint64_t *__restrict__ src_start,
-                                                uint32_t n_reads, uint64_t total_bases, uint32_t *__restrict__ W,
-                                                uint32_t iters) {
+// (Measured on B200: gathering the two enclosing 16-byte blocks with 128-bit loads instead - 8 L1
+// wavefronts per warp-word instead of 20 - is not faster, profiles/r1_ingest_sweep_s8.jsonl; the kernel
+// is bound by instruction issue, not by the load path.)
+__global__ void __launch_bounds__(256)
+fastq_pack_kernel(const uint8_t *__restrict__ text, uint64_t safe_bytes, const uint64_t *__restrict__ off,
+                  const uint64_t *__restrict__ src_start, uint32_t n_reads, uint64_t total_bases,
+                  uint32_t *__restrict__ W, uint32_t iters) {
     const uint64_t nwords = (total_bases + 15) / 16;
     const uint64_t chunk_words = 32ull * iters;
     const uint64_t nchunks = (nwords + chunk_words - 1) / chunk_words;
@@ -230,8 +228,8 @@ __device__ __forceinline__ void fastq_pack_body(const uint8_t *__restrict__ text
                     sb = src_start[i];
                 }
                 const uint64_t addr = tb + sb + (g - rb);
-                const uint64_t base = addr & (WIDE ? ~15ull : ~3ull);
-                if (g + 16 <= re && safe_bytes && base + (WIDE ? 32 : 20) <= tb + safe_bytes) {
+                const uint64_t base = addr & ~3ull;
+                if (g + 16 <= re && safe_bytes && base + 20 <= tb + safe_bytes) {
                     fast[u] = true;
                     a[u] = base;
                     sh[u] = (uint32_t)(addr - base);
@@ -255,36 +253,17 @@ __device__ __forceinline__ void fastq_pack_body(const uint8_t *__restrict__ text
                     word[u] = w;
                 }
             }
-            uint32_t w[kFqPackUnroll][WIDE ? 8 : 5];
+            uint32_t w[kFqPackUnroll][5];
 #pragma unroll
-            for (int u = 0; u < kFqPackUnroll; ++u) {
-                if (WIDE) {
-                    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-                    if (fast[u]) {
-                        q0 = __ldg(reinterpret_cast<const uint4 *>(a[u]));
-                        q1 = __ldg(reinterpret_cast<const uint4 *>(a[u]) + 1);
-                    }
-                    w[u][0] = q0.x; w[u][1] = q0.y; w[u][2] = q0.z; w[u][3] = q0.w;
-                    w[u][4] = q1.x; w[u][5] = q1.y; w[u][6] = q1.z; w[u][7] = q1.w;
-                } else {
+            for (int u = 0; u < kFqPackUnroll; ++u)
 #pragma unroll
-                    for (int q = 0; q < 5; ++q) w[u][q] = fast[u] ? __ldg(reinterpret_cast<const uint32_t *>(a[u]) + q) : 0u;
-                }
-            }
+                for (int q = 0; q < 5; ++q) w[u][q] = fast[u] ? __ldg(reinterpret_cast<const uint32_t *>(a[u]) + q) : 0u;
 #pragma unroll
             for (int u = 0; u < kFqPackUnroll; ++u) {
                 const uint64_t tu = t + 32ull * u;
                 if (tu >= nwords) continue;
                 if (fast[u]) {
-                    uint32_t e0 = w[u][0], e1 = w[u][1], e2 = w[u][2], e3 = w[u][3], e4 = w[u][4];
-                    if (WIDE) {
-                        switch (sh[u] >> 2) {                  // nearly always warp-uniform
-                        case 1: e0 = w[u][1]; e1 = w[u][2]; e2 = w[u][3]; e3 = w[u][4]; e4 = w[u][WIDE ? 5 : 0]; break;
-                        case 2: e0 = w[u][2]; e1 = w[u][3]; e2 = w[u][4]; e3 = w[u][WIDE ? 5 : 0]; e4 = w[u][WIDE ? 6 : 0]; break;
-                        case 3: e0 = w[u][3]; e1 = w[u][4]; e2 = w[u][WIDE ? 5 : 0]; e3 = w[u][WIDE ? 6 : 0]; e4 = w[u][WIDE ? 7 : 0]; break;
-                        default: break;
-                        }
-                    }
+                    const uint32_t e0 = w[u][0], e1 = w[u][1], e2 = w[u][2], e3 = w[u][3], e4 = w[u][4];
                     const uint32_t bs = (sh[u] & 3) * 8;
                     const uint32_t x0 = __funnelshift_r(e0, e1, bs), x1 = __funnelshift_r(e1, e2, bs);
                     const uint32_t x2 = __funnelshift_r(e2, e3, bs), x3 = __funnelshift_r(e3, e4, bs);
@@ -294,20 +273,6 @@ __device__ __forceinline__ void fastq_pack_body(const uint8_t *__restrict__ text
             }
         }
     }
-}
-
-__global__ void __launch_bounds__(256)
-fastq_pack_kernel(const uint8_t *__restrict__ text, uint64_t safe_bytes, const uint64_t *__restrict__ off,
-                  const uint64_t *__restrict__ src_start, uint32_t n_reads, uint64_t total_bases,
-                  uint32_t *__restrict__ W, uint32_t iters) {
-    fastq_pack_body<false>(text, safe_bytes, off, src_start, n_reads, total_bases, W, iters);
-}
-
-__global__ void __launch_bounds__(256)
-fastq_pack_wide_kernel(const uint8_t *__restrict__ text, uint64_t safe_bytes, const uint64_t *__restrict__ off,
-                       const uint64_t *__restrict__ src_start, uint32_t n_reads, uint64_t total_bases,
-                       uint32_t *__restrict__ W, uint32_t iters) {
-    fastq_pack_body<true>(text, safe_bytes, off, src_start, n_reads, total_bases, W, iters);
 }
 
 // out[j] = "ATCG"[code of global base b0 + j], j < nb; a thread per 16 output bytes

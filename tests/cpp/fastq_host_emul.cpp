@@ -15,7 +15,7 @@ extern "C" {
 
 // text must stay readable up to safe_bytes (>= bytes).  Capacities: offsets >= newlines/4 + 3,
 // words >= bytes/16 + 2.  Returns 0, or -1 when a capacity is too small / a read is too long.
-int fq_emul_parse(const uint8_t *text, uint64_t bytes, uint64_t safe_bytes, unsigned grid, uint32_t pack_iters, int pack_wide, uint64_t *offsets,
+int fq_emul_parse(const uint8_t *text, uint64_t bytes, uint64_t safe_bytes, unsigned grid, uint32_t pack_iters, uint64_t *offsets,
                   uint64_t offsets_cap, uint32_t *words, uint64_t words_cap, uint32_t *num_reads_out,
                   uint64_t *newlines_out) {
     const int aligned16 = (reinterpret_cast<uintptr_t>(text) & 15) == 0;
@@ -48,8 +48,7 @@ int fq_emul_parse(const uint8_t *text, uint64_t bytes, uint64_t safe_bytes, unsi
     if (nwords)
         emu_launch(grid, 64, [&] {
             const uint32_t iters = pack_iters ? pack_iters : (uint32_t)kFqPackIters;
-            if (pack_wide) fastq_pack_wide_kernel(text, safe_bytes, offsets, src.data(), (uint32_t)num_reads, total, words, iters);
-            else fastq_pack_kernel(text, safe_bytes, offsets, src.data(), (uint32_t)num_reads, total, words, iters);
+            fastq_pack_kernel(text, safe_bytes, offsets, src.data(), (uint32_t)num_reads, total, words, iters);
         });
     *num_reads_out = (uint32_t)num_reads;
     *newlines_out = newlines;

@@ -13,7 +13,6 @@ from oracle.oracle import Oracle
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "oracle", "libfastq_emul.so")
-PACK_WIDE = 0
 
 
 @pytest.fixture(scope="module")
@@ -21,13 +20,13 @@ def emul():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "emul"])
     L = C.CDLL(SO)
     u64p, u32p = C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)
-    L.fq_emul_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_uint32, C.c_int, u64p, C.c_uint64, u32p, C.c_uint64,
+    L.fq_emul_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_uint32, u64p, C.c_uint64, u32p, C.c_uint64,
                                 u32p, u64p]
     L.fq_emul_unpack.argtypes = [u32p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint]
     return L
 
 
-def run_emul(L, text, misalign=0, grid=2, slack=64, pack_iters=0, pack_wide=None):
+def run_emul(L, text, misalign=0, grid=2, slack=64, pack_iters=0):
     """misalign: byte offset of the text inside a 64-byte aligned buffer; slack: readable bytes behind it;
     pack_iters: words per lane and chunk of the pack kernel (0 = the library's default)."""
     raw = np.zeros(len(text) + misalign + slack + 64, dtype=np.uint8)
@@ -39,7 +38,7 @@ def run_emul(L, text, misalign=0, grid=2, slack=64, pack_iters=0, pack_wide=None
     offsets = np.zeros(nl_cap, dtype=np.uint64)
     words = np.full(len(text) // 16 + 2 + 8, 0, dtype=np.uint32)
     n, nls = C.c_uint32(0), C.c_uint64(0)
-    rc = L.fq_emul_parse(buf.ctypes.data, len(text), len(text) + slack, grid, pack_iters, int(PACK_WIDE if pack_wide is None else pack_wide),
+    rc = L.fq_emul_parse(buf.ctypes.data, len(text), len(text) + slack, grid, pack_iters,
                          offsets.ctypes.data_as(C.POINTER(C.c_uint64)), offsets.size,
                          words.ctypes.data_as(C.POINTER(C.c_uint32)), words.size - 8, C.byref(n), C.byref(nls))
     assert rc == 0
@@ -49,10 +48,6 @@ def run_emul(L, text, misalign=0, grid=2, slack=64, pack_iters=0, pack_wide=None
 
 
 def check(L, orc, text, **kw):
-    """every case runs through both gathers of the pack kernel (32-bit and 128-bit loads)"""
-    if "pack_wide" not in kw:
-        check(L, orc, text, pack_wide=1, **kw)
-        kw["pack_wide"] = 0
     off, words = run_emul(L, text, **kw)
     bases, want_off = orc.fastq_reads(text)
     assert off.size == want_off.size and (off == want_off).all()

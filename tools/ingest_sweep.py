@@ -3,7 +3,7 @@
 CUDA events for several chunk sizes of the pack kernel (NSMH_FQ_PACK_ITERS, read at every call).
 Each setting is also checked: same read table and the same packed words as the ASCII load path.
 
-    python tools/ingest_sweep.py [--iters 16 32 ...] [--wide 0 1] [--reps 5] [--warmup 2]
+    python tools/ingest_sweep.py [--iters 16 32 ...] [--reps 5] [--warmup 2]
 """
 import argparse
 import ctypes as C
@@ -24,7 +24,6 @@ def main():
     import torch
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, nargs="*", default=[8, 16, 32, 64, 128])
-    ap.add_argument("--wide", type=int, nargs="*", default=[0, 1], help="pack gather: 0 = 32-bit loads, 1 = 128-bit loads")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     args = ap.parse_args()
@@ -41,9 +40,8 @@ def main():
     hbm_peak = bench.peaks()[0]
     alg_bytes = nbytes + nb + nb / 4 + 8 * n
     rd = ns.GpuReadData(device=0)
-    for wide, it in [(w, i) for w in args.wide for i in args.iters]:
+    for it in args.iters:
         os.environ["NSMH_FQ_PACK_ITERS"] = str(it)
-        os.environ["NSMH_FQ_PACK_WIDE"] = str(wide)
         for _ in range(args.warmup):
             rd.loadFromDeviceText(text.data_ptr(), nbytes)
         ms, pk = [0.0], [0.0]
@@ -56,11 +54,10 @@ def main():
         got = np.frombuffer(b"".join(rd.getRead(i) for i in (0, 1, n // 2, n - 1)), np.uint8)
         ref = np.concatenate([want[int(offsets[i]):int(offsets[i + 1])] for i in (0, 1, n // 2, n - 1)])
         ok = ok and got.size == ref.size and bool((got == ref).all())
-        print(json.dumps({"pack_wide": wide, "pack_iters": it, "parse_ms": round(float(np.mean(ms)), 4), "pack_kernel_ms": round(float(np.mean(pk)), 4),
+        print(json.dumps({"pack_iters": it, "parse_ms": round(float(np.mean(ms)), 4), "pack_kernel_ms": round(float(np.mean(pk)), 4),
                           "gbases_per_s": round(nb / (np.mean(ms) * 1e-3) / 1e9, 1),
                           "roofline_frac": round(alg_bytes / (np.mean(ms) * 1e-3) / 1e9 / hbm_peak, 3), "ok": ok}), flush=True)
     os.environ.pop("NSMH_FQ_PACK_ITERS", None)
-    os.environ.pop("NSMH_FQ_PACK_WIDE", None)
     rd.close()
 
 
