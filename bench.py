@@ -43,6 +43,9 @@ GENOME_LEN = 50_000_000
 # profiles/r1_ncu_full_s4_summary.txt.  A recorded figure, not measured by this run.
 NCU_TRAFFIC_BYTES = {"sketch_filter_kernel": 300_792_000 + 38_677_504}
 NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_s4_summary.txt (ncu --set full, one launch)"
+# smsp__inst_executed.sum of the same launch (the kernel is deterministic on this workload): with the
+# live kernel time it gives the fraction of the SMs' warp-instruction issue slots the kernel uses.
+NCU_WARP_INSTRUCTIONS = {"sketch_filter_kernel": 341_098_925}
 
 
 def log(*a):
@@ -462,6 +465,12 @@ def main():
                 "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES.get(dominant) if rank == 0 else None,
                 "traffic_source": NCU_TRAFFIC_SOURCE if dominant in NCU_TRAFFIC_BYTES else None,
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sk_ms,
+                "issue_slots": ({"warp_instructions": NCU_WARP_INSTRUCTIONS[dominant],
+                                 "peak_per_s": 148 * 4 * sm_max * 1e6,
+                                 "frac": NCU_WARP_INSTRUCTIONS[dominant] / (sk_ms * 1e-3) / (148 * 4 * sm_max * 1e6),
+                                 "note": "the kernel is bound by instruction issue, not DRAM: recorded "
+                                         "smsp__inst_executed.sum / live kernel time / (148 SMs x 4 schedulers x max SM clock)"}
+                                if dominant in NCU_WARP_INSTRUCTIONS and sk_ms > 0 and rank == 0 else None),
                 "kernel_gbases_per_s": total_bases / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else None,
                 "int32_reference_count": {"lane_ops_per_base": 6 * NHASH + 6,
                                           "achieved_tops": int_ops / (sk_ms * 1e-3) / 1e12 if sk_ms > 0 else None,
