@@ -225,6 +225,8 @@ typedef struct {
     float fastq_parse_ms;     /* nsmh_load_fastq*: device time of parse + pack (text already on the device) */
     float fastq_pack_ms;      /* ... of which the gather-pack kernel */
     float fastq_load_ms;      /* nsmh_load_fastq / _file: whole call incl. file read, inflate and H2D (host clock) */
+    uint32_t query_heavy;     /* last bulk query: queries whose gathered ids overflowed the on-chip sort buffer */
+    uint32_t query_sorted;    /* ... of which went through the global radix sort (the rest: counting-filter tier) */
 } nsmh_stats;
 int nsmh_get_stats(nsmh_handle h, nsmh_stats *out);
 /* The engine's CUDA stream (cudaStream_t as void*), for event timing by the host program. */

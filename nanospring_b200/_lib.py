@@ -29,7 +29,7 @@ class Stats(C.Structure):
                 ("sketch_main_ms", C.c_float), ("build_ms", C.c_float), ("query_ms", C.c_float),
                 ("sketch_fixups", C.c_uint64), ("query_pairs", C.c_uint64),
                 ("kernel_launches", C.c_uint32), ("fastq_parse_ms", C.c_float), ("fastq_pack_ms", C.c_float),
-                ("fastq_load_ms", C.c_float)]
+                ("fastq_load_ms", C.c_float), ("query_heavy", C.c_uint32), ("query_sorted", C.c_uint32)]
 
 
 class SynthParams(C.Structure):

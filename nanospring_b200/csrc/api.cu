@@ -55,7 +55,7 @@ void DevBuf::release(cudaStream_t s) {
 }
 
 static void free_ws(QueryWs &ws, cudaStream_t s) {
-    DevBuf *bufs[] = {&ws.qsketch, &ws.pval, &ws.pcnt, &ws.heavy_list, &ws.counters, &ws.hc, &ws.hoff, &ws.hout, &ws.hcnt, &ws.hstart, &ws.pairs, &ws.pairs_alt, &ws.flags,
+    DevBuf *bufs[] = {&ws.qsketch, &ws.pval, &ws.pcnt, &ws.heavy_list, &ws.heavy2_list, &ws.mid_ids, &ws.counters, &ws.hc, &ws.hoff, &ws.hout, &ws.hcnt, &ws.hstart, &ws.pairs, &ws.pairs_alt, &ws.flags,
                       &ws.qcount, &ws.qpos, &ws.tmp_ids, &ws.out_off, &ws.out_ids, &ws.nsel, &ws.cub_tmp, &ws.str_bases,
                       &ws.tile_start};
     for (DevBuf *b : bufs) b->release(s);
@@ -694,6 +694,8 @@ int nsmh_query_all(nsmh_handle c, int rc_mode, uint64_t *total_ids) {
     if (!rc) {
         c->stats.query_ms = elapsed(e0, e1);
         c->stats.query_pairs = ws.last_pairs;
+        c->stats.query_heavy = ws.last_heavy;
+        c->stats.query_sorted = ws.last_sorted;
         c->bulk_valid = true;
         if (total_ids) *total_ids = ws.last_total;
     }
@@ -782,6 +784,8 @@ int nsmh_count_lists(nsmh_handle c, uint32_t num_queries, uint32_t parts, const 
     NSMH_TRY(count_lists_device(c, c->bulk, num_queries, parts, d_offsets, d_ids, c->stream));
     c->bulk_valid = true;
     c->stats.query_pairs = c->bulk.last_pairs;
+    c->stats.query_heavy = c->bulk.last_heavy;
+    c->stats.query_sorted = c->bulk.last_sorted;
     if (total_ids) *total_ids = c->bulk.last_total;
     return NSMH_OK;
 }

@@ -8,6 +8,10 @@
 
 #include "nsmh_internal.cuh"
 
+// cub::TransformInputIterator is deprecated in favour of thrust::transform_iterator in CUDA 12.9 but
+// still the documented input adaptor of this CUB version; keep the build output clean.
+#pragma GCC diagnostic ignored "-Wdeprecated-declarations"
+
 namespace nsmh {
 
 struct U32ToU64 {

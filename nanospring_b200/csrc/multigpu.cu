@@ -402,6 +402,8 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
     }
     c->bulk_valid = true;
     c->stats.query_pairs = c->bulk.last_pairs;
+    c->stats.query_heavy = c->bulk.last_heavy;
+    c->stats.query_sorted = c->bulk.last_sorted;
     c->stats.build_ms = m->stage_ms[2];
     c->stats.query_ms = m->stage_ms[3] + m->stage_ms[5];
     if (total_ids) *total_ids = c->bulk.last_total;

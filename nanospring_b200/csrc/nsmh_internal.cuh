@@ -99,7 +99,9 @@ struct QueryWs {
     DevBuf qsketch;     // u64 [nq*n]  (string queries)
     DevBuf pval, pcnt;  // u32 [nq*n]  probe results
     DevBuf heavy_list;  // u32 [nq]    queries that overflow the warp buffer
-    DevBuf counters;    // u64 [4]
+    DevBuf heavy2_list; // u32 [nh]    ... of which the counting-filter tier could not resolve
+    DevBuf mid_ids;     // u32         results of the counting-filter tier, completion order
+    DevBuf counters;    // u64 [8]     [0..2] count_kernel, [4..6] mid_count_kernel
     DevBuf hc;          // u32 [nh*n+1], global path
     DevBuf hoff;        // u64 [nh*n+1]
     DevBuf hout;        // u32 results of heavy queries
@@ -122,6 +124,8 @@ struct QueryWs {
     uint64_t last_total = 0;
     uint64_t last_pairs = 0;
     uint32_t last_nq = 0;
+    uint32_t last_heavy = 0;    // queries of the last call that overflowed the warp buffer
+    uint32_t last_sorted = 0;   // ... of which went through the global sort
     uint32_t launches = 0;
 };
 

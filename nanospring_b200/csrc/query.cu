@@ -20,8 +20,10 @@
 // SURVEY S5) take the global path: (query, id) pairs, one radix sort, run flags,
 // compaction.
 #include <algorithm>
+#include <cstdlib>
 
 #include "nsmh_internal.cuh"
+#include "query_mid.cuh"
 
 namespace nsmh {
 
@@ -30,15 +32,8 @@ constexpr int kHashSlots = 512;      // counting table of the common path: 512 k
 constexpr int kHashMaxIds = 256;     // ... for up to this many gathered ids (load factor <= 0.5)
 constexpr int kWarpWords = kLookupCap + kHashMaxIds + 32;   // + result list + a few scalars
 constexpr int kLookupWarps = 8;
+constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
 constexpr int kMaxParts = 16;        // PartsSrc: at most this many partial lists per query
-constexpr uint32_t kNoId = 0xFFFFFFFFu;   // read ids are < 2^32-1 (ReadData.cpp:122-124)
-
-// one id list: c ids at ptr, or (ptr == nullptr, c == 1) the single id `one`
-struct ListRef {
-    const uint32_t *ptr;
-    uint32_t c, one;
-};
-
 // The n tables, probed for a batch of query sketches.  probe_items_kernel resolves every
 // (query, hash) item and stores {val, group size}; everything downstream reads those.
 __device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
@@ -349,14 +344,6 @@ struct CountArgs {
     uint32_t nq, thr;
 };
 
-__device__ __forceinline__ ListRef empty_list() {
-    ListRef r;
-    r.ptr = nullptr;
-    r.c = 0;
-    r.one = 0;
-    return r;
-}
-
 // counting table: one more occurrence of `id`; the lane that brings the count to `thr` emits it
 __device__ __forceinline__ void count_id(uint32_t *keys, uint32_t *cnts, uint32_t *res, uint32_t *rcount,
                                          uint32_t id, uint32_t thr) {
@@ -367,22 +354,6 @@ __device__ __forceinline__ void count_id(uint32_t *keys, uint32_t *cnts, uint32_
         h = (h + 1) & (kHashSlots - 1);
     }
     if (atomicAdd(cnts + h, 1u) + 1u == thr) res[atomicAdd(rcount, 1u)] = id;
-}
-
-// ascending bitonic sort of buf[0..P), P a power of two >= 32, by one warp
-__device__ __forceinline__ void warp_bitonic_smem(uint32_t *buf, uint32_t P, int lane) {
-    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
-        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-            for (uint32_t i = lane; i < P / 2; i += 32) {
-                const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
-                const uint32_t hi = lo | j;
-                const uint32_t x = buf[lo], y = buf[hi];
-                const bool asc = (lo & kk) == 0;
-                if ((x > y) == asc) { buf[lo] = y; buf[hi] = x; }
-            }
-            __syncwarp();
-        }
-    }
 }
 
 // One warp per query, ONE pass.  Common case (<= kHashMaxIds gathered ids): the ids are counted
@@ -553,16 +524,28 @@ count_kernel(Src src, CountArgs a) {
 
 // tmp_ids (completion order) -> CSR (query order); 8 lanes per query
 __global__ void __launch_bounds__(256)
-csr_place_kernel(CountArgs a, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids) {
+csr_place_kernel(CountArgs a, const uint32_t *__restrict__ mid_ids, const uint64_t *__restrict__ out_off,
+                 uint32_t *__restrict__ out_ids) {
     const uint32_t sub = threadIdx.x & 7;
     const uint32_t groups = gridDim.x * (blockDim.x >> 3);
     for (uint32_t q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); q < a.nq; q += groups) {
         const uint64_t pos = a.qpos[q];
-        if (pos == ~0ULL) continue;          // heavy query: heavy_copy_kernel places it
+        if (pos == ~0ULL) continue;          // global-path query: heavy_copy_kernel places it
         const uint32_t cnt = a.qcount[q];
         uint32_t *dst = out_ids + out_off[q];
-        for (uint32_t i = sub; i < cnt; i += 8) dst[i] = a.tmp_ids[pos + i];
+        const uint32_t *src = (pos & kMidPosFlag) ? mid_ids + (pos & ~kMidPosFlag) : a.tmp_ids + pos;
+        for (uint32_t i = sub; i < cnt; i += 8) dst[i] = src[i];
     }
+}
+
+// ---------------------------------------------------------------- counting-filter tier --
+// query_mid.cuh: a warp per query that overflowed the warp buffer; exact, no global sort.
+template <typename Src>
+__global__ void __launch_bounds__(kMidWarps * 32)
+mid_count_kernel(Src src, MidArgs m) {
+    extern __shared__ __align__(16) uint32_t s_mid[];
+    const uint32_t warp = threadIdx.x >> 5;
+    mid_count_body(src, m, s_mid + (size_t)warp * kMidWarpWords, blockIdx.x * kMidWarps + warp, gridDim.x * kMidWarps);
 }
 
 // ---------------------------------------------------------------- global path --
@@ -630,6 +613,12 @@ heavy_copy_kernel(const uint32_t *__restrict__ heavy_list, uint32_t nh, const ui
     }
 }
 
+// NSMH_MID_TIER=0 sends every query that overflows the warp buffer to the global sort (A/B runs, tests)
+static bool mid_tier_enabled() {
+    const char *e = getenv("NSMH_MID_TIER");
+    return e && *e ? atoi(e) != 0 : kMidTierDefault;
+}
+
 static int grid_for(uint64_t items, int sms, int per_block = 256) {
     uint64_t b = (items + per_block - 1) / per_block;
     uint64_t cap = (uint64_t)sms * 16;
@@ -638,9 +627,9 @@ static int grid_for(uint64_t items, int sms, int per_block = 256) {
 
 // Queries that overflowed the warp buffer: global (heavy index, id) pair sort in batches.
 template <typename Src>
-static int heavy_path(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t subs, uint32_t nh, cudaStream_t s) {
+static int heavy_path(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t subs, const uint32_t *hl, uint32_t nh,
+                      cudaStream_t s) {
     const uint64_t items = (uint64_t)nh * subs;
-    uint32_t *hl = ws.heavy_list.as<uint32_t>();
     NSMH_TRY(ws.hc.ensure((items + 1) * sizeof(uint32_t), s));
     NSMH_TRY(ws.hoff.ensure((items + 1) * sizeof(uint64_t), s));
     NSMH_CK(cudaMemsetAsync(ws.hc.as<uint32_t>() + items, 0, sizeof(uint32_t), s));
@@ -726,6 +715,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     ws.last_nq = nq;
     ws.last_total = 0;
     ws.last_pairs = 0;
+    ws.last_heavy = ws.last_sorted = 0;
     NSMH_TRY(ws.out_off.ensure(((size_t)nq + 1) * sizeof(uint64_t), s));
     if (nq == 0) {
         NSMH_CK(cudaMemsetAsync(ws.out_off.p, 0, sizeof(uint64_t), s));
@@ -735,7 +725,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     NSMH_TRY(ws.qcount.ensure(((size_t)nq + 1) * sizeof(uint32_t), s));
     NSMH_TRY(ws.qpos.ensure((size_t)nq * sizeof(uint64_t), s));
     NSMH_TRY(ws.heavy_list.ensure((size_t)nq * sizeof(uint32_t), s));
-    NSMH_TRY(ws.counters.ensure(4 * sizeof(uint64_t), s));
+    NSMH_TRY(ws.counters.ensure(8 * sizeof(uint64_t), s));
     // results land in tmp_ids in completion order; its size is a guess that the kernel checks
     // (the cursor keeps counting past the end), so at most one repeat with the exact size
     if (ws.tmp_ids.cap < (size_t)nq * 16 * sizeof(uint32_t))
@@ -759,7 +749,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.tmp_ids = ws.tmp_ids.as<uint32_t>();
         a.tmp_cap = ws.tmp_ids.cap / sizeof(uint32_t);
-        NSMH_CK(cudaMemsetAsync(ws.counters.p, 0, 4 * sizeof(uint64_t), s));
+        NSMH_CK(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(uint64_t), s));
         NSMH_CK(cudaMemsetAsync(ws.qcount.as<uint32_t>() + nq, 0, sizeof(uint32_t), s));
         count_kernel<Src><<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
         ++ws.launches;
@@ -769,23 +759,58 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
         if (cnt[2] <= a.tmp_cap) break;
         NSMH_TRY(ws.tmp_ids.ensure((size_t)cnt[2] * sizeof(uint32_t), s));
     }
-    const uint32_t nh = (uint32_t)cnt[0];
+    uint32_t nh = (uint32_t)cnt[0];
+    const uint32_t *hl = ws.heavy_list.as<uint32_t>();
     ws.last_pairs = cnt[1];
+    ws.last_heavy = nh;
     // a result id needs at least one gathered id, so their number bounds the output size
     NSMH_TRY(ws.out_ids.ensure((size_t)std::max<uint64_t>(cnt[1], 1) * sizeof(uint32_t), s));
-    if (nh) NSMH_TRY(heavy_path(c, ws, src, subs, nh, s));
+    if (nh && mid_tier_enabled()) {
+        // counting-filter tier: resolves the heavy queries that have few ids above the threshold
+        // (query_mid.cuh); what it cannot resolve goes on to the global sort.  A result needs thr
+        // gathered ids, so cnt[1] / thr bounds what all queries together can emit.
+        MidArgs m;
+        m.mid_cap = cnt[1] / a.thr + 1;
+        NSMH_TRY(ws.mid_ids.ensure((size_t)m.mid_cap * sizeof(uint32_t), s));
+        NSMH_TRY(ws.heavy2_list.ensure((size_t)nh * sizeof(uint32_t), s));
+        m.heavy_list = hl;
+        m.unresolved_list = ws.heavy2_list.as<uint32_t>();
+        m.mid_ids = ws.mid_ids.as<uint32_t>();
+        m.qcount = a.qcount;
+        m.qpos = a.qpos;
+        m.counters = a.counters + 4;
+        m.nh = nh;
+        m.thr = a.thr;
+        const size_t mid_smem = (size_t)kMidWarps * kMidWarpWords * sizeof(uint32_t);
+        NSMH_CK(cudaFuncSetAttribute(mid_count_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem));
+        int mocc = 0;
+        NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&mocc, mid_count_kernel<Src>, kMidWarps * 32, mid_smem));
+        const int mblocks = (int)std::min<uint64_t>(((uint64_t)nh + kMidWarps - 1) / kMidWarps,
+                                                    (uint64_t)c->num_sms * (mocc > 0 ? mocc : 1));
+        mid_count_kernel<Src><<<mblocks, kMidWarps * 32, mid_smem, s>>>(src, m);
+        ++ws.launches;
+        NSMH_CK(cudaGetLastError());
+        unsigned long long mc[3] = {0, 0, 0};
+        NSMH_CK(cudaMemcpyAsync(mc, m.counters, sizeof mc, cudaMemcpyDeviceToHost, s));
+        NSMH_CK(cudaStreamSynchronize(s));
+        if (mc[2] || mc[0] > nh) return fail(NSMH_ECUDA, "query: internal error in the counting-filter tier");
+        nh = (uint32_t)mc[0];
+        hl = ws.heavy2_list.as<uint32_t>();
+    }
+    ws.last_sorted = nh;
+    if (nh) NSMH_TRY(heavy_path(c, ws, src, subs, hl, nh, s));
 
     size_t tmp_bytes = 0;
     NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
     NSMH_TRY(ws.cub_tmp.ensure(tmp_bytes, s));
     NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
-    csr_place_kernel<<<grid_for((uint64_t)nq * 8, c->num_sms), 256, 0, s>>>(a, ws.out_off.as<uint64_t>(),
+    csr_place_kernel<<<grid_for((uint64_t)nq * 8, c->num_sms), 256, 0, s>>>(a, ws.mid_ids.as<uint32_t>(), ws.out_off.as<uint64_t>(),
                                                                           ws.out_ids.as<uint32_t>());
     ws.launches += 3;
     NSMH_CK(cudaGetLastError());
     if (nh) {
         heavy_copy_kernel<<<grid_for(nh, c->num_sms, 8), 256, 0, s>>>(
-            ws.heavy_list.as<uint32_t>(), nh, ws.hcnt.as<uint32_t>(), ws.hstart.as<uint64_t>(),
+            hl, nh, ws.hcnt.as<uint32_t>(), ws.hstart.as<uint64_t>(),
             ws.hout.as<uint32_t>(), ws.out_off.as<uint64_t>(), ws.out_ids.as<uint32_t>());
         ++ws.launches;
         NSMH_CK(cudaGetLastError());

@@ -1,0 +1,179 @@
+// Device code shared by the lookup kernels of query.cu, plus the "counting filter" tier for
+// queries whose gathered id lists do not fit the warp-private sort buffer (kLookupCap ids).
+// Kept free of runtime-API includes so that tests/cpp/query_mid_host_emul.cpp can compile the SAME
+// code for the host (tests/cpp/cuda_host_shim.h, lock-step warp emulation) and check it against a
+// plain sort-and-count of the lists without a GPU.
+//
+// Reference semantics (src/ReadFilter.cpp:65-83): the ids of all n probed lists are gathered,
+// sorted, and an id is emitted when it occurs at least overlapSketchThreshold times.
+#pragma once
+#include <stdint.h>
+
+namespace nsmh {
+
+constexpr uint32_t kNoId = 0xFFFFFFFFu;   // read ids are < 2^32-1 (ReadData.cpp:122-124)
+
+// one id list: c ids at ptr, or (ptr == nullptr, c == 1) the single id `one`
+struct ListRef {
+    const uint32_t *ptr;
+    uint32_t c, one;
+};
+
+__device__ __forceinline__ ListRef empty_list() {
+    ListRef r;
+    r.ptr = nullptr;
+    r.c = 0;
+    r.one = 0;
+    return r;
+}
+
+// ascending bitonic sort of buf[0..P), P a power of two >= 32, by one warp
+__device__ __forceinline__ void warp_bitonic_smem(uint32_t *buf, uint32_t P, int lane) {
+    for (uint32_t kk = 2; kk <= P; kk <<= 1) {
+        for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+            for (uint32_t i = lane; i < P / 2; i += 32) {
+                const uint32_t lo = ((i & ~(j - 1)) << 1) | (i & (j - 1));
+                const uint32_t hi = lo | j;
+                const uint32_t x = buf[lo], y = buf[hi];
+                const bool asc = (lo & kk) == 0;
+                if ((x > y) == asc) { buf[lo] = y; buf[hi] = x; }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ counting-filter tier --
+// With small k (or very deep coverage) most table groups hold tens of reads that share a sketch
+// value by chance, so a query gathers thousands of ids of which only a handful occur
+// overlapSketchThreshold times.  Sorting all of them (globally: 8 bytes per id through several
+// radix passes in HBM) is wasted work.  One warp per such query instead
+//   1. counts every gathered id into kMidBuckets 16-bit counters in shared memory (a query with at
+//      most 65535 ids cannot overflow a counter),
+//   2. walks the lists a second time and keeps the ids whose bucket reached the threshold - every
+//      occurrence of an id that qualifies survives, because its bucket counts at least its own
+//      occurrences; ids that do not qualify survive only through bucket collisions,
+//   3. sorts the survivors (<= kMidCap) and thresholds the run lengths exactly like the sort path.
+// The result is exact; a query with too many ids or survivors is handed to the global sort path.
+constexpr int kMidBuckets = 4096;
+constexpr int kMidCap = 1024;
+constexpr uint32_t kMidMaxIds = 65535;
+constexpr int kMidWarpWords = kMidBuckets / 2 + kMidCap + 32;
+constexpr int kMidWarps = 4;
+constexpr uint64_t kMidPosFlag = 1ULL << 63;     // in qpos: "results are in mid_ids" (~0 stays "global path")
+
+struct MidArgs {
+    const uint32_t *heavy_list;     // [nh] queries that overflowed the warp buffer
+    uint32_t *unresolved_list;      // [nh] out: the ones this tier hands on
+    uint32_t *mid_ids;              // results of the resolved ones, in completion order
+    uint64_t mid_cap;
+    uint32_t *qcount;               // [nq]
+    uint64_t *qpos;                 // [nq]
+    unsigned long long *counters;   // [0] unresolved, [1] cursor in mid_ids, [2] overflow of mid_ids (must stay 0)
+    uint32_t nh, thr;
+};
+
+__device__ __forceinline__ uint32_t mid_bucket(uint32_t id) { return (id * 0x9E3779B1u) >> 20; }   // 12 bits
+
+// f(id) for every id of the query's lists: short lists by the lane that owns them, longer ones by
+// the whole warp (coalesced)
+template <typename Src, typename F>
+__device__ __forceinline__ void mid_for_each_id(const Src &src, uint32_t q, uint32_t subs, int lane, F f) {
+    for (uint32_t j0 = 0; j0 < subs; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const ListRef r = j < subs ? src.get(q, j) : empty_list();
+        if (r.c == 1) f(r.ptr ? r.ptr[0] : r.one);
+        else if (r.c > 1 && r.c <= 4)
+            for (uint32_t i = 0; i < r.c; ++i) f(r.ptr[i]);
+        uint32_t big = __ballot_sync(0xffffffffu, r.c > 4);
+        while (big) {
+            const int sl = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t *bp = reinterpret_cast<const uint32_t *>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r.ptr), sl));
+            const uint32_t bc = __shfl_sync(0xffffffffu, r.c, sl);
+            for (uint32_t i = lane; i < bc; i += 32) f(bp[i]);
+        }
+    }
+}
+
+// One warp: heavy queries first, first + stride, ...; wbuf = kMidWarpWords warp-private words.
+template <typename Src>
+__device__ __forceinline__ void mid_count_body(const Src &src, const MidArgs &m, uint32_t *wbuf, uint32_t first,
+                                               uint32_t stride) {
+    const int lane = threadIdx.x & 31;
+    uint32_t *cnt = wbuf;                          // kMidBuckets 16-bit counters
+    uint32_t *surv = wbuf + kMidBuckets / 2;       // kMidCap ids
+    uint32_t *nsurv = surv + kMidCap;
+    const uint32_t subs = src.subs();
+    for (uint32_t h = first; h < m.nh; h += stride) {
+        const uint32_t q = m.heavy_list[h];
+        unsigned long long T = 0;
+        for (uint32_t j = lane; j < subs; j += 32) T += src.get(q, j).c;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) T += __shfl_xor_sync(0xffffffffu, T, o);
+        bool ok = T <= kMidMaxIds;
+        uint32_t S = 0;
+        if (ok) {
+            for (int i = lane; i < kMidBuckets / 2; i += 32) cnt[i] = 0;
+            if (lane == 0) *nsurv = 0;
+            __syncwarp();
+            mid_for_each_id(src, q, subs, lane, [&](uint32_t id) {
+                const uint32_t b = mid_bucket(id);
+                atomicAdd(cnt + (b >> 1), 1u << (16 * (b & 1)));
+            });
+            __syncwarp();
+            const uint32_t thr = m.thr;
+            mid_for_each_id(src, q, subs, lane, [&](uint32_t id) {
+                const uint32_t b = mid_bucket(id);
+                if (((cnt[b >> 1] >> (16 * (b & 1))) & 0xFFFFu) >= thr) {
+                    const uint32_t p = atomicAdd(nsurv, 1u);
+                    if (p < (uint32_t)kMidCap) surv[p] = id;
+                }
+            });
+            __syncwarp();
+            S = *nsurv;
+            ok = S <= (uint32_t)kMidCap;
+        }
+        if (!ok) {
+            if (lane == 0) m.unresolved_list[atomicAdd(m.counters, 1ULL)] = q;
+            __syncwarp();
+            continue;
+        }
+        uint32_t P = 32;
+        while (P < S) P <<= 1;
+        for (uint32_t i = S + lane; i < P; i += 32) surv[i] = kNoId;
+        __syncwarp();
+        warp_bitonic_smem(surv, P, lane);
+        // run lengths against the threshold (ReadFilter.cpp:76-82), compacted in place
+        uint32_t R = 0;
+        for (uint32_t i0 = 0; i0 < S; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool keep = false;
+            uint32_t v = 0;
+            if (i < S) {
+                v = surv[i];
+                const bool head = i == 0 || surv[i - 1] != v;
+                keep = head && (m.thr <= 1 || (i + m.thr - 1 < S && surv[i + m.thr - 1] == v));
+            }
+            const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+            __syncwarp();       // every read of this round happens before its writes (R <= i0)
+            if (keep) surv[R + __popc(mask & ((1u << lane) - 1))] = v;
+            R += __popc(mask);
+            __syncwarp();
+        }
+        unsigned long long base = 0;
+        if (lane == 0) {
+            base = atomicAdd(m.counters + 1, (unsigned long long)R);
+            if (base + R > m.mid_cap) m.counters[2] = 1ULL;
+            m.qcount[q] = R;
+            m.qpos[q] = kMidPosFlag | base;
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base + R <= m.mid_cap)
+            for (uint32_t i = lane; i < R; i += 32) m.mid_ids[base + i] = surv[i];
+        __syncwarp();
+    }
+}
+
+} // namespace nsmh

@@ -1,8 +1,8 @@
 // TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile a kernel header
 // for the HOST and run it in lock step: every lane of a warp is an OS thread, warp collectives
-// (__shfl_up_sync, __shfl_sync, __ballot_sync, __reduce_add_sync) meet on a barrier.  One warp runs at a time, so only kernels
-// without block-level cooperation (no __syncthreads / shared memory) can be emulated - which is all
-// that nanospring_b200/csrc/fastq_kernels.cuh contains.
+// (__shfl_*_sync, __ballot_sync, __reduce_add_sync, __syncwarp) meet on a barrier.  One warp runs at a time, so only
+// warp-level code can be emulated (no __syncthreads; "shared memory" is a warp-private buffer the
+// harness passes in) - which is all that csrc/fastq_kernels.cuh and csrc/query_mid.cuh contain.
 #pragma once
 #include <stdint.h>
 
@@ -66,7 +66,7 @@ static inline uint32_t __shfl_up_sync(uint32_t, uint32_t v, int d) {
     w->bar.arrive_and_wait();
     return r;
 }
-static inline uint64_t __shfl_sync(uint32_t, uint64_t v, int src) {
+static inline uint64_t emu_exchange64(uint64_t v, int src) {
     EmuWarp *w = emu_warp;
     w->slot64[emu_lane] = v;
     w->bar.arrive_and_wait();
@@ -74,6 +74,15 @@ static inline uint64_t __shfl_sync(uint32_t, uint64_t v, int src) {
     w->bar.arrive_and_wait();
     return r;
 }
+static inline uint64_t __shfl_sync(uint32_t, uint64_t v, int src) { return emu_exchange64(v, src); }
+static inline unsigned long long __shfl_sync(uint32_t, unsigned long long v, int src) { return emu_exchange64(v, src); }
+static inline uint32_t __shfl_sync(uint32_t, uint32_t v, int src) { return (uint32_t)emu_exchange64(v, src); }
+static inline unsigned long long __shfl_xor_sync(uint32_t, unsigned long long v, int m) { return emu_exchange64(v, emu_lane ^ m); }
+static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t v, int m) { return (uint32_t)emu_exchange64(v, emu_lane ^ m); }
+static inline void __syncwarp() {
+    emu_warp->bar.arrive_and_wait();
+}
+static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline uint32_t __ballot_sync(uint32_t, bool pred) {
     EmuWarp *w = emu_warp;
     w->slot[emu_lane] = pred ? 1u : 0u;

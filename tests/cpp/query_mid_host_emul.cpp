@@ -1,0 +1,70 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the counting-filter tier of the candidate lookup
+// (nanospring_b200/csrc/query_mid.cuh: mid_count_body, the code mid_count_kernel in query.cu wraps)
+// on the host with cuda_host_shim.h, over id lists given as a CSR.  tests/test_query_mid_emul.py
+// compares the outcome with a plain sort-and-count (what ReadFilter.cpp:65-83 does); a logic check
+// for the container without a GPU, never a product path.
+#include "cuda_host_shim.h"
+
+#include "../../nanospring_b200/csrc/query_mid.cuh"
+
+using namespace nsmh;
+
+namespace {
+// lists of query q: list_off[q * subs + j] .. list_off[q * subs + j + 1]; every other list of one id
+// is handed out in the inlined form the hash-table slots use (ptr == nullptr, id in `one`)
+struct CsrSrc {
+    const uint64_t *list_off;
+    const uint32_t *ids;
+    uint32_t nsubs;
+    uint32_t subs() const { return nsubs; }
+    ListRef get(uint32_t q, uint32_t j) const {
+        const uint64_t o0 = list_off[(uint64_t)q * nsubs + j], o1 = list_off[(uint64_t)q * nsubs + j + 1];
+        ListRef r;
+        r.c = (uint32_t)(o1 - o0);
+        r.one = 0;
+        r.ptr = ids + o0;
+        if (r.c == 1 && (j & 1)) {
+            r.one = ids[o0];
+            r.ptr = nullptr;
+        }
+        return r;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int mid_emul_constants(uint32_t *buckets, uint32_t *cap, uint32_t *max_ids) {
+    *buckets = kMidBuckets;
+    *cap = kMidCap;
+    *max_ids = kMidMaxIds;
+    return 0;
+}
+
+// All nq queries are "heavy".  qcount/qpos [nq] must come in as 0 / ~0 (what count_kernel leaves for a
+// heavy query); counters [3] zeroed.  grid blocks of 2 warps.
+void mid_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, uint32_t subs, uint32_t thr,
+                  unsigned grid, uint32_t *qcount, uint64_t *qpos, uint32_t *mid_ids, uint64_t mid_cap,
+                  uint32_t *unresolved, unsigned long long *counters) {
+    CsrSrc src{list_off, ids, subs};
+    std::vector<uint32_t> heavy(nq);
+    for (uint32_t q = 0; q < nq; ++q) heavy[q] = nq - 1 - q;          // any order
+    MidArgs m;
+    m.heavy_list = heavy.data();
+    m.unresolved_list = unresolved;
+    m.mid_ids = mid_ids;
+    m.mid_cap = mid_cap;
+    m.qcount = qcount;
+    m.qpos = qpos;
+    m.counters = counters;
+    m.nh = nq;
+    m.thr = thr;
+    std::vector<uint32_t> smem((size_t)grid * 2 * kMidWarpWords, 0xA5A5A5A5u);     // never assumed zero
+    emu_launch(grid, 64, [&] {
+        const uint32_t warp = threadIdx.x >> 5;
+        mid_count_body(src, m, smem.data() + ((size_t)blockIdx.x * 2 + warp) * kMidWarpWords, blockIdx.x * 2 + warp,
+                       gridDim.x * 2);
+    });
+}
+
+}  // extern "C"

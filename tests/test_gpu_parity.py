@@ -395,3 +395,39 @@ def test_rebuild_and_requery_same_handle(orc):
         T = orc.build_tables(want)
         assert_csr_equal(f.queryAll(False), T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, 0), f"set {seed}")
     f.close()
+
+
+@pytest.mark.parametrize("thr", [1, 6, 20])
+def test_counting_filter_tier_small_k(orc, monkeypatch, thr):
+    """k = 8: every table group holds tens of reads that share a sketch value by chance, so most
+    queries gather 1000..3000 ids (more than the warp's sort buffer) of which a handful reach the
+    threshold.  The counting-filter tier (csrc/query_mid.cuh) resolves them without the global sort;
+    with thr = 1 every id survives the filter and the queries are handed on.  Same CSR as the oracle
+    and as the run with the tier switched off."""
+    k, n = 8, 60
+    rnd = ns.rand_from_seed(11, n)
+    lengths = ns.synth_lengths(3000, 1500, seed=21)
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=300_000, genome_seed=5, read_seed=6))
+    want_sk = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    T = orc.build_tables(want_sk)
+    results = {}
+    for tier in ("1", "0"):
+        monkeypatch.setenv("NSMH_MID_TIER", tier)
+        f = make_filter(k, n, thr, rnd)
+        f.initialize(rd)
+        assert (f.sketches() == want_sk).all()
+        for rc in (False, True):
+            got = f.queryAll(rc)
+            st = f.stats()
+            assert_csr_equal(got, T.query_all(rd.bases, rd.offsets, want_sk, k, rnd, thr, int(rc)), f"tier {tier} rc {rc}")
+            results[(tier, rc)] = (st["query_heavy"], st["query_sorted"])
+        f.close()
+    for rc in (False, True):
+        heavy_on, sorted_on = results[("1", rc)]
+        heavy_off, sorted_off = results[("0", rc)]
+        assert heavy_on == heavy_off and heavy_on > 1000, "most queries overflow the warp buffer on this input"
+        assert sorted_off == heavy_off, "tier off: every heavy query goes through the global sort"
+        if thr == 1:
+            assert sorted_on == heavy_on, "thr 1: nothing can be filtered out"
+        else:
+            assert sorted_on < heavy_on // 10, "the tier resolves nearly all heavy queries"

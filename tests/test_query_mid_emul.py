@@ -1,0 +1,141 @@
+"""The counting-filter tier of the candidate lookup (nanospring_b200/csrc/query_mid.cuh) compiled for
+the HOST and run in lock step (tests/cpp/cuda_host_shim.h), compared with a plain sort-and-count of
+the gathered ids - the definition in ReadFilter.cpp:65-83.  A logic check of the device code for the
+container without a GPU; the GPU parity proper is tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "oracle", "libquery_mid_emul.so")
+u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "emul"])
+    L = C.CDLL(SO)
+    L.mid_emul_run.argtypes = [u64p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, u32p, u64p, u32p, C.c_uint64,
+                               u32p, C.POINTER(C.c_ulonglong)]
+    L.mid_emul_run.restype = None
+    b, cap, mx = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    L.mid_emul_constants(C.byref(b), C.byref(cap), C.byref(mx))
+    L.consts = (b.value, cap.value, mx.value)
+    return L
+
+
+def run(L, queries, subs, thr, grid=2):
+    """queries: list of lists of id arrays (subs lists per query).  Returns per query either the
+    emitted ids (np.uint32, in the order stored) or None when the tier handed the query on."""
+    nq = len(queries)
+    flat, off = [], [0]
+    for lists in queries:
+        assert len(lists) == subs
+        for l in lists:
+            flat.append(np.asarray(l, dtype=np.uint32))
+            off.append(off[-1] + len(l))
+    ids = np.concatenate(flat + [np.zeros(1, np.uint32)])
+    off = np.asarray(off, dtype=np.uint64)
+    total = int(off[-1])
+    qcount = np.zeros(nq, dtype=np.uint32)
+    qpos = np.full(nq, np.iinfo(np.uint64).max, dtype=np.uint64)
+    mid_cap = total // max(thr, 1) + 1
+    mid_ids = np.full(mid_cap + 8, 0xDEADBEEF, dtype=np.uint32)
+    unresolved = np.full(nq + 1, 0xFFFFFFFF, dtype=np.uint32)
+    counters = (C.c_ulonglong * 3)(0, 0, 0)
+    L.mid_emul_run(off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p), nq, subs, thr, grid,
+                   qcount.ctypes.data_as(u32p), qpos.ctypes.data_as(u64p), mid_ids.ctypes.data_as(u32p), mid_cap,
+                   unresolved.ctypes.data_as(u32p), counters)
+    assert counters[2] == 0, "mid_ids overflowed although its size is the proven bound"
+    assert (mid_ids[mid_cap:] == 0xDEADBEEF).all()
+    handed_on = set(int(x) for x in unresolved[:counters[0]])
+    assert len(handed_on) == counters[0] and (unresolved[counters[0]:] == 0xFFFFFFFF).all()
+    out, used = [], 0
+    for q in range(nq):
+        if q in handed_on:
+            assert qcount[q] == 0 and qpos[q] == np.iinfo(np.uint64).max     # untouched for the global path
+            out.append(None)
+            continue
+        pos = int(qpos[q])
+        assert pos >> 63 == 1, "resolved queries carry the mid flag"
+        pos &= (1 << 63) - 1
+        out.append(mid_ids[pos:pos + int(qcount[q])].copy())
+        used += int(qcount[q])
+    assert used == counters[1]
+    return out
+
+
+def expected(lists, thr):
+    allids = np.concatenate([np.asarray(l, dtype=np.uint32) for l in lists] + [np.zeros(0, np.uint32)])
+    v, c = np.unique(allids, return_counts=True)
+    return v[c >= max(thr, 1)].astype(np.uint32)
+
+
+def must_hand_on(L, lists, thr):
+    """exactly the tier's own rule: too many ids, or too many ids in buckets that reach the threshold"""
+    buckets, cap, max_ids = L.consts
+    allids = np.concatenate([np.asarray(l, dtype=np.uint32) for l in lists] + [np.zeros(0, np.uint32)])
+    if allids.size > max_ids:
+        return True
+    b = ((allids.astype(np.uint64) * 0x9E3779B1) & 0xFFFFFFFF) >> 20
+    assert buckets == 4096
+    cnt = np.bincount(b.astype(np.int64), minlength=buckets)
+    return int((cnt[b.astype(np.int64)] >= max(thr, 1)).sum()) > cap
+
+
+def check(L, queries, subs, thr, grid=2):
+    got = run(L, queries, subs, thr, grid)
+    for q, lists in enumerate(queries):
+        if must_hand_on(L, lists, thr):
+            assert got[q] is None, f"query {q} should have been handed to the global path"
+        else:
+            assert got[q] is not None, f"query {q} should have been resolved"
+            want = expected(lists, thr)
+            assert got[q].size == want.size and (got[q] == want).all(), f"query {q}"
+
+
+def chance_query(rng, subs, list_len, true_ids, hits_per_true):
+    """lists of unrelated ids (chance collisions) + a few ids present in hits_per_true of the lists"""
+    lists = [list(rng.integers(0, 2_000_000, size=int(rng.integers(0, list_len + 1)))) for _ in range(subs)]
+    for t in true_ids:
+        for j in rng.choice(subs, size=min(hits_per_true, subs), replace=False):
+            lists[j].append(t)
+    return [np.asarray(rng.permutation(l), dtype=np.uint32) for l in lists]
+
+
+@pytest.mark.parametrize("subs,thr", [(60, 6), (120, 12), (30, 3), (7, 1), (33, 2)])
+def test_chance_collisions_and_true_candidates(emul, subs, thr):
+    rng = np.random.default_rng(subs * 100 + thr)
+    qs = [chance_query(rng, subs, L, rng.integers(0, 4_000_000_000, size=t), h)
+          for L, t, h in ((40, 3, subs), (120, 20, thr), (300, 0, 0), (3, 1, thr - 1 if thr > 1 else 1), (0, 2, subs),
+                          (1, 5, thr + 1))]
+    check(emul, qs, subs, thr, grid=int(rng.integers(1, 4)))
+
+
+def test_empty_singleton_and_sentinel_like_ids(emul):
+    subs = 12
+    big = 0xFFFFFFFE                                    # largest legal read id
+    qs = [[np.zeros(0, np.uint32)] * subs,
+          [np.asarray([5], np.uint32)] * subs,          # singletons in both representations
+          [np.asarray([big, 0], np.uint32)] * subs,
+          [np.asarray([7] * 9, np.uint32)] + [np.zeros(0, np.uint32)] * (subs - 1)]     # one list repeats an id
+    for thr in (1, 2, 9, 12, 13):
+        check(emul, qs, subs, thr, grid=1)
+
+
+def test_hand_on_rules(emul):
+    """more than 65535 ids, or more than kMidCap ids above the threshold, go to the global path; the
+    query next to them is still resolved"""
+    buckets, cap, max_ids = emul.consts
+    rng = np.random.default_rng(3)
+    subs = 40
+    too_many = [rng.integers(0, 1 << 31, size=max_ids // subs + 2).astype(np.uint32) for _ in range(subs)]
+    crowd = [np.arange(1000, 1000 + 400, dtype=np.uint32)] * subs        # 400 ids x 40 lists, all above thr
+    fits = [np.arange(50, 50 + cap // subs, dtype=np.uint32)] * subs      # exactly kMidCap-ish survivors
+    normal = chance_query(rng, subs, 60, [11, 12, 13], 10)
+    qs = [too_many, normal, crowd, fits]
+    assert must_hand_on(emul, too_many, 5) and must_hand_on(emul, crowd, 5) and not must_hand_on(emul, fits, 5)
+    check(emul, qs, subs, 5, grid=2)
