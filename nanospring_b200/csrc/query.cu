@@ -30,6 +30,7 @@ namespace nsmh {
 constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer
 constexpr int kHashSlots = 512;      // counting table of the common path: 512 keys + 512 counters (same buffer)
 constexpr int kHashMaxIds = 256;     // ... for up to this many gathered ids (load factor <= 0.5)
+static_assert(kHashMaxIds >= kWarpFilterBuckets / 2, "the sort path keeps its filter counters in the result area");
 constexpr int kWarpWords = kLookupCap + kHashMaxIds + 32;   // + result list + a few scalars
 constexpr int kLookupWarps = 8;
 constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
@@ -483,20 +484,27 @@ count_kernel(Src src, CountArgs a) {
                 __syncwarp();
                 continue;
             }
+            // ids whose counting-filter bucket stays below the threshold cannot qualify: drop them
+            // before sorting (query_mid.cuh; `res` is unused on this path and holds the counters)
+            uint32_t Ts = T;
+            if (a.thr > 1 && T > 64) {
+                __syncwarp();
+                Ts = warp_filter_ids(buf, T, a.thr, res, lane);
+            }
             uint32_t P = 32;
-            while (P < T) P <<= 1;
-            for (uint32_t i = T + lane; i < P; i += 32) buf[i] = kNoId;
+            while (P < Ts) P <<= 1;
+            for (uint32_t i = Ts + lane; i < P; i += 32) buf[i] = kNoId;
             __syncwarp();
             warp_bitonic_smem(buf, P, lane);
             // run lengths against the threshold (ReadFilter.cpp:76-82), compacted in place
-            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+            for (uint32_t i0 = 0; i0 < Ts; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 bool ok = false;
                 uint32_t v = 0;
-                if (i < T) {
+                if (i < Ts) {
                     v = buf[i];
                     const bool head = i == 0 || buf[i - 1] != v;
-                    ok = head && (a.thr <= 1 || (i + a.thr - 1 < T && buf[i + a.thr - 1] == v));
+                    ok = head && (a.thr <= 1 || (i + a.thr - 1 < Ts && buf[i + a.thr - 1] == v));
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, ok);
                 __syncwarp();       // every read of this round happens before its writes (R <= i0)

@@ -43,6 +43,42 @@ __device__ __forceinline__ void warp_bitonic_smem(uint32_t *buf, uint32_t P, int
     }
 }
 
+// ------------------------------------------------------------------ counting filter, in place --
+// The same idea for the ids a warp has already laid out in its sort buffer (count_kernel's sort path,
+// 256 < gathered ids <= kLookupCap): count them into 512 16-bit counters, keep the ids whose bucket
+// reaches the threshold (stable, in place), and let the bitonic sort run on the survivors only -
+// typically tens instead of a thousand.  Exact for the same reason as below; T <= 65535.
+constexpr int kWarpFilterBuckets = 512;     // two per word: c16 = kWarpFilterBuckets / 2 words
+
+__device__ __forceinline__ uint32_t warp_filter_bucket(uint32_t id) { return (id * 0x9E3779B1u) >> 23; }   // 9 bits
+
+__device__ __forceinline__ uint32_t warp_filter_ids(uint32_t *buf, uint32_t T, uint32_t thr, uint32_t *c16, int lane) {
+    for (int i = lane; i < kWarpFilterBuckets / 2; i += 32) c16[i] = 0;
+    __syncwarp();
+    for (uint32_t i = lane; i < T; i += 32) {
+        const uint32_t b = warp_filter_bucket(buf[i]);
+        atomicAdd(c16 + (b >> 1), 1u << (16 * (b & 1)));
+    }
+    __syncwarp();
+    uint32_t S = 0;
+    for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        bool keep = false;
+        uint32_t v = 0;
+        if (i < T) {
+            v = buf[i];
+            const uint32_t b = warp_filter_bucket(v);
+            keep = ((c16[b >> 1] >> (16 * (b & 1))) & 0xFFFFu) >= thr;
+        }
+        const uint32_t mask = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();       // every read of this round happens before its writes (S <= i0)
+        if (keep) buf[S + __popc(mask & ((1u << lane) - 1))] = v;
+        S += __popc(mask);
+        __syncwarp();
+    }
+    return S;
+}
+
 // ------------------------------------------------------------------ counting-filter tier --
 // With small k (or very deep coverage) most table groups hold tens of reads that share a sketch
 // value by chance, so a query gathers thousands of ids of which only a handful occur

@@ -67,4 +67,51 @@ void mid_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, ui
     });
 }
 
+// count_kernel's sort path for ONE query whose T <= 1024 gathered ids are already laid out: counting
+// filter in place (warp_filter_ids, counters in a 256-word area), bitonic sort of the survivors,
+// run lengths against the threshold.  out gets the emitted ids, *survivors what the filter kept.
+void sortpath_emul_run(const uint32_t *ids, uint32_t T, uint32_t thr, int use_filter, uint32_t *out, uint32_t *R_out,
+                       uint32_t *survivors) {
+    std::vector<uint32_t> buf(1024 + 256 + 32, 0xA5A5A5A5u);
+    for (uint32_t i = 0; i < T; ++i) buf[i] = ids[i];
+    uint32_t R_shared = 0, S_shared = 0;
+    emu_launch(1, 32, [&] {
+        const int lane = threadIdx.x & 31;
+        uint32_t *b = buf.data(), *res = b + 1024;
+        uint32_t Ts = T;
+        if (use_filter && thr > 1 && T > 64) {
+            __syncwarp();
+            Ts = warp_filter_ids(b, T, thr, res, lane);
+        }
+        uint32_t P = 32;
+        while (P < Ts) P <<= 1;
+        for (uint32_t i = Ts + lane; i < P; i += 32) b[i] = kNoId;
+        __syncwarp();
+        warp_bitonic_smem(b, P, lane);
+        uint32_t R = 0;
+        for (uint32_t i0 = 0; i0 < Ts; i0 += 32) {
+            const uint32_t i = i0 + lane;
+            bool ok = false;
+            uint32_t v = 0;
+            if (i < Ts) {
+                v = b[i];
+                const bool head = i == 0 || b[i - 1] != v;
+                ok = head && (thr <= 1 || (i + thr - 1 < Ts && b[i + thr - 1] == v));
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, ok);
+            __syncwarp();
+            if (ok) b[R + __popc(m & ((1u << lane) - 1))] = v;
+            R += __popc(m);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            R_shared = R;
+            S_shared = Ts;
+        }
+    });
+    for (uint32_t i = 0; i < R_shared; ++i) out[i] = buf[i];
+    *R_out = R_shared;
+    *survivors = S_shared;
+}
+
 }  // extern "C"

@@ -139,3 +139,41 @@ def test_hand_on_rules(emul):
     qs = [too_many, normal, crowd, fits]
     assert must_hand_on(emul, too_many, 5) and must_hand_on(emul, crowd, 5) and not must_hand_on(emul, fits, 5)
     check(emul, qs, subs, 5, grid=2)
+
+
+@pytest.mark.parametrize("thr", [1, 2, 6, 12, 60])
+def test_in_place_filter_of_the_warp_sort_path(emul, thr):
+    """count_kernel's sort path (up to 1024 gathered ids in the warp buffer): with the counting
+    filter in front of the bitonic sort the emitted ids are the same as without it, and equal to
+    sort-and-count; on chance-collision inputs the filter leaves a small fraction to sort."""
+    emul.sortpath_emul_run.argtypes = [u32p, C.c_uint32, C.c_uint32, C.c_int, u32p, u32p, u32p]
+    emul.sortpath_emul_run.restype = None
+    rng = np.random.default_rng(100 + thr)
+    cases = []
+    for T in (0, 1, 31, 64, 65, 257, 600, 1000, 1024):
+        ids = rng.integers(0, 3_000_000, size=T).astype(np.uint32)          # chance collisions only
+        cases.append(ids)
+        if T >= 65:
+            true = rng.integers(0, 0xFFFFFFFE, size=4, dtype=np.uint64).astype(np.uint32)
+            reps = np.repeat(true, [max(thr, 1), max(thr - 1, 1), min(3 * max(thr, 1), 60), 1])[:T // 2]
+            mixed = np.concatenate([ids[:T - reps.size], reps])
+            cases.append(rng.permutation(mixed).astype(np.uint32))
+    cases.append(np.full(1024, 77, dtype=np.uint32))                        # one id only
+    cases.append(np.repeat(np.arange(64, dtype=np.uint32), 16))             # everything qualifies for thr <= 16
+    for ids in cases:
+        v, c = np.unique(ids, return_counts=True)
+        want = v[c >= max(thr, 1)].astype(np.uint32)
+        for use_filter in (1, 0):
+            out = np.zeros(1024 + 8, dtype=np.uint32)
+            R, S = C.c_uint32(0), C.c_uint32(0)
+            emul.sortpath_emul_run(np.ascontiguousarray(ids).ctypes.data_as(u32p), ids.size, thr, use_filter,
+                                   out.ctypes.data_as(u32p), C.byref(R), C.byref(S))
+            assert R.value == want.size and (out[:R.value] == want).all(), (ids.size, thr, use_filter)
+            if use_filter and thr > 1 and ids.size > 64:
+                b = (((ids.astype(np.uint64) * 0x9E3779B1) & 0xFFFFFFFF) >> 23).astype(np.int64)
+                kept = int((np.bincount(b, minlength=512)[b] >= thr).sum())
+                assert S.value == kept, "the filter keeps exactly the ids of the buckets that reach the threshold"
+                if thr >= 6 and c.max() == 1 and ids.size >= 600:
+                    assert kept <= ids.size // 4, "chance collisions are mostly filtered out"
+            else:
+                assert S.value == ids.size
