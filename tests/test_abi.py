@@ -40,6 +40,21 @@ def test_header_compiles_as_plain_c(tmp_path):
                            "-c", str(src), "-o", str(tmp_path / "t.o")])
 
 
+def test_struct_layouts_match_the_python_bindings(tmp_path):
+    """sizeof / offsetof of nsmh_stats and nsmh_synth_params as the C compiler sees them vs the ctypes mirrors."""
+    fields = [f for f, _ in _lib.Stats._fields_]
+    src = tmp_path / "layout.c"
+    body = "".join(f'printf("{f} %zu\\n", offsetof(nsmh_stats, {f}));\n' for f in fields)
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "nsmh.h"\nint main(void){\n'
+                   'printf("sizeof %zu\\n", sizeof(nsmh_stats));\n' + body + 'return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = dict(line.split() for line in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(out["sizeof"]) == C.sizeof(_lib.Stats)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.Stats, f).offset, f
+
+
 def test_library_is_sm100a_only():
     out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     archs = set(re.findall(r"sm_(\d+a?)", out))
