@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/nsmh.h"
+#include "nsmh_constants.h"
 
 namespace nsmh {
 
@@ -40,7 +41,6 @@ struct DevBuf {
 };
 
 // ------------------------------------------------------------- constants --
-constexpr int kWordBases = 16;          // bases per packed u32 word, first base in bits 31..30
 constexpr int kTileWords = 640;         // default words (10240 k-mer start positions) per sketch tile: 32 warps per SM fit
 constexpr int kFilterMaxBits = 12;      // largest prefix width b of the sketch filter tables
 constexpr int kFilterTabSize = 1 << (kFilterMaxBits + 1);  // table for b lives at [2^b, 2^(b+1))
@@ -48,7 +48,6 @@ constexpr int kFilterLambdaLog2 = 2;    // default: b = floor(log2(#kmers)) - 2 
 constexpr int kFilter3MaxBits = 11;     // 3-positions-per-lookup tables: window of b+4 bits
 constexpr int kFilter3TabSize = 1 << (kFilter3MaxBits + 5);   // table for b lives at [2^(b+4), 2^(b+5))
 constexpr uint64_t kEmptyKey = ~0ULL;   // empty marker of the hash tables (key ~0 has its own slot)
-constexpr int kPackPadWords = 8;        // zero words after the last packed word (k-mer window overrun)
 
 // A set of reads resident on the device: the reference's ReadData as far as the
 // MinHash path needs it (ReadData.h:26-60), 2-bit packed in ONE continuous
