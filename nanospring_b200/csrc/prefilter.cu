@@ -53,7 +53,8 @@ int compute_read_flags(nsmh_ctx *c) {
 }
 
 // Compacts ws.out_off / ws.out_ids in place (through ws.tmp_ids), dropping ids whose flags
-// intersect `drop`.  flags index = id - id_base (ids outside the local reads are kept).
+// intersect `drop`.  flags index = candidate id: nsmh_query_all_drop only accepts single-GPU bulk results,
+// where ids are ids of the loaded reads (ids >= num_reads cannot occur there and would be kept).
 int drop_flagged_candidates(nsmh_ctx *c, QueryWs &ws, uint32_t drop, cudaStream_t s) {
     const uint32_t nq = ws.last_nq;
     if (nq == 0 || ws.last_total == 0) return NSMH_OK;
