@@ -27,12 +27,6 @@
 
 namespace nsmh {
 
-constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer
-constexpr int kHashSlots = 512;      // counting table of the common path: 512 keys + 512 counters (same buffer)
-constexpr int kHashMaxIds = 256;     // ... for up to this many gathered ids (load factor <= 0.5)
-static_assert(kHashMaxIds >= kWarpFilterBuckets / 2, "the sort path keeps its filter counters in the result area");
-constexpr int kWarpWords = kLookupCap + kHashMaxIds + 32;   // + result list + a few scalars
-constexpr int kLookupWarps = 8;
 constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
 constexpr int kMaxParts = 16;        // PartsSrc: at most this many partial lists per query
 // The n tables, probed for a batch of query sketches.  probe_items_kernel resolves every
@@ -87,15 +81,6 @@ struct ProbeSrc {
     }
     __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
 };
-
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    return v;
-}
 
 constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
 constexpr int kProbeRows = 256;    // queries per block = threads per block
@@ -335,199 +320,12 @@ struct PeerSrc {
     __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
 };
 
-struct CountArgs {
-    uint32_t *qcount;        // [nq+1] result ids per query
-    uint64_t *qpos;          // [nq]   where the query's results start in tmp_ids (~0: heavy query)
-    uint32_t *tmp_ids;       // results in completion order
-    uint64_t tmp_cap;
-    uint32_t *heavy_list;    // [nq]
-    unsigned long long *counters;   // [0] heavy queries, [1] gathered ids, [2] result ids (tmp cursor)
-    uint32_t nq, thr;
-};
-
-// counting table: one more occurrence of `id`; the lane that brings the count to `thr` emits it
-__device__ __forceinline__ void count_id(uint32_t *keys, uint32_t *cnts, uint32_t *res, uint32_t *rcount,
-                                         uint32_t id, uint32_t thr) {
-    uint32_t h = (id * 0x9E3779B1u) >> 23;      // 9 bits = kHashSlots
-    for (;;) {
-        const uint32_t prev = atomicCAS(keys + h, kNoId, id);
-        if (prev == kNoId || prev == id) break;
-        h = (h + 1) & (kHashSlots - 1);
-    }
-    if (atomicAdd(cnts + h, 1u) + 1u == thr) res[atomicAdd(rcount, 1u)] = id;
-}
-
-// One warp per query, ONE pass.  Common case (<= kHashMaxIds gathered ids): the ids are counted
-// in a warp-private shared-memory hash table as they arrive and an id is emitted the moment its
-// count reaches the threshold; the handful of results is sorted with warp shuffles.  Larger
-// queries (<= kLookupCap ids) are laid out, sorted with a bitonic network and run-length
-// thresholded.  Results go to tmp_ids in completion order; a prefix sum over qcount and
-// csr_place_kernel then produce the CSR.  Queries beyond kLookupCap take the global path.
+// count_kernel: query_mid.cuh (count_body) - one warp per query, one pass
 template <typename Src>
 __global__ void __launch_bounds__(kLookupWarps * 32)
 count_kernel(Src src, CountArgs a) {
     extern __shared__ __align__(16) uint32_t s_buf[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *buf = s_buf + (size_t)warp * kWarpWords;
-    uint32_t *keys = buf, *cnts = buf + kHashSlots;
-    uint32_t *res = buf + kLookupCap;           // kHashMaxIds entries
-    uint32_t *rcount = res + kHashMaxIds;
-    const uint32_t total_warps = gridDim.x * kLookupWarps;
-    const uint32_t subs = src.subs();
-    unsigned long long pairs_local = 0;
-
-    for (uint32_t q = blockIdx.x * kLookupWarps + warp; q < a.nq; q += total_warps) {
-        // ---- common path: count while gathering ----
-        {
-            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
-            uint4 *c4 = reinterpret_cast<uint4 *>(cnts);
-#pragma unroll
-            for (int i = 0; i < kHashSlots / 4 / 32; ++i) {
-                k4[i * 32 + lane] = make_uint4(kNoId, kNoId, kNoId, kNoId);
-                c4[i * 32 + lane] = make_uint4(0, 0, 0, 0);
-            }
-            if (lane == 0) *rcount = 0;
-        }
-        __syncwarp();
-        uint32_t T = 0;
-        bool small = true;
-        for (uint32_t j0 = 0; j0 < subs && small; j0 += 64) {
-            const uint32_t ja = j0 + lane, jb = j0 + 32 + lane;
-            typename Src::Pending pa, pb;
-            if (ja < subs) pa = src.begin(q, ja);
-            if (jb < subs) pb = src.begin(q, jb);
-            ListRef r[2];
-            r[0] = ja < subs ? src.finish(pa) : empty_list();
-            r[1] = jb < subs ? src.finish(pb) : empty_list();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t rt = r[h].c;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);
-                T = (uint64_t)T + rt > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + rt;
-                if (T > kHashMaxIds) { small = false; break; }
-                if (r[h].c == 1) count_id(keys, cnts, res, rcount, r[h].ptr ? r[h].ptr[0] : r[h].one, a.thr);
-                else if (r[h].c > 1 && r[h].c <= 8)
-                    for (uint32_t i = 0; i < r[h].c; ++i) count_id(keys, cnts, res, rcount, r[h].ptr[i], a.thr);
-                uint32_t big = __ballot_sync(0xffffffffu, r[h].c > 8);
-                while (big) {
-                    const int sl = __ffs(big) - 1;
-                    big &= big - 1;
-                    const uint32_t *bp = reinterpret_cast<const uint32_t *>(
-                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r[h].ptr), sl));
-                    const uint32_t bc = __shfl_sync(0xffffffffu, r[h].c, sl);
-                    for (uint32_t i = lane; i < bc; i += 32) count_id(keys, cnts, res, rcount, bp[i], a.thr);
-                }
-            }
-        }
-        __syncwarp();
-        uint32_t R = 0;
-        const uint32_t *out = res;
-        if (small) {
-            R = *rcount;
-            if (R > 1 && R <= 32) {
-                // shuffle bitonic sort of up to 32 results
-                uint32_t v = lane < (int)R ? res[lane] : kNoId;
-#pragma unroll
-                for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-                    for (int j = kk >> 1; j > 0; j >>= 1) {
-                        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
-                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
-                        v = (lower == up) ? min(v, o) : max(v, o);
-                    }
-                }
-                __syncwarp();
-                if (lane < (int)R) res[lane] = v;
-                __syncwarp();
-            } else if (R > 32) {
-                uint32_t P = 64;
-                while (P < R) P <<= 1;
-                for (uint32_t i = R + lane; i < P; i += 32) res[i] = kNoId;
-                __syncwarp();
-                warp_bitonic_smem(res, P, lane);
-            }
-        } else {
-            // ---- sort path: lay the lists out in the buffer (the counting table is abandoned) ----
-            T = 0;
-            for (uint32_t j0 = 0; j0 < subs; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                const ListRef r = j < subs ? src.get(q, j) : empty_list();
-                const uint32_t incl = warp_incl_scan(r.c, lane);
-                const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t off = T + incl - r.c;
-                if ((uint64_t)T + round_total <= kLookupCap) {
-                    if (r.c == 1) buf[off] = r.ptr ? r.ptr[0] : r.one;
-                    else if (r.c > 1 && r.c <= 8)
-                        for (uint32_t i = 0; i < r.c; ++i) buf[off + i] = r.ptr[i];
-                    uint32_t big = __ballot_sync(0xffffffffu, r.c > 8);
-                    while (big) {
-                        const int sl = __ffs(big) - 1;
-                        big &= big - 1;
-                        const uint32_t *bp = reinterpret_cast<const uint32_t *>(
-                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r.ptr), sl));
-                        const uint32_t bc = __shfl_sync(0xffffffffu, r.c, sl);
-                        const uint32_t bo = __shfl_sync(0xffffffffu, off, sl);
-                        for (uint32_t i = lane; i < bc; i += 32) buf[bo + i] = bp[i];
-                    }
-                }
-                // saturate: the sum of the list sizes can exceed 32 bits only in theory
-                T = (uint64_t)T + round_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + round_total;
-            }
-            if (T > kLookupCap) {                     // global path handles this query
-                pairs_local += lane == 0 ? T : 0;
-                if (lane == 0) {
-                    a.qcount[q] = 0;
-                    a.qpos[q] = ~0ULL;
-                    a.heavy_list[atomicAdd(a.counters, 1ULL)] = q;
-                }
-                __syncwarp();
-                continue;
-            }
-            // ids whose counting-filter bucket stays below the threshold cannot qualify: drop them
-            // before sorting (query_mid.cuh; `res` is unused on this path and holds the counters)
-            uint32_t Ts = T;
-            if (a.thr > 1 && T > 64) {
-                __syncwarp();
-                Ts = warp_filter_ids(buf, T, a.thr, res, lane);
-            }
-            uint32_t P = 32;
-            while (P < Ts) P <<= 1;
-            for (uint32_t i = Ts + lane; i < P; i += 32) buf[i] = kNoId;
-            __syncwarp();
-            warp_bitonic_smem(buf, P, lane);
-            // run lengths against the threshold (ReadFilter.cpp:76-82), compacted in place
-            for (uint32_t i0 = 0; i0 < Ts; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                bool ok = false;
-                uint32_t v = 0;
-                if (i < Ts) {
-                    v = buf[i];
-                    const bool head = i == 0 || buf[i - 1] != v;
-                    ok = head && (a.thr <= 1 || (i + a.thr - 1 < Ts && buf[i + a.thr - 1] == v));
-                }
-                const uint32_t m = __ballot_sync(0xffffffffu, ok);
-                __syncwarp();       // every read of this round happens before its writes (R <= i0)
-                if (ok) buf[R + __popc(m & ((1u << lane) - 1))] = v;
-                R += __popc(m);
-                __syncwarp();
-            }
-            out = buf;
-        }
-        pairs_local += lane == 0 ? T : 0;
-        // ---- hand the results over ----
-        unsigned long long base = 0;
-        if (lane == 0) {
-            if (R) base = atomicAdd(a.counters + 2, (unsigned long long)R);
-            a.qcount[q] = R;
-            a.qpos[q] = base;
-        }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base + R <= a.tmp_cap)
-            for (uint32_t i = lane; i < R; i += 32) a.tmp_ids[base + i] = out[i];
-        __syncwarp();
-    }
-    if (lane == 0 && pairs_local) atomicAdd(a.counters + 1, pairs_local);
+    count_body(src, a, s_buf);
 }
 
 // tmp_ids (completion order) -> CSR (query order); 8 lanes per query

@@ -83,6 +83,12 @@ static inline void __syncwarp() {
     emu_warp->bar.arrive_and_wait();
 }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline uint32_t atomicCAS(uint32_t *p, uint32_t expected, uint32_t desired) {
+    __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
+    return expected;                                           // the value found, like the device intrinsic
+}
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline uint32_t __ballot_sync(uint32_t, bool pred) {
     EmuWarp *w = emu_warp;
     w->slot[emu_lane] = pred ? 1u : 0u;

@@ -17,6 +17,11 @@ struct CsrSrc {
     const uint32_t *ids;
     uint32_t nsubs;
     uint32_t subs() const { return nsubs; }
+    struct Pending {
+        uint32_t q, j;
+    };
+    Pending begin(uint32_t q, uint32_t j) const { return Pending{q, j}; }
+    ListRef finish(Pending p) const { return get(p.q, p.j); }
     ListRef get(uint32_t q, uint32_t j) const {
         const uint64_t o0 = list_off[(uint64_t)q * nsubs + j], o1 = list_off[(uint64_t)q * nsubs + j + 1];
         ListRef r;
@@ -65,6 +70,27 @@ void mid_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, ui
         mid_count_body(src, m, smem.data() + ((size_t)blockIdx.x * 2 + warp) * kMidWarpWords, blockIdx.x * 2 + warp,
                        gridDim.x * 2);
     });
+}
+
+// The whole lookup kernel body (count_body = what count_kernel in query.cu wraps), blocks of
+// kLookupWarps warps.  qcount [nq+1], qpos [nq], heavy_list [nq], counters [3] zeroed by the caller.
+void count_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, uint32_t subs, uint32_t thr,
+                    unsigned grid, uint32_t *qcount, uint64_t *qpos, uint32_t *tmp_ids, uint64_t tmp_cap,
+                    uint32_t *heavy_list, unsigned long long *counters) {
+    CsrSrc src{list_off, ids, subs};
+    CountArgs a;
+    a.qcount = qcount;
+    a.qpos = qpos;
+    a.tmp_ids = tmp_ids;
+    a.tmp_cap = tmp_cap;
+    a.heavy_list = heavy_list;
+    a.counters = counters;
+    a.nq = nq;
+    a.thr = thr ? thr : 1;
+    std::vector<uint32_t> smem((size_t)grid * kLookupWarps * kWarpWords + 4, 0xA5A5A5A5u);
+    uint32_t *base = smem.data();
+    while (reinterpret_cast<uintptr_t>(base) & 15) ++base;                  // the body stores uint4
+    emu_launch(grid, kLookupWarps * 32, [&] { count_body(src, a, base + (size_t)blockIdx.x * kLookupWarps * kWarpWords); });
 }
 
 // count_kernel's sort path for ONE query whose T <= 1024 gathered ids are already laid out: counting

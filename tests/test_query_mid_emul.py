@@ -177,3 +177,74 @@ def test_in_place_filter_of_the_warp_sort_path(emul, thr):
                     assert kept <= ids.size // 4, "chance collisions are mostly filtered out"
             else:
                 assert S.value == ids.size
+
+
+# ------------------------------------------------------------------ the lookup kernel's body --
+def run_count(L, queries, subs, thr, grid=1, tmp_cap=None):
+    L.count_emul_run.argtypes = [u64p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, u32p, u64p, u32p, C.c_uint64,
+                                 u32p, C.POINTER(C.c_ulonglong)]
+    L.count_emul_run.restype = None
+    nq = len(queries)
+    flat, off = [], [0]
+    for lists in queries:
+        assert len(lists) == subs
+        for l in lists:
+            flat.append(np.asarray(l, dtype=np.uint32))
+            off.append(off[-1] + len(l))
+    ids = np.concatenate(flat + [np.zeros(1, np.uint32)])
+    off = np.asarray(off, dtype=np.uint64)
+    cap = int(off[-1]) + 1 if tmp_cap is None else tmp_cap
+    qcount = np.full(nq + 1, 0xEEEEEEEE, dtype=np.uint32)
+    qpos = np.full(nq, 0x1234, dtype=np.uint64)
+    tmp = np.full(cap + 8, 0xDEADBEEF, dtype=np.uint32)
+    heavy = np.full(nq + 1, 0xFFFFFFFF, dtype=np.uint32)
+    counters = (C.c_ulonglong * 3)(0, 0, 0)
+    L.count_emul_run(off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p), nq, subs, thr, grid, qcount.ctypes.data_as(u32p),
+                     qpos.ctypes.data_as(u64p), tmp.ctypes.data_as(u32p), cap, heavy.ctypes.data_as(u32p), counters)
+    assert (tmp[cap:] == 0xDEADBEEF).all(), "wrote past tmp_cap"
+    return qcount, qpos, tmp, heavy, counters
+
+
+@pytest.mark.parametrize("subs,thr", [(60, 6), (60, 1), (24, 2), (120, 12), (7, 7), (33, 0)])
+def test_lookup_kernel_body_all_paths(emul, subs, thr):
+    """count_body: counting table (<= 256 gathered ids), filter + sort path (<= 1024), hand-over of larger
+    queries; results per query ascending and equal to sort-and-count; the counters add up."""
+    rng = np.random.default_rng(subs * 7 + thr)
+    specs = [(0, 0, 0), (1, 1, subs), (3, 4, max(thr, 1)), (4, 40, max(thr, 1) + 1), (8, 3, subs // 2 + 1), (12, 0, 0),
+             (16, 6, max(thr, 1)), (30, 2, subs), (90, 1, 1), (2, 45, subs), (1, 70, 3)]
+    qs = [chance_query(rng, subs, L, rng.integers(0, 0xFFFFFFFE, size=t, dtype=np.uint64), min(h, subs)) for L, t, h in specs]
+    qs.append([np.asarray([9], np.uint32)] * subs)                          # singletons only (inlined and pointed-to)
+    qs.append([np.arange(20, dtype=np.uint32)] * subs if subs * 20 <= 1024 else [np.arange(5, dtype=np.uint32)] * subs)
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, grid=int(rng.integers(1, 3)))
+    T = [sum(len(l) for l in lists) for lists in qs]
+    want_heavy = sorted(q for q, t in enumerate(T) if t > 1024)
+    assert sorted(int(x) for x in heavy[:counters[0]]) == want_heavy
+    assert counters[1] == sum(T)
+    paths = set()
+    emitted = 0
+    for q, lists in enumerate(qs):
+        if T[q] > 1024:
+            assert qcount[q] == 0 and qpos[q] == np.iinfo(np.uint64).max
+            paths.add("handed on")
+            continue
+        want = expected(lists, thr)
+        got = tmp[int(qpos[q]):int(qpos[q]) + int(qcount[q])]
+        assert got.size == want.size and (got == want).all(), f"query {q} (T = {T[q]})"
+        emitted += want.size
+        paths.add("table" if T[q] <= 256 else "sort")
+    assert counters[2] == emitted
+    assert {"table", "sort"} <= paths
+
+
+def test_lookup_kernel_body_result_buffer_too_small(emul):
+    """The result cursor keeps counting past tmp_cap and nothing is written there: the host retries once
+    with the exact size (count_and_emit in query.cu)."""
+    rng = np.random.default_rng(8)
+    subs, thr = 20, 1
+    qs = [chance_query(rng, subs, 10, [], 0) for _ in range(6)]
+    total = sum(expected(l, thr).size for l in qs)
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, tmp_cap=total // 3)
+    assert counters[2] == total and counters[0] == 0
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, tmp_cap=total)
+    for q, lists in enumerate(qs):
+        assert (tmp[int(qpos[q]):int(qpos[q]) + int(qcount[q])] == expected(lists, thr)).all()
