@@ -41,12 +41,6 @@ struct DevBuf {
 };
 
 // ------------------------------------------------------------- constants --
-constexpr int kTileWords = 640;         // default words (10240 k-mer start positions) per sketch tile: 32 warps per SM fit
-constexpr int kFilterMaxBits = 12;      // largest prefix width b of the sketch filter tables
-constexpr int kFilterTabSize = 1 << (kFilterMaxBits + 1);  // table for b lives at [2^b, 2^(b+1))
-constexpr int kFilterLambdaLog2 = 2;    // default: b = floor(log2(#kmers)) - 2  => 4..8 k-mers expected per bucket
-constexpr int kFilter3MaxBits = 11;     // 3-positions-per-lookup tables: window of b+4 bits
-constexpr int kFilter3TabSize = 1 << (kFilter3MaxBits + 5);   // table for b lives at [2^(b+4), 2^(b+5))
 constexpr uint64_t kEmptyKey = ~0ULL;   // empty marker of the hash tables (key ~0 has its own slot)
 
 // A set of reads resident on the device: the reference's ReadData as far as the

@@ -22,7 +22,10 @@ struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local emu_dim3 blockIdx, threadIdx;
 static emu_dim3 gridDim, blockDim;
 
+struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
 template <typename T> static inline T __ldg(const T *p) { return *p; }
@@ -33,6 +36,11 @@ static inline uint32_t __vcmpeq4(uint32_t a, uint32_t b) {
     for (int i = 0; i < 4; ++i)
         if (((a >> (8 * i)) & 0xFF) == ((b >> (8 * i)) & 0xFF)) r |= 0xFFu << (8 * i);
     return r;
+}
+static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) {   // shift clamped to 32
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> (sh > 32 ? 32 : sh));
 }
 static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
     const uint64_t src = ((uint64_t)b << 32) | a;              // selector nibbles 0..7 only (no sign replication)
@@ -79,14 +87,23 @@ static inline unsigned long long __shfl_sync(uint32_t, unsigned long long v, int
 static inline uint32_t __shfl_sync(uint32_t, uint32_t v, int src) { return (uint32_t)emu_exchange64(v, src); }
 static inline unsigned long long __shfl_xor_sync(uint32_t, unsigned long long v, int m) { return emu_exchange64(v, emu_lane ^ m); }
 static inline uint32_t __shfl_xor_sync(uint32_t, uint32_t v, int m) { return (uint32_t)emu_exchange64(v, emu_lane ^ m); }
+static inline uint64_t __shfl_xor_sync(uint32_t, uint64_t v, int m) { return emu_exchange64(v, emu_lane ^ m); }
 static inline void __syncwarp() {
     emu_warp->bar.arrive_and_wait();
 }
+// only meaningful for kernels launched with ONE warp per block (emu_launch(grid, 32, ...))
+static inline void __syncthreads() { __syncwarp(); }
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline uint32_t atomicCAS(uint32_t *p, uint32_t expected, uint32_t desired) {
     __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
     return expected;                                           // the value found, like the device intrinsic
 }
+static inline unsigned long long atomicMin(unsigned long long *p, unsigned long long v) {
+    unsigned long long old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { }
+    return old;
+}
+static inline uint64_t min(uint64_t a, uint64_t b) { return a < b ? a : b; }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline uint32_t __ballot_sync(uint32_t, bool pred) {
@@ -98,6 +115,7 @@ static inline uint32_t __ballot_sync(uint32_t, bool pred) {
     w->bar.arrive_and_wait();
     return r;
 }
+static inline bool __any_sync(uint32_t m, bool pred) { return __ballot_sync(m, pred) != 0; }
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
     EmuWarp *w = emu_warp;
     w->slot[emu_lane] = v;
