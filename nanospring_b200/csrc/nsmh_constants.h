@@ -13,5 +13,25 @@ constexpr int kFilterTabSize = 1 << (kFilterMaxBits + 1);  // table for b lives 
 constexpr int kFilterLambdaLog2 = 2;    // default: b = floor(log2(#kmers)) - 2  => 4..8 k-mers expected per bucket
 constexpr int kFilter3MaxBits = 11;     // 3-positions-per-lookup tables: window of b+4 bits
 constexpr int kFilter3TabSize = 1 << (kFilter3MaxBits + 5);   // table for b lives at [2^(b+4), 2^(b+5))
+constexpr uint64_t kEmptyKey = ~0ULL;   // empty marker of the hash tables (key ~0 has its own slot)
+
+// One 16-byte hash-table slot = one 32-byte sector per probe.  Slots start as
+// all-ones: key ~0 is the empty marker and cntm1 (group size - 1) wraps to 0 on
+// the first insert.  val = the read id itself for a group of one, else the start
+// of the group in Tables::ids.
+struct __align__(16) Slot {
+    uint64_t key;
+    uint32_t val;
+    uint32_t cntm1;
+};
+
+// home slot / bucket of a key among `cap` of them (cap < 2^32, any value)
+__host__ __device__ __forceinline__ uint64_t slot_index(uint64_t key, uint64_t cap) {
+    const uint64_t h = (key * 0x9E3779B97F4A7C15ULL) >> 32;
+    return (h * cap) >> 32;
+}
+
+// slots per table region: cap (even) + the slot of key ~0, padded so every region starts on a sector
+__host__ __device__ __forceinline__ uint64_t region_stride(uint64_t cap) { return cap + 2; }
 
 } // namespace nsmh

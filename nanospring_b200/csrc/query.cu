@@ -29,59 +29,6 @@ namespace nsmh {
 
 constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
 constexpr int kMaxParts = 16;        // PartsSrc: at most this many partial lists per query
-// The n tables, probed for a batch of query sketches.  probe_items_kernel resolves every
-// (query, hash) item and stores {val, group size}; everything downstream reads those.
-__device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
-}
-
-struct ProbeSrc {
-    const uint64_t *qsk;     // [nq][n]
-    const Slot *slots;
-    const uint32_t *ids;
-    uint32_t *pval, *pcnt;   // [nq][n] probe results: the id / the start in ids, the group size
-    uint64_t cap;
-    uint32_t n;
-    // Probing is split in two so that the (random, DRAM-latency) bucket loads of several lists
-    // are in flight together: begin() issues the 32-byte load of the home bucket (both slots of
-    // one sector), finish() resolves the probe and only rarely has to move to the next bucket.
-    struct Pending {
-        uint64_t key, b;
-        uint64_t sa, sb, sc, sd;    // slot = {key, val | (cnt-1) << 32}, twice
-        uint32_t j;
-    };
-    __device__ __forceinline__ uint32_t subs() const { return n; }
-    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
-        Pending p;
-        p.j = j;
-        p.key = __ldg(qsk + (size_t)q * n + j);
-        p.b = p.key == kEmptyKey ? (cap >> 1) : slot_index(p.key, cap >> 1);   // key ~0 lives in the extra slot
-        ldg256(slots + (uint64_t)j * region_stride(cap) + 2 * p.b, p.sa, p.sb, p.sc, p.sd);
-        return p;
-    }
-    // group size (0 = absent) and val (the id itself for a group of one, else the start in ids)
-    __device__ __forceinline__ ListRef finish(Pending p) const {
-        const Slot *region = slots + (uint64_t)p.j * region_stride(cap);
-        const uint64_t nb = cap >> 1;
-        uint64_t hit = 0;
-        bool found = false;
-        for (;;) {
-            if (p.key == kEmptyKey || p.sa == p.key) { hit = p.sb; found = true; break; }
-            if (p.sa == kEmptyKey) break;
-            if (p.sc == p.key) { hit = p.sd; found = true; break; }
-            if (p.sc == kEmptyKey) break;
-            p.b = p.b + 1 == nb ? 0 : p.b + 1;
-            ldg256(region + 2 * p.b, p.sa, p.sb, p.sc, p.sd);
-        }
-        ListRef r;
-        r.c = found ? (uint32_t)(hit >> 32) + 1u : 0u;     // untouched extra slot: 0xFFFFFFFF + 1 = 0
-        r.one = (uint32_t)hit;
-        r.ptr = r.c == 1 ? nullptr : ids + r.one;
-        return r;
-    }
-    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
-};
-
 constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
 constexpr int kProbeRows = 256;    // queries per block = threads per block
 

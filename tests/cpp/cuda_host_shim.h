@@ -16,7 +16,8 @@
 #define __host__
 #define __forceinline__ inline
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
+#define __align__(x) alignas(x)
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 static thread_local emu_dim3 blockIdx, threadIdx;
@@ -91,8 +92,13 @@ static inline uint64_t __shfl_xor_sync(uint32_t, uint64_t v, int m) { return emu
 static inline void __syncwarp() {
     emu_warp->bar.arrive_and_wait();
 }
-// only meaningful for kernels launched with ONE warp per block (emu_launch(grid, 32, ...))
-static inline void __syncthreads() { __syncwarp(); }
+// emu_launch: one warp runs at a time, so this is only meaningful with ONE warp per block
+// (emu_launch(grid, 32, ...)); emu_launch_block runs all warps of a block concurrently and meets here
+static thread_local std::barrier<> *emu_block_bar = nullptr;
+static inline void __syncthreads() {
+    if (emu_block_bar) emu_block_bar->arrive_and_wait();
+    else __syncwarp();
+}
 static inline uint32_t atomicAdd(uint32_t *p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline uint32_t atomicCAS(uint32_t *p, uint32_t expected, uint32_t desired) {
     __atomic_compare_exchange_n(p, &expected, desired, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED);
@@ -116,6 +122,7 @@ static inline uint32_t __ballot_sync(uint32_t, bool pred) {
     return r;
 }
 static inline bool __any_sync(uint32_t m, bool pred) { return __ballot_sync(m, pred) != 0; }
+static inline bool __all_sync(uint32_t m, bool pred) { return __ballot_sync(m, !pred) == 0; }
 static inline uint32_t __reduce_add_sync(uint32_t, uint32_t v) {
     EmuWarp *w = emu_warp;
     w->slot[emu_lane] = v;
@@ -144,4 +151,30 @@ static inline void emu_launch(unsigned grid, unsigned block, const std::function
                 });
             for (auto &t : lanes) t.join();
         }
+}
+
+// The same with all warps of a block alive at once (block-level cooperation: __syncthreads, shared
+// counters).  `__shared__` variables are function-local statics: blocks run one after the other, so
+// one instance serves them all.  block must be a multiple of 32.
+#define __shared__ static
+static inline void emu_launch_block(unsigned grid, unsigned block, const std::function<void()> &body) {
+    gridDim.x = grid;
+    blockDim.x = block;
+    const unsigned nwarps = block / 32;
+    for (unsigned b = 0; b < grid; ++b) {
+        std::vector<EmuWarp> warps(nwarps);
+        std::barrier<> block_bar((std::ptrdiff_t)block);
+        std::vector<std::thread> threads;
+        for (unsigned t = 0; t < block; ++t)
+            threads.emplace_back([&, t] {
+                emu_warp = &warps[t / 32];
+                emu_lane = (int)(t % 32);
+                emu_block_bar = &block_bar;
+                blockIdx.x = b;
+                threadIdx.x = t;
+                body();
+                emu_block_bar = nullptr;
+            });
+        for (auto &th : threads) th.join();
+    }
 }
