@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE.json configs at FULL size on one B200, with size-independent parity checks.
 
-    python tools/config_sweep.py [--configs c2,c3,c4,c5] [--out profiles/x.jsonl]
+    python tests/config_sweep.py [--configs c2,c3,c4,c5] [--out profiles/x.jsonl]
 
   c2  100 000 reads, ~10 kb mean, 10 % error, 50 Mb genome, k=23 n=60 thr=6        (~1 Gbase)
   c2lo  the same at 2 % error: rich candidate sets for the lookup checks

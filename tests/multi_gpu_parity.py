@@ -1,7 +1,7 @@
 """Multi-GPU parity check, launched with torchrun (one process per GPU):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
-        --master-port 29511 tools/multi_gpu_parity.py
+        --master-port 29511 tests/multi_gpu_parity.py
 
 Every rank sketches its shard (boundaries on the prefix sum of bases), the sketch rows are
 all-gathered over NCCL, every rank builds the full tables and queries its own shard.  Rank 0

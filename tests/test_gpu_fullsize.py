@@ -1,4 +1,4 @@
-"""BASELINE.json configs at their FULL sizes on one B200 (tools/config_sweep.py does the work):
+"""BASELINE.json configs at their FULL sizes on one B200 (tests/config_sweep.py does the work):
 configs[1] (100 k reads, ~1 Gbase), configs[2]'s read set (1 M reads, ~10 Gbases) on a single GPU,
 the corners of configs[3]'s parameter sweep on it, and configs[4]'s ultra-long reads (~5 Gbases).
 No CPU pass over 10 Gbases: parity goes through size-independent properties - brute-force kernel ==
@@ -12,7 +12,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def _check(res):

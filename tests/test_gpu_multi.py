@@ -1,4 +1,4 @@
-"""2-GPU parity (skipped on a single-GPU box): tools/multi_gpu_parity.py under torchrun."""
+"""2-GPU parity (skipped on a single-GPU box): tests/multi_gpu_parity.py under torchrun."""
 import os
 import subprocess
 import sys
@@ -14,7 +14,7 @@ def test_two_gpu_sharded_run_equals_single_gpu():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tools", "multi_gpu_parity.py")]
+           "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "multi_gpu_parity.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
