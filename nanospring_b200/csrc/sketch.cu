@@ -40,9 +40,8 @@
 
 namespace nsmh {
 
-// ---- host side --------------------------------------------------------------------
-// Per prefix width b: hit/first tables at [2^b, 2^(b+1)), a per-b chain of hashes that
-// share a target prefix, and the 3-position table at [2^(b+4), 2^(b+5)).
+// ---- host side (the kernels are in sketch_kernels.cuh) -------------------------------
+// uploads the lookup tables of the filter kernel (layout: sketch_tables.h)
 int build_filter_tables(nsmh_ctx *c) {
     const FilterTables ft = make_filter_tables(c->rand.data(), c->n, c->k);
     const std::vector<uint8_t> &first = ft.first, &next = ft.next, &hit3 = ft.hit3;
