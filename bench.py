@@ -512,6 +512,22 @@ def main():
         except Exception as e:  # noqa: BLE001
             line["ingest"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
+    # ---- reverse-complement lookup: the production caller queries every window forward AND
+    #      reverse-complemented (Consensus.cpp:181-191); the second bulk pass is reported beside the step,
+    #      never inside `value`.  It packs the reverse complements, sketches them and probes the same tables.
+    if n_gpus == 1 and not args.no_e2e:
+        try:
+            f.queryAll(True, fetch=False)
+            rc_ms = []
+            for _ in range(max(1, min(args.steps, 3))):
+                rc_total = f.queryAll(True, fetch=False)
+                rc_ms.append(f.stats()["query_ms"])
+            line["rc_query"] = {"ms": float(np.mean(rc_ms)), "candidate_ids": int(rc_total),
+                                "gbases_per_s": total_bases / (float(np.mean(rc_ms)) * 1e-3) / 1e9,
+                                "what": "nsmh_query_all(rc=1): reverse-complement pack + sketch + bulk lookup of all reads"}
+        except Exception as e:  # noqa: BLE001
+            line["rc_query"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample ----
     if n_gpus == 1 and not args.no_cpu_baseline:
         from oracle.oracle import Oracle, RefLib
