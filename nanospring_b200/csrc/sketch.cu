@@ -117,7 +117,10 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     if (ev0) NSMH_CK(cudaEventRecord(ev0, s));
     if (mode == 0) {
         // per-device attribute: set on every call (cheap) rather than once per process
-        NSMH_CK(cudaFuncSetAttribute(sketch_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        const char *ev_bal = getenv("NSMH_SKETCH_BALANCED");        // experiment: see sketch_kernels.cuh
+        const bool balanced = ev_bal && *ev_bal && atoi(ev_bal) != 0;
+        auto filter_kernel = balanced ? sketch_filter_kernel<true> : sketch_filter_kernel<false>;
+        NSMH_CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // one block per SM, as many warps as the shared memory holds (each warp owns a tile)
         const FilterSmem L(c->n, a.tile_words);
         const size_t budget = smem_budget;
@@ -125,7 +128,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
             return fail(NSMH_EINVAL, "sketch: n too large for the filter kernel's shared memory");
         int warps = (int)std::min<size_t>(32, (budget - L.tab_bytes) / L.warp_bytes);
         const size_t smem = L.tab_bytes + (size_t)warps * L.warp_bytes;
-        sketch_filter_kernel<<<c->num_sms, warps * 32, smem, s>>>(a);
+        filter_kernel<<<c->num_sms, warps * 32, smem, s>>>(a);
         ++*launches;
         NSMH_CK(cudaGetLastError());
         if (ev1) NSMH_CK(cudaEventRecord(ev1, s));

@@ -168,6 +168,14 @@ struct FilterSmem {
 
 // ---- filter kernel ------------------------------------------------------------------
 // a.tile_words is a multiple of 64: in every step a lane owns two adjacent words = 32 positions.
+//
+// BALANCED = true (experiment, NSMH_SKETCH_BALANCED=1): phase 2 hands every lane the same number of
+// hits.  The lanes' hit counts (known after phase 1) are prefix-summed, lane L takes the hits of ranks
+// [L * ceil(H/32), ...) in lane-major order of the masks, finds its first hit with a binary search over
+// the prefix sums and walks on from there, possibly into the masks of the following lanes.  The minima
+// do not depend on who processes a hit, so the result is the same; what changes is that the warp no
+// longer waits for the lane with the most hits (47 % of the lanes are active in phase 2 today).
+template <bool BALANCED>
 __global__ void __launch_bounds__(1024)
 sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
     NSMH_FILTER_SMEM_DECL
@@ -237,6 +245,7 @@ sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
         phase ^= 1;
 
         // ---- phase 1: 32 positions per lane and step -> hit mask (bit 31-q = position q) ----
+        uint32_t mycnt = 0;
         for (uint32_t it = 0; it < steps; ++it) {
             const uint32_t i0 = it * 64 + 2 * lane;
             const uint2 w01 = *reinterpret_cast<const uint2 *>(sw + i0);
@@ -262,10 +271,11 @@ sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
                 m &= keep_hi & keep_lo;
             }
             own[it * 32 + lane] = m;
+            if (BALANCED) mycnt += __popc(m);
         }
 
         // ---- phase 2: every lane walks its own hits ----
-        {
+        if (!BALANCED) {
             uint32_t c = 0;
             uint32_t m = own[lane];
             for (;;) {
@@ -274,6 +284,60 @@ sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
                 const int q = __clz(m);
                 m &= ~(0x80000000u >> q);
                 const uint32_t wi = c * 64 + 2 * lane + (q >> 4);
+                uint32_t h32;
+                const uint64_t x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], q & 15, kshift, h32);
+                uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)];
+                do {
+                    const ulonglong2 rm = my_min[l];
+                    const uint32_t ln = nxt[l];
+                    const uint64_t y = x ^ rm.x;
+                    if (y < rm.y) atomicMin(&my_min[l].y, (unsigned long long)y);
+                    l = ln;
+                } while (l != 0xFFu);
+            }
+        } else {
+            // ---- phase 2, balanced: the same hits, ceil(H/32) per lane ----
+            __syncwarp();                                       // the masks of all lanes are in place
+            uint32_t incl = mycnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const uint32_t H = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t quota = (H + 31) >> 5;
+            const uint32_t start = (uint32_t)lane * quota;
+            uint32_t mine = start < H ? min(quota, H - start) : 0u;
+            // owner of my first hit = number of lanes whose inclusive count is <= start (incl is monotone)
+            uint32_t ow = 0;
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + s - 1));
+                if (v <= start) ow += s;
+            }
+            const uint32_t prev = __shfl_sync(0xffffffffu, incl, (int)(ow ? ow - 1 : 0));
+            uint32_t skip = start - (ow ? prev : 0u);           // hits of the owner that belong to earlier lanes
+            uint32_t c = 0, m = 0;
+            if (mine) {
+                m = own[ow];
+                while ((uint32_t)__popc(m) <= skip) {           // ends inside the owner's masks: skip < its count
+                    skip -= __popc(m);
+                    ++c;
+                    m = own[c * 32 + ow];
+                }
+                for (; skip; --skip) m &= ~(0x80000000u >> __clz(m));
+            }
+            for (; mine; --mine) {
+                while (m == 0) {                                // a hit of mine is still ahead, in lane-major order
+                    if (++c == steps) {
+                        c = 0;
+                        ++ow;
+                    }
+                    m = own[c * 32 + ow];
+                }
+                const int q = __clz(m);
+                m &= ~(0x80000000u >> q);
+                const uint32_t wi = c * 64 + 2 * ow + (q >> 4);
                 uint32_t h32;
                 const uint64_t x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], q & 15, kshift, h32);
                 uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)];

@@ -17,14 +17,14 @@ using namespace nsmh;
 extern "C" {
 
 // W: packed stream followed by kPackPadWords zero words.  mode 0 = filter kernel + exact fix-up,
-// 1 = brute force.  sk [n_reads][n] out; *fixups = entries the fix-up pass recomputed.  Returns 0,
+// 1 = brute force, 2 = filter kernel with the balanced phase 2 (NSMH_SKETCH_BALANCED) + fix-up.  sk [n_reads][n] out; *fixups = entries the fix-up pass recomputed.  Returns 0,
 // or -1 when the configuration does not fit the filter kernel (n > 255).
 int sketch_emul_run(const uint32_t *W, const uint64_t *off, uint32_t n_reads, uint32_t k, uint32_t n,
                     const uint64_t *rnd, int mode, int lambda_log2, uint32_t tile_words, unsigned grid, uint64_t *sk,
                     unsigned long long *fixups) {
     *fixups = 0;
     if (n_reads == 0) return 0;
-    if (mode == 0 && n > 255) return -1;
+    if (mode != 1 && n > 255) return -1;
     const FilterTables ft = make_filter_tables(rnd, n, k);
     unsigned long long counters[8] = {0};
     SketchArgs a;
@@ -53,12 +53,13 @@ int sketch_emul_run(const uint32_t *W, const uint64_t *off, uint32_t n_reads, ui
     for (uint32_t i = 0; i < n_reads; ++i) ts[i + 1] = ts[i] + cnt[i];
     if (ts[n_reads] > max_tiles) return -2;                                  // the bound sketch_reads allocates by
     emu_launch(grid, 64, [&] { sketch_tile_map_kernel(ts.data(), n_reads, tile_read.data()); });
-    if (mode == 0) {
+    if (mode != 1) {
         const FilterSmem L(n, a.tile_words);
         const size_t bytes = L.tab_bytes + L.warp_bytes;                     // one warp per block
         uint8_t *smem = static_cast<uint8_t *>(aligned_alloc(16, (bytes + 15) & ~(size_t)15));
         memset(smem, 0xA5, bytes);
-        emu_launch(grid, 32, [&] { sketch_filter_kernel(a, smem); });
+        if (mode == 2) emu_launch(grid, 32, [&] { sketch_filter_kernel<true>(a, smem); });
+        else emu_launch(grid, 32, [&] { sketch_filter_kernel<false>(a, smem); });
         free(smem);
         std::vector<uint32_t> miss((size_t)n_reads * n + 1, 0);
         emu_launch(grid, 64, [&] { sketch_missing_kernel(a, miss.data(), queue + 1); });

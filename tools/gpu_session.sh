@@ -25,6 +25,10 @@ SECTION=tests
 if want "$@"; then
     (time timeout 400 python -m pytest tests -m gpu -x -q --durations=10) > "$OUT/pytest_gpu_$TAG.log" 2>&1
     tail -n 3 "$OUT/pytest_gpu_$TAG.log"
+    # experimental kernel variants (default off): parity before any of them is switched on
+    (time NSMH_TEST_EXPERIMENTS=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -k experiment) \
+        > "$OUT/pytest_experiments_$TAG.log" 2>&1
+    tail -n 3 "$OUT/pytest_experiments_$TAG.log"
 fi
 
 SECTION=bench
@@ -65,6 +69,16 @@ fi
 
 SECTION=ab
 if want "$@"; then
+    # filter kernel: default phase 2 vs the balanced one (NSMH_SKETCH_BALANCED), device-resident step only
+    for B in 0 1; do
+        NSMH_SKETCH_BALANCED=$B timeout 120 python bench.py --steps 10 --no-cpu-baseline --no-e2e --no-ingest \
+            > "$OUT/bench_balanced${B}_$TAG.json" 2> "$OUT/bench_balanced${B}_$TAG.err"
+        python - "$OUT/bench_balanced${B}_$TAG.json" <<'PY'
+import json, sys
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+print("balanced", sys.argv[1][-12:], "ms/step", round(d["ms_per_step"], 4), "sketch_main_ms", round(d["phases_last_step"]["sketch_main_kernel_ms"], 4))
+PY
+    done
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
     timeout 120 python tools/ingest_sweep.py --iters 16 32 64 > "$OUT/ingest_sweep_$TAG.jsonl" 2> "$OUT/ingest_sweep_$TAG.err"
     cat "$OUT/mid_tier_ab_$TAG.jsonl" "$OUT/ingest_sweep_$TAG.jsonl"
