@@ -291,6 +291,24 @@ csr_place_kernel(CountArgs a, const uint32_t *__restrict__ mid_ids, const uint64
     }
 }
 
+// The same placement launched BEFORE the host has seen the counters (experiment,
+// NSMH_LOOKUP_SPECULATE=1): a query whose results did not fit tmp_ids, or whose place lies beyond
+// out_ids, is skipped - the host then repeats the placement on the general path.
+__global__ void __launch_bounds__(256)
+csr_place_guarded_kernel(CountArgs a, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids,
+                         uint64_t out_cap) {
+    const uint32_t sub = threadIdx.x & 7;
+    const uint32_t groups = gridDim.x * (blockDim.x >> 3);
+    for (uint32_t q = blockIdx.x * (blockDim.x >> 3) + (threadIdx.x >> 3); q < a.nq; q += groups) {
+        const uint64_t pos = a.qpos[q];
+        if (pos == ~0ULL) continue;
+        const uint32_t cnt = a.qcount[q];
+        const uint64_t dst0 = out_off[q];
+        if (pos + cnt > a.tmp_cap || dst0 + cnt > out_cap) continue;
+        for (uint32_t i = sub; i < cnt; i += 8) out_ids[dst0 + i] = a.tmp_ids[pos + i];
+    }
+}
+
 // ---------------------------------------------------------------- counting-filter tier --
 // query_mid.cuh: a warp per query that overflowed the warp buffer; exact, no global sort.
 template <typename Src>
@@ -370,6 +388,12 @@ heavy_copy_kernel(const uint32_t *__restrict__ heavy_list, uint32_t nh, const ui
 static bool mid_tier_enabled() {
     const char *e = getenv("NSMH_MID_TIER");
     return e && *e ? atoi(e) != 0 : kMidTierDefault;
+}
+
+// NSMH_LOOKUP_SPECULATE=1: see count_and_emit (experiment, off by default)
+static bool speculate_enabled() {
+    const char *e = getenv("NSMH_LOOKUP_SPECULATE");
+    return e && *e && atoi(e) != 0;
 }
 
 static int grid_for(uint64_t items, int sms, int per_block = 256) {
@@ -499,6 +523,16 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     const int blocks = (int)std::min<uint64_t>(((uint64_t)nq + kLookupWarps - 1) / kLookupWarps,
                                                (uint64_t)c->num_sms * (occ > 0 ? occ : 1));
     unsigned long long cnt[3] = {0, 0, 0};
+    // Experiment (NSMH_LOOKUP_SPECULATE=1): prefix sum and placement are queued right behind the counting
+    // kernel, before the host knows whether a query overflowed; when none did and the results fit
+    // (the common case) the single read-back below is the only host round trip of the lookup.
+    const bool speculate = speculate_enabled();
+    size_t spec_tmp_bytes = 0;
+    if (speculate) {
+        NSMH_TRY(ws.out_ids.ensure(ws.tmp_ids.cap, s));
+        NSMH_CK(cub_exclusive_sum_u32_to_u64(nullptr, spec_tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
+        NSMH_TRY(ws.cub_tmp.ensure(spec_tmp_bytes, s));
+    }
     for (int attempt = 0; attempt < 2; ++attempt) {
         a.tmp_ids = ws.tmp_ids.as<uint32_t>();
         a.tmp_cap = ws.tmp_ids.cap / sizeof(uint32_t);
@@ -507,8 +541,23 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
         count_kernel<Src><<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
         ++ws.launches;
         NSMH_CK(cudaGetLastError());
+        uint64_t spec_total = 0;
+        if (speculate && attempt == 0) {
+            NSMH_CK(cub_exclusive_sum_u32_to_u64(ws.cub_tmp.p, spec_tmp_bytes, ws.qcount.as<uint32_t>(), ws.out_off.as<uint64_t>(), (size_t)nq + 1, s));
+            csr_place_guarded_kernel<<<grid_for((uint64_t)nq * 8, c->num_sms), 256, 0, s>>>(
+                a, ws.out_off.as<uint64_t>(), ws.out_ids.as<uint32_t>(), ws.out_ids.cap / sizeof(uint32_t));
+            NSMH_CK(cudaGetLastError());
+            ws.launches += 3;
+            NSMH_CK(cudaMemcpyAsync(&spec_total, ws.out_off.as<uint64_t>() + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        }
         NSMH_CK(cudaMemcpyAsync(cnt, ws.counters.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
         NSMH_CK(cudaStreamSynchronize(s));
+        if (speculate && attempt == 0 && cnt[0] == 0 && cnt[2] <= a.tmp_cap &&
+            spec_total <= ws.out_ids.cap / sizeof(uint32_t)) {
+            ws.last_pairs = cnt[1];
+            ws.last_total = spec_total;          // == cnt[2]: nothing was skipped by the guards
+            return NSMH_OK;
+        }
         if (cnt[2] <= a.tmp_cap) break;
         NSMH_TRY(ws.tmp_ids.ensure((size_t)cnt[2] * sizeof(uint32_t), s));
     }

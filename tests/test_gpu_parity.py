@@ -455,3 +455,36 @@ def test_experiment_balanced_phase2_of_the_filter_kernel(orc, edge, monkeypatch,
             fix[bal] = f.stats()["sketch_fixups"]
             f.close()
         assert fix["0"] == fix["1"]
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("NSMH_TEST_EXPERIMENTS"),
+                    reason="experimental host flow: set NSMH_TEST_EXPERIMENTS=1 (tools/gpu_session.sh does)")
+def test_experiment_speculative_placement_of_the_lookup(orc, edge, monkeypatch):
+    """NSMH_LOOKUP_SPECULATE=1 (query.cu: prefix sum + guarded placement queued behind the counting kernel,
+    one host round trip when no query overflows): same CSR as the oracle on inputs that take the fast
+    exit, the result-buffer overflow (dozens of results per query), the counting-filter tier and the
+    global sort; bulk and online queries."""
+    monkeypatch.setenv("NSMH_LOOKUP_SPECULATE", "1")
+    cases = []
+    lengths = ns.synth_lengths(1200, 900, seed=15)
+    cases.append((ns.synth_reads_host(lengths, ns.synth_params(genome_len=12_000, genome_seed=4, read_seed=5,
+                                                               p_ins=0.0, p_del=0.0, p_sub=0.005)), 15, 24, (1, 2, 5)))
+    lengths = ns.synth_lengths(3000, 1500, seed=21)
+    cases.append((ns.synth_reads_host(lengths, ns.synth_params(genome_len=300_000, genome_seed=5, read_seed=6)), 8, 60, (1, 6)))
+    cases.append((ReadData(edge["bases"], edge["offsets"]), 23, 60, (6,)))
+    lengths = ns.synth_lengths(2000, 2500, seed=1)
+    cases.append((ns.synth_reads_host(lengths, ns.synth_params(genome_len=150_000)), 23, 60, (6,)))     # fast exit
+    for rd, k, n, thrs in cases:
+        rnd = ns.rand_from_seed(k + n, n)
+        want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+        T = orc.build_tables(want)
+        for thr in thrs:
+            f = make_filter(k, n, thr, rnd)
+            f.initialize(rd)
+            for rc in (False, True):
+                assert_csr_equal(f.queryAll(rc), T.query_all(rd.bases, rd.offsets, want, k, rnd, thr, int(rc)),
+                                 f"k {k} n {n} thr {thr} rc {rc}")
+            for i in (0, 7, rd.numReads - 1):
+                q = rd.getRead(i)
+                assert (f.getFilteredReads(q) == T.query_string(q, k, rnd, thr)).all()
+            f.close()

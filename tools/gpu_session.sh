@@ -19,10 +19,11 @@ cd "$(dirname "$0")/.."
 OUT=gpurun_out
 mkdir -p "$OUT"
 TAG=${TAG:-$(date +%H%M)}
-want() { [[ " $* " == *" all "* ]] || [[ " $* " == *" $SECTION "* ]]; }
+ARGS=" $* "
+want() { [[ "$ARGS" == *" all "* ]] || [[ "$ARGS" == *" $SECTION "* ]]; }
 
 SECTION=tests
-if want "$@"; then
+if want; then
     (time timeout 400 python -m pytest tests -m gpu -x -q --durations=10) > "$OUT/pytest_gpu_$TAG.log" 2>&1
     tail -n 3 "$OUT/pytest_gpu_$TAG.log"
     # experimental kernel variants (default off): parity before any of them is switched on
@@ -32,14 +33,14 @@ if want "$@"; then
 fi
 
 SECTION=bench
-if want "$@"; then
+if want; then
     timeout 300 python bench.py > "$OUT/bench_$TAG.json" 2> "$OUT/bench_$TAG.err"
     timeout 200 python bench.py --impl reference > "$OUT/bench_reference_$TAG.json" 2>> "$OUT/bench_$TAG.err"
     cut -c1-400 "$OUT/bench_$TAG.json"
 fi
 
 SECTION=launch
-if want "$@"; then
+if want; then
     timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
         --log-file "$OUT/launches_$TAG.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
         > "$OUT/bench_under_ncu_$TAG.log" 2>&1
@@ -47,7 +48,7 @@ if want "$@"; then
 fi
 
 SECTION=ncu
-if want "$@"; then
+if want; then
     # -s skips the warm-up launches of each kernel, -c 1 captures one launch; ~40 replays each
     for K in sketch_filter_kernel table_insert_kernel count_kernel pack_ascii_kernel sketch_fixup_kernel; do
         timeout 200 ncu --set full --clock-control none --import-source on -k "regex:$K" -s 3 -c 1 \
@@ -62,21 +63,24 @@ if want "$@"; then
 fi
 
 SECTION=sweep
-if want "$@"; then
+if want; then
     timeout 600 python tests/config_sweep.py --out "$OUT/config_sweep_$TAG.jsonl" > "$OUT/config_sweep_$TAG.log" 2>&1
     tail -n 3 "$OUT/config_sweep_$TAG.log"
 fi
 
 SECTION=ab
-if want "$@"; then
+if want; then
     # filter kernel: default phase 2 vs the balanced one (NSMH_SKETCH_BALANCED), device-resident step only
-    for B in 0 1; do
-        NSMH_SKETCH_BALANCED=$B timeout 120 python bench.py --steps 10 --no-cpu-baseline --no-e2e --no-ingest \
-            > "$OUT/bench_balanced${B}_$TAG.json" 2> "$OUT/bench_balanced${B}_$TAG.err"
-        python - "$OUT/bench_balanced${B}_$TAG.json" <<'PY'
+    # ... and the lookup with / without the speculative placement (NSMH_LOOKUP_SPECULATE)
+    for V in "0 0" "1 0" "0 1" "1 1"; do
+        set -- $V
+        NSMH_SKETCH_BALANCED=$1 NSMH_LOOKUP_SPECULATE=$2 timeout 120 python bench.py --steps 10 --no-cpu-baseline \
+            --no-e2e --no-ingest > "$OUT/bench_bal$1_spec$2_$TAG.json" 2> "$OUT/bench_bal$1_spec$2_$TAG.err"
+        python - "$OUT/bench_bal$1_spec$2_$TAG.json" "$1" "$2" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-print("balanced", sys.argv[1][-12:], "ms/step", round(d["ms_per_step"], 4), "sketch_main_ms", round(d["phases_last_step"]["sketch_main_kernel_ms"], 4))
+p = d["phases_last_step"]
+print(f"balanced={sys.argv[2]} speculate={sys.argv[3]}: ms/step {d['ms_per_step']:.4f}  sketch_main {p['sketch_main_kernel_ms']:.4f}  query {p['query_ms']:.4f}")
 PY
     done
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
@@ -85,7 +89,7 @@ PY
 fi
 
 SECTION=peer
-if want "$@"; then
+if want; then
     export NSMH_MG_TIMEOUT_MS=60000
     for W in 4 8; do
         (time timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $W --master-addr 127.0.0.1 \
