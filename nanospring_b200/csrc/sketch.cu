@@ -135,7 +135,9 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         uint32_t *miss_list = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(cub_tmp.p) + list_off);
         unsigned int *miss_count = a.tile_queue + 1;
         sketch_missing_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
-        sketch_fixup_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+        const char *ev_fw = getenv("NSMH_FIXUP_WIDTH");            // experiment: see sketch_kernels.cuh
+        if (ev_fw && atoi(ev_fw) == 8) sketch_fixup_kernel<8><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+        else sketch_fixup_kernel<4><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
         *launches += 2;
         NSMH_CK(cudaGetLastError());
     } else {

@@ -403,6 +403,9 @@ __device__ __forceinline__ uint64_t word_min64(const uint32_t *__restrict__ W, u
 // remembers the word of its own minimum; the winning words are then redone in 64 bits.  If a
 // lane saw its minimum in two different words (a 32-bit tie, probability ~2^-32 per pair) the
 // entry falls back to a plain 64-bit scan, so the result is exact in every case.
+// U = words per lane and step (4 by default; NSMH_FIXUP_WIDTH=8 is an experiment: half as many
+// dependent L2 round trips for the long reads that make up the kernel's tail).
+template <int U>
 __global__ void __launch_bounds__(256)
 sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ count) {
     const int lane = threadIdx.x & 31;
@@ -428,18 +431,18 @@ sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsig
         uint32_t m = 0xFFFFFFFFu;
         uint64_t mw = 0;
         bool has = false, tie = false;
-        // four words per lane and step, all loads first: the scan is a chain of L2 round trips
-        for (uint64_t wb = g.w_begin + lane; wb < g.w_end; wb += 128) {
-            uint32_t w0[4], w1[4];
+        // U words per lane and step, all loads first: the scan is a chain of L2 round trips
+        for (uint64_t wb = g.w_begin + lane; wb < g.w_end; wb += 32 * U) {
+            uint32_t w0[U], w1[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const uint64_t w = wb + 32 * u;
                 const bool in = w < g.w_end;
                 w0[u] = in ? __ldg(a.W + w) : 0u;
                 w1[u] = in ? __ldg(a.W + w + 1) : 0u;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const uint64_t w = wb + 32 * u;
                 if (w >= g.w_end) break;
                 int lo, hi;

@@ -435,10 +435,12 @@ def test_counting_filter_tier_small_k(orc, monkeypatch, thr):
 
 @pytest.mark.skipif(not __import__("os").environ.get("NSMH_TEST_EXPERIMENTS"),
                     reason="experimental kernel variants: set NSMH_TEST_EXPERIMENTS=1 (tools/gpu_session.sh does)")
+@pytest.mark.parametrize("var,val", [("NSMH_SKETCH_BALANCED", "1"), ("NSMH_FIXUP_WIDTH", "8")])
 @pytest.mark.parametrize("k,n", [(23, 60), (15, 30), (31, 120), (9, 33)])
-def test_experiment_balanced_phase2_of_the_filter_kernel(orc, edge, monkeypatch, k, n):
-    """NSMH_SKETCH_BALANCED=1 (sketch_kernels.cuh: every lane takes the same number of hits in phase 2):
-    same sketch matrix as the oracle and as the default kernel, same number of fix-ups."""
+def test_experiment_sketch_kernel_variants(orc, edge, monkeypatch, k, n, var, val):
+    """NSMH_SKETCH_BALANCED=1 (sketch_kernels.cuh: every lane takes the same number of hits in phase 2) and
+    NSMH_FIXUP_WIDTH=8 (8 words per lane and step in the fix-up scan): same sketch matrix as the oracle
+    and as the default kernels, same number of fix-ups."""
     rnd = ns.rand_from_seed(k * n, n)
     lengths = ns.synth_lengths(1500, 3000, seed=k)
     lengths[:8] = [0, 1, k - 1, k, k + 1, 40, 70000, 33]
@@ -447,14 +449,14 @@ def test_experiment_balanced_phase2_of_the_filter_kernel(orc, edge, monkeypatch,
     for s in sets:
         want = orc.sketch_all(s.bases, s.offsets, k, n, rnd)
         fix = {}
-        for bal in ("0", "1"):
-            monkeypatch.setenv("NSMH_SKETCH_BALANCED", bal)
+        for setting in ("0", val):
+            monkeypatch.setenv(var, setting)
             f = make_filter(k, n, 3, rnd)
             f.initialize(s)
-            assert (f.sketches() == want).all(), f"balanced={bal}"
-            fix[bal] = f.stats()["sketch_fixups"]
+            assert (f.sketches() == want).all(), f"{var}={setting}"
+            fix[setting] = f.stats()["sketch_fixups"]
             f.close()
-        assert fix["0"] == fix["1"]
+        assert fix["0"] == fix[val]
 
 
 @pytest.mark.skipif(not __import__("os").environ.get("NSMH_TEST_EXPERIMENTS"),

@@ -71,16 +71,18 @@ fi
 SECTION=ab
 if want; then
     # filter kernel: default phase 2 vs the balanced one (NSMH_SKETCH_BALANCED), device-resident step only
-    # ... and the lookup with / without the speculative placement (NSMH_LOOKUP_SPECULATE)
-    for V in "0 0" "1 0" "0 1" "1 1"; do
+    # ... the lookup with / without the speculative placement (NSMH_LOOKUP_SPECULATE), the fix-up scan with
+    # 4 / 8 words per lane and step (NSMH_FIXUP_WIDTH); last line: all three together
+    for V in "0 0 4" "1 0 4" "0 1 4" "0 0 8" "1 1 8"; do
         set -- $V
-        NSMH_SKETCH_BALANCED=$1 NSMH_LOOKUP_SPECULATE=$2 timeout 120 python bench.py --steps 10 --no-cpu-baseline \
-            --no-e2e --no-ingest > "$OUT/bench_bal$1_spec$2_$TAG.json" 2> "$OUT/bench_bal$1_spec$2_$TAG.err"
-        python - "$OUT/bench_bal$1_spec$2_$TAG.json" "$1" "$2" <<'PY'
+        NSMH_SKETCH_BALANCED=$1 NSMH_LOOKUP_SPECULATE=$2 NSMH_FIXUP_WIDTH=$3 timeout 120 python bench.py --steps 10 \
+            --no-cpu-baseline --no-e2e --no-ingest > "$OUT/bench_bal$1_spec$2_fix$3_$TAG.json" 2> "$OUT/bench_bal$1_spec$2_fix$3_$TAG.err"
+        python - "$OUT/bench_bal$1_spec$2_fix$3_$TAG.json" "$1" "$2" "$3" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 p = d["phases_last_step"]
-print(f"balanced={sys.argv[2]} speculate={sys.argv[3]}: ms/step {d['ms_per_step']:.4f}  sketch_main {p['sketch_main_kernel_ms']:.4f}  query {p['query_ms']:.4f}")
+print(f"balanced={sys.argv[2]} speculate={sys.argv[3]} fixup_width={sys.argv[4]}: ms/step {d['ms_per_step']:.4f}  "
+      f"sketch {p['sketch_ms']:.4f} (main kernel {p['sketch_main_kernel_ms']:.4f})  query {p['query_ms']:.4f}")
 PY
     done
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
