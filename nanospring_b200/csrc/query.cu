@@ -23,7 +23,7 @@
 #include <cstdlib>
 
 #include "nsmh_internal.cuh"
-#include "query_mid.cuh"
+#include "query_kernels.cuh"
 
 namespace nsmh {
 
@@ -267,7 +267,7 @@ struct PeerSrc {
     __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
 };
 
-// count_kernel: query_mid.cuh (count_body) - one warp per query, one pass
+// count_kernel: query_kernels.cuh (count_body) - one warp per query, one pass
 template <typename Src>
 __global__ void __launch_bounds__(kLookupWarps * 32)
 count_kernel(Src src, CountArgs a) {
@@ -310,7 +310,7 @@ csr_place_guarded_kernel(CountArgs a, const uint64_t *__restrict__ out_off, uint
 }
 
 // ---------------------------------------------------------------- counting-filter tier --
-// query_mid.cuh: a warp per query that overflowed the warp buffer; exact, no global sort.
+// query_kernels.cuh: a warp per query that overflowed the warp buffer; exact, no global sort.
 template <typename Src>
 __global__ void __launch_bounds__(kMidWarps * 32)
 mid_count_kernel(Src src, MidArgs m) {
@@ -569,7 +569,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     NSMH_TRY(ws.out_ids.ensure((size_t)std::max<uint64_t>(cnt[1], 1) * sizeof(uint32_t), s));
     if (nh && mid_tier_enabled()) {
         // counting-filter tier: resolves the heavy queries that have few ids above the threshold
-        // (query_mid.cuh); what it cannot resolve goes on to the global sort.  A result needs thr
+        // (query_kernels.cuh); what it cannot resolve goes on to the global sort.  A result needs thr
         // gathered ids, so cnt[1] / thr bounds what all queries together can emit.
         MidArgs m;
         m.mid_cap = cnt[1] / a.thr + 1;

@@ -3,7 +3,7 @@
 // larger queries) and the "counting filter" tier for queries whose gathered id lists do not fit the
 // warp-private sort buffer (kLookupCap ids).  Everything here is warp-level and templated on the
 // source of the id lists, and the file is kept free of runtime-API includes, so that
-// tests/cpp/query_mid_host_emul.cpp can compile the SAME code for the host
+// tests/cpp/query_host_emul.cpp can compile the SAME code for the host
 // (tests/cpp/cuda_host_shim.h, lock-step warp emulation) with lists given as a CSR and check it
 // against a plain sort-and-count without a GPU.
 //
@@ -310,7 +310,7 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
                 continue;
             }
             // ids whose counting-filter bucket stays below the threshold cannot qualify: drop them
-            // before sorting (query_mid.cuh; `res` is unused on this path and holds the counters)
+            // before sorting (query_kernels.cuh; `res` is unused on this path and holds the counters)
             uint32_t Ts = T;
             if (a.thr > 1 && T > 64) {
                 __syncwarp();

@@ -2,7 +2,7 @@
 // for the HOST and run it in lock step: every lane of a warp is an OS thread, warp collectives
 // (__shfl_*_sync, __ballot_sync, __reduce_add_sync, __syncwarp) meet on a barrier.  One warp runs at a time, so only
 // warp-level code can be emulated (no __syncthreads; "shared memory" is a warp-private buffer the
-// harness passes in) - which is all that csrc/fastq_kernels.cuh and csrc/query_mid.cuh contain.
+// harness passes in) - which is all that csrc/fastq_kernels.cuh and csrc/query_kernels.cuh contain.
 #pragma once
 #include <stdint.h>
 

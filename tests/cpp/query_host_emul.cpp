@@ -1,11 +1,11 @@
 // TEST INFRASTRUCTURE ONLY.  Runs the counting-filter tier of the candidate lookup
-// (nanospring_b200/csrc/query_mid.cuh: mid_count_body, the code mid_count_kernel in query.cu wraps)
-// on the host with cuda_host_shim.h, over id lists given as a CSR.  tests/test_query_mid_emul.py
+// (nanospring_b200/csrc/query_kernels.cuh: mid_count_body, the code mid_count_kernel in query.cu wraps)
+// on the host with cuda_host_shim.h, over id lists given as a CSR.  tests/test_query_emul.py
 // compares the outcome with a plain sort-and-count (what ReadFilter.cpp:65-83 does); a logic check
 // for the container without a GPU, never a product path.
 #include "cuda_host_shim.h"
 
-#include "../../nanospring_b200/csrc/query_mid.cuh"
+#include "../../nanospring_b200/csrc/query_kernels.cuh"
 
 using namespace nsmh;
 

@@ -2,7 +2,7 @@
 // nanospring_b200/csrc/table_kernels.cuh on the host (cuda_host_shim.h; whole 256-thread blocks run
 // concurrently as OS threads, NSMH_HOST_EMUL swaps the three PTX accesses for host atomics) in the
 // order build_tables (table.cu) launches them, then probes them with the lookup kernel's body
-// (query_mid.cuh: count_body<ProbeSrc>).  tests/test_table_emul.py compares key counts and candidate
+// (query_kernels.cuh: count_body<ProbeSrc>).  tests/test_table_emul.py compares key counts and candidate
 // lists with the oracle; a logic check for the container without a GPU, never a product path.
 #define NSMH_HOST_EMUL 1
 #include "cuda_host_shim.h"
@@ -11,7 +11,7 @@
 #include <cstring>
 
 #include "../../nanospring_b200/csrc/table_kernels.cuh"
-#include "../../nanospring_b200/csrc/query_mid.cuh"
+#include "../../nanospring_b200/csrc/query_kernels.cuh"
 
 using namespace nsmh;
 
@@ -76,7 +76,7 @@ uint32_t table_emul_num_keys(uint32_t j) {
 }
 
 // nq query sketches [nq][n] against the tables through the lookup kernel's body.  Outputs as in
-// count_emul_run (query_mid_host_emul.cpp); counters [3] zeroed by the caller.
+// count_emul_run (query_host_emul.cpp); counters [3] zeroed by the caller.
 void table_emul_query(const uint64_t *qsk, uint32_t nq, uint32_t thr, unsigned grid, uint32_t *qcount, uint64_t *qpos,
                       uint32_t *tmp_ids, uint64_t tmp_cap, uint32_t *heavy_list, unsigned long long *counters) {
     ProbeSrc src;

@@ -401,7 +401,7 @@ def test_rebuild_and_requery_same_handle(orc):
 def test_counting_filter_tier_small_k(orc, monkeypatch, thr):
     """k = 8: every table group holds tens of reads that share a sketch value by chance, so most
     queries gather 1000..3000 ids (more than the warp's sort buffer) of which a handful reach the
-    threshold.  The counting-filter tier (csrc/query_mid.cuh) resolves them without the global sort;
+    threshold.  The counting-filter tier (csrc/query_kernels.cuh) resolves them without the global sort;
     with thr = 1 every id survives the filter and the queries are handed on.  Same CSR as the oracle
     and as the run with the tier switched off."""
     k, n = 8, 60

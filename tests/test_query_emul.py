@@ -1,4 +1,4 @@
-"""The counting-filter tier of the candidate lookup (nanospring_b200/csrc/query_mid.cuh) compiled for
+"""The counting-filter tier of the candidate lookup (nanospring_b200/csrc/query_kernels.cuh) compiled for
 the HOST and run in lock step (tests/cpp/cuda_host_shim.h), compared with a plain sort-and-count of
 the gathered ids - the definition in ReadFilter.cpp:65-83.  A logic check of the device code for the
 container without a GPU; the GPU parity proper is tests/test_gpu_parity.py."""
@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "oracle", "libquery_mid_emul.so")
+SO = os.path.join(ROOT, "oracle", "libquery_emul.so")
 u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 
 

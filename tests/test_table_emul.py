@@ -1,5 +1,5 @@
 """The table build (nanospring_b200/csrc/table_kernels.cuh: insert with one 128-bit compare-and-swap per
-new key, group ranges, member fill) and the probing lookup (csrc/query_mid.cuh: count_body<ProbeSrc>)
+new key, group ranges, member fill) and the probing lookup (csrc/query_kernels.cuh: count_body<ProbeSrc>)
 compiled for the HOST and run as real concurrent threads (tests/cpp/cuda_host_shim.h, whole 256-thread
 blocks), compared with the oracle's dictionary (BBHashMap semantics: exact key -> list of read ids,
 BBHashMap.cpp:10-120) and candidate lists (ReadFilter.cpp:65-83).  A logic check of the device code for

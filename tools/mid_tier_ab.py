@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A/B of the candidate lookup on BASELINE config C4's small-k corner (1 M reads, ~10 Gbases, k=15):
-bulk forward lookup with the counting-filter tier (csrc/query_mid.cuh) and with every overflowing
+bulk forward lookup with the counting-filter tier (csrc/query_kernels.cuh) and with every overflowing
 query sent to the global radix sort (NSMH_MID_TIER=0).  Prints one JSON line per run; the CSRs of
 the two runs must be identical (same offsets, same ids).
 
