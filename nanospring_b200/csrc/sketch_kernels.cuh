@@ -243,6 +243,7 @@ sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
         const uint32_t steps = (nw + 63) / 64;
         while (!mbar_try_wait(bar, phase)) { }
         phase ^= 1;
+        __syncwarp();       // the minima initialised above by their owner lanes are read and updated by any lane in phase 2
 
         // ---- phase 1: 32 positions per lane and step -> hit mask (bit 31-q = position q) ----
         uint32_t mycnt = 0;

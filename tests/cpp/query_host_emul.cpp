@@ -3,6 +3,7 @@
 // on the host with cuda_host_shim.h, over id lists given as a CSR.  tests/test_query_emul.py
 // compares the outcome with a plain sort-and-count (what ReadFilter.cpp:65-83 does); a logic check
 // for the container without a GPU, never a product path.
+#define NSMH_HOST_EMUL 1
 #include "cuda_host_shim.h"
 
 #include "../../nanospring_b200/csrc/query_kernels.cuh"
