@@ -309,12 +309,13 @@ int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offs
     // Double-buffered chunks: H2D of chunk i+1 on the copy stream overlaps the pack of chunk i.
     const uint64_t chunk = 64ULL << 20;   // bases per chunk, multiple of 16
     DevBuf stage[2];
-    cudaEvent_t copied[2], packed[2];
-    for (int i = 0; i < 2; ++i) {
-        NSMH_CK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
-        NSMH_CK(cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming));
-    }
+    cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
     int rc = NSMH_OK;
+    for (int i = 0; i < 2 && !rc; ++i) {
+        cudaError_t ee;
+        if ((ee = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(ee, "event", __FILE__, __LINE__);
+        else if ((ee = cudaEventCreateWithFlags(&packed[i], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(ee, "event", __FILE__, __LINE__);
+    }
     const size_t stage_bytes = (size_t)std::min<uint64_t>(chunk, total ? total : 1) + 16;
     for (int i = 0; i < 2 && !rc; ++i) rc = stage[i].ensure(stage_bytes, c->stream);
     if (!rc && cudaEventRecord(packed[0], c->stream) != cudaSuccess) rc = NSMH_ECUDA;
@@ -335,10 +336,15 @@ int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offs
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
     }
+    if (rc) {   // a copy may still be writing into a staging buffer: let it finish before the buffers go
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        cudaGetLastError();
+    }
     for (int i = 0; i < 2; ++i) {
         stage[i].release(c->stream);
-        cudaEventDestroy(copied[i]);
-        cudaEventDestroy(packed[i]);
+        if (copied[i]) cudaEventDestroy(copied[i]);
+        if (packed[i]) cudaEventDestroy(packed[i]);
     }
     if (rc) return rc;
     c->stats.h2d_pack_ms = elapsed(c->ev[0], c->ev[1]);
