@@ -919,7 +919,7 @@ int nsmh_get_stats(nsmh_handle c, nsmh_stats *out) {
     CTX_GUARD(c);
     if (!out) return fail(NSMH_EINVAL, "get_stats: null output");
     NSMH_CK(cudaStreamSynchronize(c->stream));
-    if (c->reads_loaded) c->stats.pack_ms = c->stats.pack_ms;   // device-resident loads: see below
+    // device-resident loads return before the pack kernel has run: its events are read here
     if (c->reads.external_offsets && c->reads_loaded) c->stats.pack_ms = elapsed(c->ev[0], c->ev[1]);
     if (c->sketched) {
         c->stats.sketch_ms = elapsed(c->ev[2], c->ev[3]);
