@@ -459,6 +459,12 @@ def main():
     # the reference's operation count on the INT32 pipe: (6n+6) lane-ops per base
     int_ops = total_bases * (6 * NHASH + 6)
     int_peak = 148 * 64 * sm_max * 1e6          # ALU pipe: 16 lanes/clk/SMSP (B300_MICROARCH rt_SMSP=2)
+    int_measured = None                         # tools/micro/int_roof on a B200, when a copy has been committed
+    try:
+        with open(os.path.join(ROOT, "profiles", "int_roof.json")) as fh:
+            int_measured = json.loads(fh.read().strip().splitlines()[-1])
+    except (OSError, ValueError, IndexError):
+        pass
     dominant = "sketch_filter_kernel" if args.sketch_mode == 0 else "sketch_brute_kernel"
     if args.sketch_mode == 0 and os.environ.get("NSMH_SKETCH_BALANCED", "0") not in ("", "0"):
         dominant = "sketch_filter_kernel<balanced>"      # experiment: the recorded ncu figures do not apply
@@ -477,6 +483,9 @@ def main():
                 "int32_reference_count": {"lane_ops_per_base": 6 * NHASH + 6,
                                           "achieved_tops": int_ops / (sk_ms * 1e-3) / 1e12 if sk_ms > 0 else None,
                                           "nominal_alu_peak_tops": int_peak / 1e12,
+                                          "measured_xormin64_lane_tops": (int_measured or {}).get("xormin64_lane_tops_survey_count"),
+                                          "frac_of_measured": ((int_ops / (sk_ms * 1e-3) / 1e12) / int_measured["xormin64_lane_tops_survey_count"]
+                                                               if int_measured and sk_ms > 0 and int_measured.get("xormin64_lane_tops_survey_count") else None),
                                           "frac": (int_ops / (sk_ms * 1e-3)) / int_peak if sk_ms > 0 else None,
                                           "note": "filter kernel skips most (k-mer,hash) pairs exactly; >1 means faster than the brute-force INT32 roof"}}
 

@@ -13,6 +13,8 @@
 #           sweep   BASELINE configs at full size with their parity checks (tests/config_sweep.py)
 #           ab      small-k lookup A/B (tools/mid_tier_ab.py) and the FASTQ-ingest kernels (tools/ingest_sweep.py)
 #           peer    the peer-memory multi-rank path with 4 and 8 ranks sharing one device
+#           micro   tools/micro: the integer roof (int_roof -> copy to profiles/int_roof.json, bench.py reads it)
+#                   and the random-slot atomics benchmark
 # No number printed by a run under ncu is a bench value.
 set -u
 cd "$(dirname "$0")/.."
@@ -88,6 +90,13 @@ PY
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
     timeout 120 python tools/ingest_sweep.py --iters 16 32 64 > "$OUT/ingest_sweep_$TAG.jsonl" 2> "$OUT/ingest_sweep_$TAG.err"
     cat "$OUT/mid_tier_ab_$TAG.jsonl" "$OUT/ingest_sweep_$TAG.jsonl"
+fi
+
+SECTION=micro
+if want; then
+    timeout 120 tools/micro/int_roof > "$OUT/int_roof_$TAG.json" 2> "$OUT/int_roof_$TAG.err"
+    cat "$OUT/int_roof_$TAG.json"
+    timeout 120 tools/micro/atom_bench > "$OUT/atom_bench_$TAG.txt" 2>&1
 fi
 
 SECTION=peer
