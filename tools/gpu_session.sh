@@ -74,17 +74,20 @@ SECTION=ab
 if want; then
     # filter kernel: default phase 2 vs the balanced one (NSMH_SKETCH_BALANCED), device-resident step only
     # ... the lookup with / without the speculative placement (NSMH_LOOKUP_SPECULATE), the fix-up scan with
-    # 4 / 8 words per lane and step (NSMH_FIXUP_WIDTH); last line: all three together
-    for V in "0 0 4" "1 0 4" "0 1 4" "0 0 8" "1 1 8"; do
+    # 4 / 8 words per lane and step (NSMH_FIXUP_WIDTH), the filter density (NSMH_LAMBDA_LOG2: a cheaper
+    # phase 2 moves the optimum towards fewer fix-ups); last line: everything together
+    for V in "0 0 4 2" "1 0 4 2" "0 1 4 2" "0 0 8 2" "0 0 4 3" "1 0 4 3" "1 1 4 3"; do
         set -- $V
-        NSMH_SKETCH_BALANCED=$1 NSMH_LOOKUP_SPECULATE=$2 NSMH_FIXUP_WIDTH=$3 timeout 120 python bench.py --steps 10 \
-            --no-cpu-baseline --no-e2e --no-ingest > "$OUT/bench_bal$1_spec$2_fix$3_$TAG.json" 2> "$OUT/bench_bal$1_spec$2_fix$3_$TAG.err"
-        python - "$OUT/bench_bal$1_spec$2_fix$3_$TAG.json" "$1" "$2" "$3" <<'PY'
+        NSMH_SKETCH_BALANCED=$1 NSMH_LOOKUP_SPECULATE=$2 NSMH_FIXUP_WIDTH=$3 NSMH_LAMBDA_LOG2=$4 timeout 120 python bench.py \
+            --steps 10 --no-cpu-baseline --no-e2e --no-ingest > "$OUT/bench_bal$1_spec$2_fix$3_lam$4_$TAG.json" \
+            2> "$OUT/bench_bal$1_spec$2_fix$3_lam$4_$TAG.err"
+        python - "$OUT/bench_bal$1_spec$2_fix$3_lam$4_$TAG.json" "$1" "$2" "$3" "$4" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 p = d["phases_last_step"]
-print(f"balanced={sys.argv[2]} speculate={sys.argv[3]} fixup_width={sys.argv[4]}: ms/step {d['ms_per_step']:.4f}  "
-      f"sketch {p['sketch_ms']:.4f} (main kernel {p['sketch_main_kernel_ms']:.4f})  query {p['query_ms']:.4f}")
+print(f"balanced={sys.argv[2]} speculate={sys.argv[3]} fixup_width={sys.argv[4]} lambda_log2={sys.argv[5]}: "
+      f"ms/step {d['ms_per_step']:.4f}  sketch {p['sketch_ms']:.4f} (main kernel {p['sketch_main_kernel_ms']:.4f})  "
+      f"query {p['query_ms']:.4f}")
 PY
     done
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
