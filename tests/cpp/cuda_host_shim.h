@@ -1,10 +1,14 @@
-// TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile a kernel header
-// for the HOST and run it in lock step: every lane of a warp is an OS thread, warp collectives
-// (__shfl_*_sync, __ballot_sync, __reduce_add_sync, __syncwarp) meet on a barrier.  One warp runs at a time, so only
-// warp-level code can be emulated (no __syncthreads; "shared memory" is a warp-private buffer the
-// harness passes in) - which is all that csrc/fastq_kernels.cuh and csrc/query_kernels.cuh contain.
+// TEST INFRASTRUCTURE ONLY.  Just enough of the CUDA device vocabulary to compile the kernel headers
+// of nanospring_b200/csrc (*_kernels.cuh) for the HOST and run them with real threads: every lane of
+// a warp is an OS thread, warp collectives (__shfl_*_sync, __ballot_sync, __any/__all_sync,
+// __reduce_add_sync, __syncwarp) meet on a barrier, atomics are host atomics.
+//   emu_launch        one warp at a time: for warp-level kernels ("shared memory" is a buffer the harness
+//                     passes in; __syncthreads is only meaningful with one warp per block)
+//   emu_launch_block  all warps of a block alive at once: __syncthreads is a block barrier, `__shared__`
+//                     variables are function-local statics (blocks run one after the other)
 // All state is `inline` (one instance per program or shared library), so several harnesses can be
-// linked into one executable (tests/cpp/tsan_driver.cpp) as well as loaded as separate libraries.
+// linked into one executable (tests/cpp/tsan_driver.cpp, the ThreadSanitizer run) as well as loaded
+// as separate libraries by the Python tests.
 #pragma once
 #include <stdint.h>
 
