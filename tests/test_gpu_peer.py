@@ -96,11 +96,14 @@ def test_mg_argument_checks():
     f.close()
 
 
-@pytest.mark.parametrize("n", [60, 30])
-def test_two_ranks_sharing_one_device(n):
+@pytest.mark.parametrize("world,n", [(2, 60), (2, 30), (4, 60)])
+def test_ranks_sharing_one_device(world, n):
+    """world processes, each with its own CUDA context on device 0: real cudaIpc mappings and the
+    device-side flag barriers; with 4 ranks the 15 column units of n = 60 split unevenly (4, 4, 4, 3).
+    (8 ranks: profiles/r1_peer_same_device_w8_s8.log, tools/gpu_session.sh peer.)"""
     env = dict(os.environ, NSMH_TEST_N=str(n), NSMH_MG_TIMEOUT_MS="60000")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-           "--master-addr", "127.0.0.1", "--master-port", str(29541 + n), os.path.join(ROOT, "tools", "peer_same_device.py")]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29541 + n + world), os.path.join(ROOT, "tools", "peer_same_device.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=400, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "OK" in r.stdout
