@@ -28,6 +28,7 @@
 #include <cstring>
 
 #include "nsmh_internal.cuh"
+#include "multigpu_kernels.cuh"
 
 namespace nsmh {
 
@@ -58,55 +59,6 @@ struct MgState {
     cudaEvent_t ev[7] = {};
     float stage_ms[6] = {};
 };
-
-struct ScatterArgs {
-    uint64_t *m[kMgMaxRanks];         // column block of rank o: [total_rows][ncols_o]
-    uint32_t col_end[kMgMaxRanks];
-    uint32_t world, row0;             // row0: global row of local row 0
-};
-
-// One warp per local row (strided), a lane per hash function: loads are the contiguous sketch
-// row, stores are runs of ncols_o * 8 bytes in the owner's memory.
-__global__ void __launch_bounds__(256)
-mg_scatter_columns_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_t n, ScatterArgs a) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-    const uint32_t w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (uint32_t j = lane; j < n; j += 32) {
-        uint32_t o = 0;
-        while (o + 1 < a.world && j >= a.col_end[o]) ++o;
-        const uint32_t cb = o ? a.col_end[o - 1] : 0u, nc = a.col_end[o] - cb;
-        uint64_t *dst = a.m[o] + (size_t)a.row0 * nc + (j - cb);
-        uint32_t i = w0;
-        for (; i + 3 * warps < rows; i += 4 * warps) {          // four loads in flight per lane
-            const uint64_t v0 = __ldg(S + (size_t)i * n + j), v1 = __ldg(S + (size_t)(i + warps) * n + j);
-            const uint64_t v2 = __ldg(S + (size_t)(i + 2 * warps) * n + j), v3 = __ldg(S + (size_t)(i + 3 * warps) * n + j);
-            dst[(size_t)i * nc] = v0;
-            dst[(size_t)(i + warps) * nc] = v1;
-            dst[(size_t)(i + 2 * warps) * nc] = v2;
-            dst[(size_t)(i + 3 * warps) * nc] = v3;
-        }
-        for (; i < rows; i += warps) dst[(size_t)i * nc] = __ldg(S + (size_t)i * n + j);
-    }
-}
-
-// The same when every rank owns a multiple of 4 hash functions: a thread moves 4 adjacent
-// columns of one row = one 32-byte sector in (256-bit load) and one out (256-bit store).
-__global__ void __launch_bounds__(256)
-mg_scatter_columns4_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_t n, ScatterArgs a) {
-    const uint32_t groups = n >> 2;
-    const uint64_t total = (uint64_t)rows * groups, stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
-        const uint32_t i = (uint32_t)(t / groups), j = (uint32_t)(t - (uint64_t)i * groups) << 2;
-        uint64_t v0, v1, v2, v3;
-        asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v0), "=l"(v1), "=l"(v2), "=l"(v3) : "l"(S + t * 4));
-        uint32_t o = 0;
-        while (o + 1 < a.world && j >= a.col_end[o]) ++o;
-        const uint32_t cb = o ? a.col_end[o - 1] : 0u, nc = a.col_end[o] - cb;
-        uint64_t *d = a.m[o] + (size_t)(a.row0 + i) * nc + (j - cb);
-        asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(d), "l"(v0), "l"(v1), "l"(v2), "l"(v3) : "memory");
-    }
-}
 
 struct BarrierArgs {
     uint32_t *flags[kMgMaxRanks];     // flags block of every rank: [2][kMgMaxRanks] epochs, [1] error, [kMgMaxRanks] inbox cursors
@@ -145,8 +97,6 @@ __global__ void mg_barrier_kernel(BarrierArgs a, uint32_t epoch, uint32_t which)
     }
 }
 
-static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
 void mg_destroy(nsmh_ctx *c) {
     MgState *m = c->mg;
     if (!m) return;
@@ -180,10 +130,8 @@ int nsmh_mg_init(nsmh_handle c, uint32_t rank, uint32_t world, const uint32_t *r
     if (!rows_per_rank || !token_out) return fail(NSMH_EINVAL, "mg_init: null argument");
     if (world < 1 || world > (uint32_t)kMgMaxRanks || rank >= world)
         return fail(NSMH_EINVAL, "mg_init: world must be in 1..16 and rank < world");
-    // hash functions are handed out in units of 4 (one 32-byte sector of a sketch row) when possible
-    const uint32_t unit = (c->n % 4 == 0 && c->n / 4 >= world) ? 4 : 1;
-    const uint32_t units = c->n / unit;
-    if (units < world) return fail(NSMH_EINVAL, "mg_init: more ranks than hash functions");
+    uint32_t split[kMgMaxRanks];
+    if (!mg_split_columns(c->n, world, split)) return fail(NSMH_EINVAL, "mg_init: more ranks than hash functions");
     int prev = -1;
     cudaGetDevice(&prev);
     if (cudaSetDevice(c->device) != cudaSuccess) return fail(NSMH_ECUDA, "cudaSetDevice failed");
@@ -195,13 +143,11 @@ int nsmh_mg_init(nsmh_handle c, uint32_t rank, uint32_t world, const uint32_t *r
     m->world = world;
     m->n_total = c->n;
     uint64_t total = 0;
-    uint32_t cend = 0;
     for (uint32_t r = 0; r < world; ++r) {
         m->rows[r] = rows_per_rank[r];
         total += rows_per_rank[r];
         m->row_end[r] = (uint32_t)total;
-        cend += (units / world + (r < units % world ? 1u : 0u)) * unit;
-        m->col_end[r] = cend;
+        m->col_end[r] = split[r];
     }
     int rc = NSMH_OK;
     do {
@@ -215,20 +161,19 @@ int nsmh_mg_init(nsmh_handle c, uint32_t rank, uint32_t world, const uint32_t *r
         MgToken &t = m->self;
         memset(&t, 0, sizeof t);
         const size_t items = std::max<size_t>((size_t)m->total_rows * m->ncols, 1);
-        const size_t local = std::max<size_t>((size_t)m->rows[rank] * m->n_total, 1);
-        size_t off = 0;
-        t.off_m = off;      off = align256(off + items * sizeof(uint64_t));
-        t.off_pr = off;     off = align256(off + local * sizeof(uint64_t));
-        t.off_ids = off;    off = align256(off + items * sizeof(uint32_t));
-        // inbox: one segment per source rank, room for 2 ids per (local read, hash of that rank)
         uint32_t max_cols = 0;
         for (uint32_t r = 0; r < world; ++r) max_cols = std::max(max_cols, m->col_end[r] - (r ? m->col_end[r - 1] : 0u));
-        t.inbox_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(2ull * m->rows[rank] * max_cols, 64), 1ull << 30);
         const char *ic = getenv("NSMH_MG_INBOX_CAP");        // tests: force the overflow path
-        if (ic && *ic && atoll(ic) > 0) t.inbox_cap = (uint32_t)std::min<long long>(atoll(ic), 1ll << 30);
-        t.off_inbox = off;  off = align256(off + (size_t)world * t.inbox_cap * sizeof(uint32_t));
-        t.off_flags = off;  off = align256(off + (3 * kMgMaxRanks + 8) * sizeof(uint32_t));
-        t.arena_bytes = off;
+        const MgLayout lay = mg_layout(m->total_rows, m->ncols, m->rows[rank], m->n_total, max_cols, world,
+                                       ic && *ic ? atoll(ic) : 0);
+        t.off_m = lay.off_m;
+        t.off_pr = lay.off_pr;
+        t.off_ids = lay.off_ids;
+        t.off_inbox = lay.off_inbox;
+        t.off_flags = lay.off_flags;
+        t.inbox_cap = lay.inbox_cap;
+        t.arena_bytes = lay.arena_bytes;
+        const size_t off = lay.arena_bytes;
         cudaError_t ce = cudaMalloc(reinterpret_cast<void **>(&m->arena), off);
         if (ce != cudaSuccess) { rc = cuda_fail(ce, "cudaMalloc(arena)", __FILE__, __LINE__); break; }
         if ((ce = cudaMemset(m->arena + t.off_flags, 0, (3 * kMgMaxRanks + 8) * sizeof(uint32_t))) != cudaSuccess) { rc = cuda_fail(ce, "memset", __FILE__, __LINE__); break; }

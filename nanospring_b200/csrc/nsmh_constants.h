@@ -1,7 +1,10 @@
 // Layout constants shared by the host code (nsmh_internal.cuh) and the kernel headers that are also
 // compiled for the host by the emulation tests (no CUDA includes here).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
+
+#include "../../include/nsmh.h"
 
 namespace nsmh {
 
@@ -33,5 +36,32 @@ __host__ __device__ __forceinline__ uint64_t slot_index(uint64_t key, uint64_t c
 
 // slots per table region: cap (even) + the slot of key ~0, padded so every region starts on a sector
 __host__ __device__ __forceinline__ uint64_t region_stride(uint64_t cap) { return cap + 2; }
+
+// ---- multi-GPU over peer memory (kernels in query_kernels.cuh / multigpu_kernels.cuh) ----
+constexpr int kMgMaxRanks = NSMH_MG_MAX_RANKS;
+// Probe results travel as one u64 per (read, hash): {id | group start} | (group size) << 32.
+// In the arena of the rank that owns the reads they are blocked by table owner: block o holds
+// [local row][hash functions of rank o], starting at rows * col_begin(o); a probing thread
+// writes the results of 4 adjacent hash functions as ONE 32-byte store and consecutive threads
+// (rows) write consecutive sectors, so the NVLink traffic is a contiguous stream.
+constexpr int kInboxMaxGroup = 32;           // groups of up to this many ids are pushed to the read owner's inbox
+constexpr uint32_t kInboxFlag = 0x80000000u; // in the size field: "val is a position in your inbox"
+struct PeerDst {
+    uint64_t *pr[kMgMaxRanks];        // probe-result area in rank r's arena
+    uint32_t *inbox[kMgMaxRanks];     // this rank's segment of rank r's inbox
+    uint32_t inbox_cap[kMgMaxRanks];  // ... and its capacity in ids
+    uint32_t *cursor;                 // [kMgMaxRanks] local: ids pushed to rank r so far (zeroed per run)
+    uint32_t row_end[kMgMaxRanks];    // global row index one past rank r's rows
+    uint32_t world, col0, ncols;      // hash functions this rank owns: [col0, col0 + ncols)
+};
+// Probe results stored locally by the table owners + where the owners keep their group ids.
+struct PeerLists {
+    const uint64_t *pr;                     // local probe-result area (layout above)
+    const uint32_t *inbox;                  // local inbox: segment o (inbox_cap ids) is filled by rank o
+    uint32_t inbox_cap;
+    const uint32_t *ids[kMgMaxRanks];       // ids array of the rank that owns the hash function
+    uint32_t col_end[kMgMaxRanks];          // hash functions [col_end[r-1], col_end[r]) belong to rank r
+    uint32_t world, n, rows;
+};
 
 } // namespace nsmh

@@ -28,245 +28,6 @@
 namespace nsmh {
 
 constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
-constexpr int kMaxParts = 16;        // PartsSrc: at most this many partial lists per query
-constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
-constexpr int kProbeRows = 256;    // queries per block = threads per block
-
-// One thread per (query, 4 adjacent hash functions): the four keys are one 32-byte sector of the
-// sketch row, every probe fetches one bucket = the two slots of one sector with ONE 256-bit
-// load, and the four results leave as 16-byte stores.  Blocks are ordered by hash function
-// (like table_insert_kernel), so the few table regions being probed at any time are L2
-// resident: DRAM streams every region once instead of serving 64-byte bursts for random
-// sectors all over the table.  The kernel is bound by the rate of 32-byte sector requests
-// (tools/micro/atom_bench.cu), hence one request per probe.
-__global__ void __launch_bounds__(kProbeRows, 4)
-probe_items_kernel(ProbeSrc src, uint32_t nq) {
-    const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
-    const uint32_t colgroups = (src.n + kProbeCols - 1) / kProbeCols;
-    const uint32_t units = chunks * colgroups;      // nq * n < 2^32 (probe_all)
-    const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
-    const bool vec = (src.n & 3) == 0;      // rows are sector aligned
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t cg = u / chunks;
-        const uint32_t q = (u - cg * chunks) * kProbeRows + threadIdx.x;
-        const uint32_t l0 = cg * kProbeCols;
-        if (q >= nq) continue;
-        const size_t t0 = (size_t)q * src.n + l0;
-        uint64_t key[kProbeCols];
-        if (vec) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
-        else {
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) key[j] = l0 + j < src.n ? __ldg(src.qsk + t0 + j) : 0;
-        }
-        uint64_t b[kProbeCols], sa[kProbeCols], sb[kProbeCols], sc[kProbeCols], sd[kProbeCols];
-#pragma unroll
-        for (int j = 0; j < kProbeCols; ++j) {
-            b[j] = key[j] == kEmptyKey ? nb : slot_index(key[j], nb);   // key ~0 lives in the extra slot
-            const uint32_t l = min(l0 + j, src.n - 1);
-            ldg256(src.slots + (uint64_t)l * rstride + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
-        }
-        uint32_t val[kProbeCols], cnt[kProbeCols];
-#pragma unroll
-        for (int j = 0; j < kProbeCols; ++j) {
-            const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
-            for (;;) {
-                // slot = {key, val | (cnt-1) << 32}
-                if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
-                if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
-                if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
-                ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
-            }
-        }
-        if (vec) {
-            *reinterpret_cast<uint4 *>(src.pval + t0) = make_uint4(val[0], val[1], val[2], val[3]);
-            *reinterpret_cast<uint4 *>(src.pcnt + t0) = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j)
-                if (l0 + j < src.n) { src.pval[t0 + j] = val[j]; src.pcnt[t0 + j] = cnt[j]; }
-        }
-    }
-}
-
-// The same probe, for the tables this rank owns (src.n hash functions starting at dst.col0) and
-// the reads of ALL ranks (q = global row).  The results are stored straight into the memory of
-// the rank that owns read q (peer mapping over NVLink).  Groups of 2..kInboxMaxGroup members
-// are pushed along: their ids are copied into this rank's segment of the read owner's inbox
-// (space comes from a LOCAL cursor, one warp-aggregated atomic per warp), so the counting
-// kernel over there finds them in its own memory instead of paying an NVLink round trip per
-// list.  Larger groups and anything beyond the inbox capacity stay behind and are read
-// remotely on demand.
-__global__ void __launch_bounds__(kProbeRows, 4)
-probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
-    const uint32_t colgroups = (src.n + kProbeCols - 1) / kProbeCols;
-    const uint32_t units = chunks * colgroups;
-    const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
-    const bool vec_in = (src.n & 3) == 0;
-    const bool vec_out = ((dst.col0 | dst.ncols) & 3) == 0 && vec_in;   // then every destination is 32-byte aligned
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t cg = u / chunks;
-        const uint32_t q = (u - cg * chunks) * kProbeRows + threadIdx.x;
-        const uint32_t l0 = cg * kProbeCols;
-        const bool active = q < nq;
-        uint32_t val[kProbeCols], cnt[kProbeCols];
-        uint32_t o = 0, need = 0;
-        if (active) {
-            const size_t t0 = (size_t)q * src.n + l0;
-            uint64_t key[kProbeCols];
-            if (vec_in) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
-            else {
-#pragma unroll
-                for (int j = 0; j < kProbeCols; ++j) key[j] = l0 + j < src.n ? __ldg(src.qsk + t0 + j) : 0;
-            }
-            uint64_t b[kProbeCols], sa[kProbeCols], sb[kProbeCols], sc[kProbeCols], sd[kProbeCols];
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) {
-                b[j] = key[j] == kEmptyKey ? nb : slot_index(key[j], nb);
-                const uint32_t l = min(l0 + j, src.n - 1);
-                ldg256(src.slots + (uint64_t)l * rstride + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) {
-                const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
-                for (;;) {
-                    if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
-                    if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                    if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
-                    if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                    b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
-                    ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
-                }
-                if (l0 + j >= src.n) cnt[j] = 0;
-                if (cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) need += cnt[j];
-            }
-            while (o + 1 < dst.world && q >= dst.row_end[o]) ++o;        // owner of read q
-        }
-        // inbox space: one atomic per warp for the lanes that share the first lane's destination
-        const uint32_t o_lead = __shfl_sync(0xffffffffu, o, 0);
-        const bool agg = active && o == o_lead;
-        const uint32_t incl = warp_incl_scan(agg ? need : 0u, lane);
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (tot) {
-            if (lane == 31) base = atomicAdd(dst.cursor + o_lead, tot);
-            base = __shfl_sync(0xffffffffu, base, 31);
-        }
-        if (!active) continue;
-        uint32_t pos = agg ? base + incl - need : (need ? atomicAdd(dst.cursor + o, need) : 0u);
-        const bool fits = need && (uint64_t)pos + need <= dst.inbox_cap[o];
-        const uint32_t r0 = o ? dst.row_end[o - 1] : 0u, rows_o = dst.row_end[o] - r0;
-        uint64_t *d = dst.pr[o] + (size_t)rows_o * dst.col0 + (size_t)(q - r0) * dst.ncols + l0;
-        uint64_t out[kProbeCols];
-#pragma unroll
-        for (int j = 0; j < kProbeCols; ++j) {
-            out[j] = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
-            if (fits && cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
-                uint32_t *box = dst.inbox[o] + pos;
-                for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
-                out[j] = (uint64_t)pos | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
-                pos += cnt[j];
-            }
-        }
-        if (vec_out) {
-            asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(d), "l"(out[0]), "l"(out[1]), "l"(out[2]), "l"(out[3]) : "memory");
-        } else {
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j)
-                if (l0 + j < src.n) d[j] = out[j];
-        }
-    }
-}
-
-// id lists from stored probe results
-struct StoredSrc {
-    const uint32_t *pval, *pcnt;   // [nq][n]
-    const uint32_t *ids;
-    uint32_t n;
-    struct Pending {
-        uint32_t val, c;
-    };
-    __device__ __forceinline__ uint32_t subs() const { return n; }
-    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
-        Pending p;
-        p.val = __ldg(pval + (size_t)q * n + j);
-        p.c = __ldg(pcnt + (size_t)q * n + j);
-        return p;
-    }
-    __device__ __forceinline__ ListRef finish(Pending p) const {
-        ListRef r;
-        r.c = p.c;
-        r.one = p.val;
-        r.ptr = p.c == 1 ? nullptr : ids + p.val;
-        return r;
-    }
-    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
-};
-
-struct PartsSrc {
-    const uint64_t *offs[kMaxParts];   // each [nq+1]
-    const uint32_t *ids[kMaxParts];
-    uint32_t parts;
-    struct Pending {
-        uint64_t o0, o1;
-        uint32_t j;
-    };
-    __device__ __forceinline__ uint32_t subs() const { return parts; }
-    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
-        Pending p;
-        p.j = j;
-        p.o0 = offs[j][q];
-        p.o1 = offs[j][q + 1];
-        return p;
-    }
-    __device__ __forceinline__ ListRef finish(Pending p) const {
-        ListRef r;
-        r.ptr = ids[p.j] + p.o0;
-        r.c = (uint32_t)(p.o1 - p.o0);
-        r.one = 0;
-        return r;
-    }
-    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
-};
-
-// Multi-GPU (multigpu.cu): the probe results of every (query, hash) were stored here by the
-// rank that owns the hash function's table; the ids of groups with two or more members stay
-// in the owner's memory and are read through the NVLink peer mapping.
-struct PeerSrc {
-    PeerLists L;
-    struct Pending {
-        uint64_t v;
-        uint32_t o;
-    };
-    __device__ __forceinline__ uint32_t subs() const { return L.n; }
-    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
-        Pending p;
-        uint32_t o = 0;
-        while (o + 1 < L.world && j >= L.col_end[o]) ++o;
-        const uint32_t cb = o ? L.col_end[o - 1] : 0u, nc = L.col_end[o] - cb;
-        p.o = o;
-        p.v = __ldg(L.pr + (size_t)L.rows * cb + (size_t)q * nc + (j - cb));
-        return p;
-    }
-    __device__ __forceinline__ ListRef finish(Pending p) const {
-        ListRef r;
-        r.c = (uint32_t)(p.v >> 32);
-        r.one = (uint32_t)p.v;
-        r.ptr = nullptr;
-        if (r.c & kInboxFlag) {                  // the owner pushed the ids into our inbox
-            r.c &= ~kInboxFlag;
-            r.ptr = L.inbox + (size_t)p.o * L.inbox_cap + r.one;
-        } else if (r.c > 1) {
-            r.ptr = L.ids[p.o] + r.one;          // NVLink read from the owner
-        }
-        return r;
-    }
-    __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
-};
-
 // count_kernel: query_kernels.cuh (count_body) - one warp per query, one pass
 template <typename Src>
 __global__ void __launch_bounds__(kLookupWarps * 32)

@@ -17,7 +17,7 @@
 #include <thread>
 #include <vector>
 
-#define __global__
+#define __global__ inline
 #define __device__
 #define __host__
 #define __forceinline__ inline
