@@ -72,3 +72,70 @@ def test_lookup_body_any_lists(query_emul, lists, thr, spread):
         want = expected(ls, thr)
         got = tmp[int(qpos[q]):int(qpos[q]) + int(qcount[q])]
         assert got.size == want.size and (got == want).all()
+
+
+# ---------------------------------------------------------------- FASTQ ingest, tables ----
+from fastq_cases import expected_packed  # noqa: E402
+from test_fastq_emul import run_emul  # noqa: E402
+from test_table_emul import query_all  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def fastq_emul():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "emul"])
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libfastq_emul.so"))
+    L.fq_emul_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint, C.c_uint32, u64p, C.c_uint64, u32p, C.c_uint64,
+                                u32p, u64p]
+    return L
+
+
+@pytest.fixture(scope="module")
+def table_emul():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "emul"])
+    L = C.CDLL(os.path.join(ROOT, "oracle", "libtable_emul.so"))
+    L.table_emul_build.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint]
+    L.table_emul_num_keys.argtypes = [C.c_uint32]
+    L.table_emul_num_keys.restype = C.c_uint32
+    L.table_emul_query.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint, u32p, u64p, u32p, C.c_uint64, u32p,
+                                   C.POINTER(C.c_ulonglong)]
+    L.table_emul_query.restype = None
+    return L
+
+
+line = st.one_of(st.binary(min_size=0, max_size=40).map(lambda b: b.replace(b"\n", b"N")),
+                 st.text(alphabet="ACGTN\r@+", min_size=0, max_size=600).map(str.encode))
+
+
+@settings(max_examples=80, **COMMON)
+@given(lines=st.lists(line, min_size=0, max_size=14), trailing=st.booleans(), misalign=st.integers(0, 15),
+       pack_iters=st.sampled_from([0, 4, 16, 64]))
+def test_fastq_ingest_any_text(fastq_emul, orc, lines, trailing, misalign, pack_iters):
+    """any sequence of lines (any bytes but the newline itself), with or without a final newline, at any
+    alignment: read table and packed words as the reference's record loop gives them"""
+    text = b"\n".join(lines) + (b"\n" if trailing and lines else b"")
+    off, words = run_emul(fastq_emul, text, misalign=misalign, grid=1, pack_iters=pack_iters)
+    bases, want_off = orc.fastq_reads(text)
+    assert off.size == want_off.size and (off == want_off).all()
+    want = expected_packed(bases)
+    assert (words[:want.size] == want).all()
+
+
+@settings(max_examples=25, **COMMON)
+@given(rows=st.integers(1, 90), n=st.integers(1, 9), keyspace=st.sampled_from([1, 3, 40, 2**40]), thr=st.integers(1, 4),
+       seed=st.integers(0, 2**31))
+def test_tables_any_key_multiplicity(table_emul, orc, rows, n, keyspace, thr, seed):
+    """sketch matrices whose columns hold one key only, a few keys (large groups), mostly distinct keys, the
+    empty marker ~0 and 0: distinct keys per table and the candidate list of every row equal the oracle"""
+    rng = np.random.default_rng(seed)
+    S = rng.integers(0, keyspace, size=(rows, n), dtype=np.uint64)
+    S[rng.random((rows, n)) < 0.1] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    S = np.ascontiguousarray(S)
+    assert table_emul.table_emul_build(S.ctypes.data_as(u64p), rows, n, 2) == 0
+    T = orc.build_tables(S)
+    for j in range(n):
+        assert table_emul.table_emul_num_keys(j) == T.num_keys(j)
+    got = query_all(table_emul, S, thr, grid=1)
+    for q in range(rows):
+        if got[q] is not None:
+            want = T.query_sketch(S[q], thr)
+            assert got[q].size == want.size and (got[q] == want).all()

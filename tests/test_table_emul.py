@@ -33,7 +33,7 @@ def emul():
 
 def query_all(L, qsk, thr, grid=2):
     nq, n = qsk.shape
-    cap = nq * 64 + 1024
+    cap = max(nq * 64, nq * nq) + 1024           # every row can match every row of a small table
     qcount = np.zeros(nq + 1, dtype=np.uint32)
     qpos = np.zeros(nq, dtype=np.uint64)
     tmp = np.zeros(cap, dtype=np.uint32)
