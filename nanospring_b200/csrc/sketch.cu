@@ -40,6 +40,8 @@
 
 namespace nsmh {
 
+constexpr bool kSketchBalancedDefault = false;   // flip once tools/gpu_session.sh ab has shown the balanced phase 2 to win
+
 // ---- host side (the kernels are in sketch_kernels.cuh) -------------------------------
 // uploads the lookup tables of the filter kernel (layout: sketch_tables.h)
 int build_filter_tables(nsmh_ctx *c) {
@@ -118,7 +120,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     if (mode == 0) {
         // per-device attribute: set on every call (cheap) rather than once per process
         const char *ev_bal = getenv("NSMH_SKETCH_BALANCED");        // experiment: see sketch_kernels.cuh
-        const bool balanced = ev_bal && *ev_bal && atoi(ev_bal) != 0;
+        const bool balanced = ev_bal && *ev_bal ? atoi(ev_bal) != 0 : kSketchBalancedDefault;
         auto filter_kernel = balanced ? sketch_filter_kernel<true> : sketch_filter_kernel<false>;
         NSMH_CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // one block per SM, as many warps as the shared memory holds (each warp owns a tile)
