@@ -252,7 +252,7 @@ int nsmh_destroy(nsmh_handle h) {
         h->pool.clear();
         cudaStream_t s = h->stream;
         free_ws(h->bulk, s);
-        DevBuf *bufs[] = {&h->d_rand, &h->d_ftab_first, &h->d_ftab_next, &h->sketches,
+        DevBuf *bufs[] = {&h->d_rand, &h->d_ftab_first, &h->d_ftab_next, &h->d_ftab_hit3, &h->sketches,
                           &h->tile_start, &h->read_flags, &h->counters, &h->build_multi, &h->build_tmp,
                           &h->tables.slots, &h->tables.ids};
         for (DevBuf *b : bufs) b->release(s);

@@ -23,11 +23,11 @@
 //    answers three consecutive positions) and touches the 64-bit path only for
 //    the ~n*lambda positions per read that hit, lambda = 2^lambda_log2 .. twice
 //    that being the expected k-mers per bucket (b = floor(log2 #kmers) - lambda_log2).
-//    A warp owns a tile (<= 1024 packed words of one read): the words arrive in
+//    A warp owns a tile (<= 640 packed words of one read): the words arrive in
 //    shared memory through ONE bulk asynchronous copy (cp.async.bulk + mbarrier),
-//    phase 1 turns them into one 32-position hit mask per lane and step, and in
-//    phase 2 every lane walks the hits of its own masks, so no compaction is
-//    needed and only the imbalance between lanes is lost.  A (read, hash) pair
+//    phase 1 turns them into one 32-position hit mask per lane and step and appends
+//    the hits of all lanes to one list, and phase 2 consumes the list 32 hits at a
+//    time with plain shared-memory loads and stores (no atomics).  A (read, hash) pair
 //    whose bucket stayed empty (probability ~e^-lambda on random sequence, certain
 //    on e.g. homopolymers) is rescanned exhaustively by sketch_fixup_kernel, which
 //    makes the result unconditional.
@@ -40,21 +40,20 @@
 
 namespace nsmh {
 
-constexpr bool kSketchBalancedDefault = false;   // flip once tools/gpu_session.sh ab has shown the balanced phase 2 to win
-
 // ---- host side (the kernels are in sketch_kernels.cuh) -------------------------------
 // uploads the lookup tables of the filter kernel (layout: sketch_tables.h)
 int build_filter_tables(nsmh_ctx *c) {
     const FilterTables ft = make_filter_tables(c->rand.data(), c->n, c->k);
-    const std::vector<uint8_t> &first = ft.first, &next = ft.next, &hit3 = ft.hit3;
+    const std::vector<uint16_t> &first = ft.first;
+    const std::vector<uint8_t> &next = ft.next, &hit3 = ft.hit3;
     const char *e = getenv("NSMH_LAMBDA_LOG2");
     if (e && *e) c->lambda_log2 = atoi(e) < 0 ? 0 : (atoi(e) > 8 ? 8 : atoi(e));
     e = getenv("NSMH_TILE_WORDS");
     if (e && *e && atoi(e) >= 32) c->tile_words = (uint32_t)atoi(e);
-    NSMH_TRY(c->d_ftab_first.ensure(first.size(), c->stream));
+    NSMH_TRY(c->d_ftab_first.ensure(first.size() * sizeof(uint16_t), c->stream));
     NSMH_TRY(c->d_ftab_next.ensure(next.size(), c->stream));
     NSMH_TRY(c->d_ftab_hit3.ensure(hit3.size(), c->stream));
-    NSMH_CK(cudaMemcpyAsync(c->d_ftab_first.p, first.data(), first.size(), cudaMemcpyHostToDevice, c->stream));
+    NSMH_CK(cudaMemcpyAsync(c->d_ftab_first.p, first.data(), first.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, c->stream));
     NSMH_CK(cudaMemcpyAsync(c->d_ftab_next.p, next.data(), next.size(), cudaMemcpyHostToDevice, c->stream));
     NSMH_CK(cudaMemcpyAsync(c->d_ftab_hit3.p, hit3.data(), hit3.size(), cudaMemcpyHostToDevice, c->stream));
     NSMH_CK(cudaStreamSynchronize(c->stream));   // host vectors die here
@@ -70,7 +69,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     a.W = rs.packed.as<uint32_t>();
     a.sk = d_sketches;
     a.rnd = c->d_rand.as<uint64_t>();
-    a.ftab_first = c->d_ftab_first.as<uint8_t>();
+    a.ftab_first = c->d_ftab_first.as<uint16_t>();
     a.ftab_next = c->d_ftab_next.as<uint8_t>();
     a.ftab_hit3 = c->d_ftab_hit3.as<uint8_t>();
     a.counters = c->counters.as<unsigned long long>();
@@ -119,9 +118,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     if (ev0) NSMH_CK(cudaEventRecord(ev0, s));
     if (mode == 0) {
         // per-device attribute: set on every call (cheap) rather than once per process
-        const char *ev_bal = getenv("NSMH_SKETCH_BALANCED");        // experiment: see sketch_kernels.cuh
-        const bool balanced = ev_bal && *ev_bal ? atoi(ev_bal) != 0 : kSketchBalancedDefault;
-        auto filter_kernel = balanced ? sketch_filter_kernel<true> : sketch_filter_kernel<false>;
+        auto filter_kernel = sketch_filter_kernel;
         NSMH_CK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         // one block per SM, as many warps as the shared memory holds (each warp owns a tile)
         const FilterSmem L(c->n, a.tile_words);
@@ -137,9 +134,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         uint32_t *miss_list = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(cub_tmp.p) + list_off);
         unsigned int *miss_count = a.tile_queue + 1;
         sketch_missing_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
-        const char *ev_fw = getenv("NSMH_FIXUP_WIDTH");            // experiment: see sketch_kernels.cuh
-        if (ev_fw && atoi(ev_fw) == 8) sketch_fixup_kernel<8><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
-        else sketch_fixup_kernel<4><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+        sketch_fixup_kernel<4><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
         *launches += 2;
         NSMH_CK(cudaGetLastError());
     } else {

@@ -20,7 +20,8 @@ struct SketchArgs {
     const uint32_t *tile_start; // [n_reads+1] exclusive scan of tiles per read
     const uint32_t *tile_read;  // [num_tiles] read of every tile (nullptr: binary search)
     const uint64_t *rnd;        // [n]
-    const uint8_t *ftab_first, *ftab_next, *ftab_hit3;
+    const uint16_t *ftab_first;         // per prefix: first hash that targets it | second one << 8 (0xFF = none)
+    const uint8_t *ftab_next, *ftab_hit3;
     unsigned long long *counters;   // [0] fix-ups
     unsigned int *tile_queue;       // next tile to hand out (filter kernel: warps take tiles dynamically)
     uint32_t n_reads, k, n;
@@ -160,7 +161,7 @@ struct FilterSmem {
     __host__ __device__ FilterSmem(uint32_t n, uint32_t tile_words) {
         stage_words = tile_words + 8;
         mask_words = tile_words / 2;
-        size_t t = kFilter3TabSize + (2 << kFilter3MaxBits) + (size_t)(kFilterMaxBits + 1) * n + (size_t)n * 8 + 8;
+        size_t t = kFilter3TabSize + (4 << kFilter3MaxBits) + (size_t)(kFilterMaxBits + 1) * n + (size_t)n * 8 + 8;
         tab_bytes = (t + 15) & ~(size_t)15;
         warp_bytes = ((size_t)stage_words * 4 + (size_t)mask_words * 4 + (size_t)n * 16 + 16 + 15) & ~(size_t)15;
     }
@@ -168,29 +169,79 @@ struct FilterSmem {
 
 // ---- filter kernel ------------------------------------------------------------------
 // a.tile_words is a multiple of 64: in every step a lane owns two adjacent words = 32 positions.
-//
-// BALANCED = true (experiment, NSMH_SKETCH_BALANCED=1): phase 2 hands every lane the same number of
-// hits.  The lanes' hit counts (known after phase 1) are prefix-summed, lane L takes the hits of ranks
-// [L * ceil(H/32), ...) in lane-major order of the masks, finds its first hit with a binary search over
-// the prefix sums and walks on from there, possibly into the masks of the following lanes.  The minima
-// do not depend on who processes a hit, so the result is the same; what changes is that the warp no
-// longer waits for the lane with the most hits (47 % of the lanes are active in phase 2 today).
-template <bool BALANCED>
+
+// Plain 64-bit accesses to the warp's minima that several lanes may make to the same word in the same
+// instruction (phase 2 below: one of the colliding stores wins, every writer re-reads).  volatile on the
+// device so that they are neither cached in registers nor moved across the warp barriers; relaxed
+// atomics in the host emulation (where every lane is an OS thread).
+#ifndef NSMH_HOST_EMUL
+__device__ __forceinline__ void racy_store64(uint64_t *p, uint64_t v) { *reinterpret_cast<volatile uint64_t *>(p) = v; }
+__device__ __forceinline__ uint64_t racy_load64(const uint64_t *p) { return *reinterpret_cast<const volatile uint64_t *>(p); }
+#else
+__device__ __forceinline__ void racy_store64(uint64_t *p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+__device__ __forceinline__ uint64_t racy_load64(const uint64_t *p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+#endif
+
+// hit mask of the 32 positions that start in words i0, i0+1 of the staged tile (bit 31-q = position q)
+__device__ __forceinline__ uint32_t filter_hits32(const uint32_t *sw, const uint8_t *s_hit3, uint32_t i0, int rshift3,
+                                                  uint32_t lo_pos, uint32_t hi_pos) {
+    const uint2 w01 = *reinterpret_cast<const uint2 *>(sw + i0);
+    const uint32_t w0 = w01.x, w1 = w01.y, w2 = sw[i0 + 2];
+    uint32_t hi = 0, lo = 0;
+#pragma unroll
+    for (int t = 0; t < 5; ++t) {          // positions 0..14
+        const uint32_t v = t ? __funnelshift_l(w1, w0, 6 * t) : w0;
+        hi = hi * 8 + s_hit3[__funnelshift_rc(v, 1u, rshift3)];   // (1<<(b+4)) | window
+    }
+#pragma unroll
+    for (int t = 5; t < 11; ++t) {         // positions 15..32
+        const uint32_t v = t == 5 ? __funnelshift_l(w1, w0, 30) : __funnelshift_l(w2, w1, 6 * t - 32);
+        lo = lo * 8 + s_hit3[__funnelshift_rc(v, 1u, rshift3)];
+    }
+    uint32_t m = (hi << 17) | (lo >> 1);
+    const uint32_t pb = i0 * kWordBases;
+    if (pb < lo_pos || pb + 32 > hi_pos) {     // read / tile edges
+        const uint32_t first = lo_pos > pb ? lo_pos - pb : 0u;          // valid q in [first, last)
+        const uint32_t last = hi_pos > pb ? min(hi_pos - pb, 32u) : 0u;
+        const uint32_t keep_hi = first >= 32 ? 0u : 0xFFFFFFFFu >> first;
+        const uint32_t keep_lo = last == 0 ? 0u : 0xFFFFFFFFu << (32 - last);
+        m &= keep_hi & keep_lo;
+    }
+    return m;
+}
+
+// One block per SM, a warp per tile.  Per tile:
+//   stage    the tile's packed words arrive in shared memory through ONE bulk copy (cp.async.bulk + mbarrier)
+//   phase 1  32 positions per lane and step: funnel shifts + table lookups (one lookup answers three
+//            consecutive positions) give a hit mask; the hits of the whole warp are appended to ONE list
+//            of tile positions (prefix sum of the lanes' counts, then every lane writes its own)
+//   phase 2  the list is consumed 32 hits at a time, one per lane, whatever lane found them: k-mer from
+//            the staged words, hash(es) that target its prefix, 64-bit XOR / compare against the warp's
+//            minima.  A smaller value is written with a PLAIN store: when lanes collide on a hash one
+//            store wins, all writers re-read after a warp barrier and the losers that are still smaller
+//            try again (shared-memory atomics cost 2 cycles per lane, 64-bit min is a compare-and-swap
+//            loop on top; the ncu capture of the first version of this kernel showed the shared-memory
+//            pipe 87 % busy, a third of it in phase 2's atomics and scattered mask reads)
+//   flush    one 64-bit atomicMin per (tile, hash) combines the tiles of a read
+// The list holds tile_words positions (16 bit each); a tile with more hits (low-complexity sequence)
+// is consumed in several rounds, and a single step with more hits than the list holds (> tile_words of
+// its 1024 positions) is walked lane by lane with atomics instead.
 __global__ void __launch_bounds__(1024)
 sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
     NSMH_FILTER_SMEM_DECL
     const FilterSmem L(a.n, a.tile_words);
     uint8_t *s_hit3 = smem;                                   // kFilter3TabSize
-    uint8_t *s_first = s_hit3 + kFilter3TabSize;              // 2^(kFilter3MaxBits+1)
-    uint8_t *s_next = s_first + (2 << kFilter3MaxBits);       // (kFilterMaxBits+1) * n
-    uint64_t *s_rlo = reinterpret_cast<uint64_t *>(smem + ((kFilter3TabSize + (2 << kFilter3MaxBits) +
+    uint16_t *s_first = reinterpret_cast<uint16_t *>(s_hit3 + kFilter3TabSize);   // 2^(kFilter3MaxBits+1) entries
+    uint8_t *s_next = s_hit3 + kFilter3TabSize + (4 << kFilter3MaxBits);          // (kFilterMaxBits+1) * n
+    uint64_t *s_rlo = reinterpret_cast<uint64_t *>(smem + ((kFilter3TabSize + (4 << kFilter3MaxBits) +
                                                             (size_t)(kFilterMaxBits + 1) * a.n + 7) & ~(size_t)7));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *mine = smem + L.tab_bytes + (size_t)warp * L.warp_bytes;
     uint32_t *sw = reinterpret_cast<uint32_t *>(mine);                      // staged words
-    uint32_t *own = sw + L.stage_words;                                     // hit masks, [step][lane]
-    ulonglong2 *my_min = reinterpret_cast<ulonglong2 *>(own + L.mask_words);   // {rand[l] & mask, running minimum}
+    uint16_t *list = reinterpret_cast<uint16_t *>(sw + L.stage_words);      // hit positions (tile-relative)
+    ulonglong2 *my_min = reinterpret_cast<ulonglong2 *>(sw + L.stage_words + L.mask_words);   // {rand[l] & mask, running minimum}
     uint64_t *bar = reinterpret_cast<uint64_t *>(my_min + a.n);
+    const uint32_t cap = 2 * L.mask_words;                                  // list entries
 
     const uint64_t mask = kmer_mask(a.k);
     {
@@ -198,7 +249,7 @@ sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
         const uint4 *gf = reinterpret_cast<const uint4 *>(a.ftab_first);
         uint4 *s3 = reinterpret_cast<uint4 *>(s_hit3), *sf = reinterpret_cast<uint4 *>(s_first);
         for (int t = threadIdx.x; t < kFilter3TabSize / 16; t += blockDim.x) s3[t] = g3[t];
-        for (int t = threadIdx.x; t < (2 << kFilter3MaxBits) / 16; t += blockDim.x) sf[t] = gf[t];
+        for (int t = threadIdx.x; t < (4 << kFilter3MaxBits) / 16; t += blockDim.x) sf[t] = gf[t];
         for (uint32_t t = threadIdx.x; t < (kFilterMaxBits + 1) * a.n; t += blockDim.x) s_next[t] = a.ftab_next[t];
         for (uint32_t t = threadIdx.x; t < a.n; t += blockDim.x) s_rlo[t] = a.rnd[t] & mask;
         if (lane == 0) {
@@ -243,112 +294,80 @@ sketch_filter_kernel(SketchArgs a NSMH_FILTER_SMEM_PARAM) {
         const uint32_t steps = (nw + 63) / 64;
         while (!mbar_try_wait(bar, phase)) { }
         phase ^= 1;
-        __syncwarp();       // the minima initialised above by their owner lanes are read and updated by any lane in phase 2
 
-        // ---- phase 1: 32 positions per lane and step -> hit mask (bit 31-q = position q) ----
-        uint32_t mycnt = 0;
-        for (uint32_t it = 0; it < steps; ++it) {
+        uint32_t total = 0;                 // hits in the list
+        for (uint32_t it = 0;; ++it) {
+            // ---- phase 1: this step's hit mask, the lanes' counts prefix-summed ----
+            const bool done = it == steps;
             const uint32_t i0 = it * 64 + 2 * lane;
-            const uint2 w01 = *reinterpret_cast<const uint2 *>(sw + i0);
-            const uint32_t w0 = w01.x, w1 = w01.y, w2 = sw[i0 + 2];
-            uint32_t hi = 0, lo = 0;
+            uint32_t m = 0, incl = 0, wt = 0;
+            if (!done) {
+                m = filter_hits32(sw, s_hit3, i0, rshift3, lo_pos, hi_pos);
+                incl = __popc(m);
 #pragma unroll
-            for (int t = 0; t < 5; ++t) {          // positions 0..14
-                const uint32_t v = t ? __funnelshift_l(w1, w0, 6 * t) : w0;
-                hi = hi * 8 + s_hit3[__funnelshift_rc(v, 1u, rshift3)];   // (1<<(b+4)) | window
-            }
-#pragma unroll
-            for (int t = 5; t < 11; ++t) {         // positions 15..32
-                const uint32_t v = t == 5 ? __funnelshift_l(w1, w0, 30) : __funnelshift_l(w2, w1, 6 * t - 32);
-                lo = lo * 8 + s_hit3[__funnelshift_rc(v, 1u, rshift3)];
-            }
-            uint32_t m = (hi << 17) | (lo >> 1);
-            const uint32_t pb = i0 * kWordBases;
-            if (pb < lo_pos || pb + 32 > hi_pos) {     // read / tile edges
-                const uint32_t first = lo_pos > pb ? lo_pos - pb : 0u;          // valid q in [first, last)
-                const uint32_t last = hi_pos > pb ? min(hi_pos - pb, 32u) : 0u;
-                const uint32_t keep_hi = first >= 32 ? 0u : 0xFFFFFFFFu >> first;
-                const uint32_t keep_lo = last == 0 ? 0u : 0xFFFFFFFFu << (32 - last);
-                m &= keep_hi & keep_lo;
-            }
-            own[it * 32 + lane] = m;
-            if (BALANCED) mycnt += __popc(m);
-        }
-
-        // ---- phase 2: every lane walks its own hits ----
-        if (!BALANCED) {
-            uint32_t c = 0;
-            uint32_t m = own[lane];
-            for (;;) {
-                while (m == 0 && ++c < steps) m = own[c * 32 + lane];
-                if (m == 0) break;
-                const int q = __clz(m);
-                m &= ~(0x80000000u >> q);
-                const uint32_t wi = c * 64 + 2 * lane + (q >> 4);
-                uint32_t h32;
-                const uint64_t x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], q & 15, kshift, h32);
-                uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)];
-                do {
-                    const ulonglong2 rm = my_min[l];
-                    const uint32_t ln = nxt[l];
-                    const uint64_t y = x ^ rm.x;
-                    if (y < rm.y) atomicMin(&my_min[l].y, (unsigned long long)y);
-                    l = ln;
-                } while (l != 0xFFu);
-            }
-        } else {
-            // ---- phase 2, balanced: the same hits, ceil(H/32) per lane ----
-            __syncwarp();                                       // the masks of all lanes are in place
-            uint32_t incl = mycnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            const uint32_t H = __shfl_sync(0xffffffffu, incl, 31);
-            const uint32_t quota = (H + 31) >> 5;
-            const uint32_t start = (uint32_t)lane * quota;
-            uint32_t mine = start < H ? min(quota, H - start) : 0u;
-            // owner of my first hit = number of lanes whose inclusive count is <= start (incl is monotone)
-            uint32_t ow = 0;
-#pragma unroll
-            for (int s = 16; s; s >>= 1) {
-                const uint32_t v = __shfl_sync(0xffffffffu, incl, (int)(ow + s - 1));
-                if (v <= start) ow += s;
-            }
-            const uint32_t prev = __shfl_sync(0xffffffffu, incl, (int)(ow ? ow - 1 : 0));
-            uint32_t skip = start - (ow ? prev : 0u);           // hits of the owner that belong to earlier lanes
-            uint32_t c = 0, m = 0;
-            if (mine) {
-                m = own[ow];
-                while ((uint32_t)__popc(m) <= skip) {           // ends inside the owner's masks: skip < its count
-                    skip -= __popc(m);
-                    ++c;
-                    m = own[c * 32 + ow];
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
                 }
-                for (; skip; --skip) m &= ~(0x80000000u >> __clz(m));
+                wt = __shfl_sync(0xffffffffu, incl, 31);
             }
-            for (; mine; --mine) {
-                while (m == 0) {                                // a hit of mine is still ahead, in lane-major order
-                    if (++c == steps) {
-                        c = 0;
-                        ++ow;
+            if (done || total + wt > cap) {
+                // ---- phase 2: consume the list, one hit per lane and round ----
+                __syncwarp();               // list entries (and, for the first round, the initial minima) are in place
+                for (uint32_t base = 0; base < total; base += 32) {
+                    const uint32_t i = base + lane;
+                    bool want = false;
+                    uint64_t x = 0, y = 0, *mp = nullptr;
+                    uint32_t l2 = 0xFFu;
+                    if (i < total) {
+                        const uint32_t pos = list[i];
+                        const uint32_t wi = pos >> 4;
+                        uint32_t h32;
+                        x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], (int)(pos & 15), kshift, h32);
+                        const uint32_t ll = s_first[__funnelshift_rc(h32, 1u, rshift)];   // a hit: at least one hash
+                        const uint32_t l = ll & 0xFFu;
+                        l2 = ll >> 8;
+                        mp = reinterpret_cast<uint64_t *>(&my_min[l].y);
+                        const ulonglong2 rm = my_min[l];
+                        y = x ^ rm.x;
+                        want = y < rm.y;
+                        if (want) racy_store64(mp, y);
                     }
-                    m = own[c * 32 + ow];
+                    __syncwarp();           // all stores of the round are done: did mine survive, or a smaller one?
+                    if (want && y < racy_load64(mp)) atomicMin(reinterpret_cast<unsigned long long *>(mp), (unsigned long long)y);
+                    // further hashes with the same prefix (3 % of the hits): atomics, no plain store is in flight now
+                    for (; l2 != 0xFFu; l2 = nxt[l2])
+                        atomicMin(reinterpret_cast<unsigned long long *>(&my_min[l2].y), (unsigned long long)(x ^ my_min[l2].x));
+                    __syncwarp();           // the next round's plain stores stay clear of this round's atomics
                 }
-                const int q = __clz(m);
-                m &= ~(0x80000000u >> q);
-                const uint32_t wi = c * 64 + 2 * ow + (q >> 4);
-                uint32_t h32;
-                const uint64_t x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], q & 15, kshift, h32);
-                uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)];
-                do {
-                    const ulonglong2 rm = my_min[l];
-                    const uint32_t ln = nxt[l];
-                    const uint64_t y = x ^ rm.x;
-                    if (y < rm.y) atomicMin(&my_min[l].y, (unsigned long long)y);
-                    l = ln;
-                } while (l != 0xFFu);
+                total = 0;
+                if (done) break;
+            }
+            if (wt > cap) {
+                // more hits in ONE step than the list holds: every lane walks its own mask
+                while (m) {
+                    const int q = __clz(m);
+                    m &= ~(0x80000000u >> q);
+                    const uint32_t wi = i0 + (q >> 4);
+                    uint32_t h32;
+                    const uint64_t x = kmer_at(sw[wi], sw[wi + 1], sw[wi + 2], q & 15, kshift, h32);
+                    uint32_t l = s_first[__funnelshift_rc(h32, 1u, rshift)] & 0xFFu;
+                    do {
+                        const uint64_t y = x ^ my_min[l].x;
+                        atomicMin(reinterpret_cast<unsigned long long *>(&my_min[l].y), (unsigned long long)y);
+                        l = nxt[l];
+                    } while (l != 0xFFu);
+                }
+                __syncwarp();
+            } else {
+                uint32_t slot = total + incl - __popc(m);
+                const uint32_t pb = i0 * kWordBases;
+                while (m) {
+                    const int q = __clz(m);
+                    m &= ~(0x80000000u >> q);
+                    list[slot++] = (uint16_t)(pb + q);
+                }
+                total += wt;
             }
         }
         __syncwarp();

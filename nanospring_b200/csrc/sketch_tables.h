@@ -12,16 +12,18 @@
 namespace nsmh {
 
 struct FilterTables {
-    std::vector<uint8_t> first, next, hit3;
+    std::vector<uint16_t> first;            // head of the chain | its successor << 8
+    std::vector<uint8_t> next, hit3;
 };
 
 inline FilterTables make_filter_tables(const uint64_t *rand, uint32_t n, uint32_t k) {
     std::vector<uint8_t> hit(kFilterTabSize, 0);
     FilterTables ft;
-    std::vector<uint8_t> &first = ft.first, &next = ft.next, &hit3 = ft.hit3;
-    first.assign(kFilterTabSize, 0xFF);
+    std::vector<uint8_t> first(kFilterTabSize, 0xFF);
+    std::vector<uint8_t> &next = ft.next, &hit3 = ft.hit3;
     next.assign((size_t)(kFilterMaxBits + 1) * (n ? n : 1), 0xFF);
     hit3.assign(kFilter3TabSize, 0);
+    ft.first.assign(kFilterTabSize, 0xFFFF);
     if (n <= 255) {
         const uint64_t mask = (1ULL << (2 * k)) - 1;
         for (int b = 0; b <= kFilterMaxBits && b <= 2 * (int)k; ++b) {
@@ -34,6 +36,9 @@ inline FilterTables make_filter_tables(const uint64_t *rand, uint32_t n, uint32_
                 first[idx] = (uint8_t)l;
             }
         }
+        for (int b = 0; b <= kFilterMaxBits && b <= 2 * (int)k; ++b)
+            for (uint32_t idx = 1u << b; idx < (2u << b); ++idx)
+                if (first[idx] != 0xFF) ft.first[idx] = (uint16_t)(first[idx] | (next[(size_t)b * n + first[idx]] << 8));
         for (int b = 0; b <= kFilter3MaxBits && b <= 2 * (int)k; ++b) {
             const uint32_t pm = (1u << b) - 1, base = 1u << b;
             for (uint32_t wv = 0; wv < (1u << (b + 4)); ++wv) {

@@ -17,7 +17,7 @@ using namespace nsmh;
 extern "C" {
 
 // W: packed stream followed by kPackPadWords zero words.  mode 0 = filter kernel + exact fix-up,
-// 1 = brute force, 2 = the experimental variants: balanced phase 2 (NSMH_SKETCH_BALANCED) + 8-word fix-up steps (NSMH_FIXUP_WIDTH=8).  sk [n_reads][n] out; *fixups = entries the fix-up pass recomputed.  Returns 0,
+// 1 = brute force.  sk [n_reads][n] out; *fixups = entries the fix-up pass recomputed.  Returns 0,
 // or -1 when the configuration does not fit the filter kernel (n > 255).
 int sketch_emul_run(const uint32_t *W, const uint64_t *off, uint32_t n_reads, uint32_t k, uint32_t n,
                     const uint64_t *rnd, int mode, int lambda_log2, uint32_t tile_words, unsigned grid, uint64_t *sk,
@@ -58,13 +58,11 @@ int sketch_emul_run(const uint32_t *W, const uint64_t *off, uint32_t n_reads, ui
         const size_t bytes = L.tab_bytes + L.warp_bytes;                     // one warp per block
         uint8_t *smem = static_cast<uint8_t *>(aligned_alloc(16, (bytes + 15) & ~(size_t)15));
         memset(smem, 0xA5, bytes);
-        if (mode == 2) emu_launch(grid, 32, [&] { sketch_filter_kernel<true>(a, smem); });
-        else emu_launch(grid, 32, [&] { sketch_filter_kernel<false>(a, smem); });
+        emu_launch(grid, 32, [&] { sketch_filter_kernel(a, smem); });
         free(smem);
         std::vector<uint32_t> miss((size_t)n_reads * n + 1, 0);
         emu_launch(grid, 64, [&] { sketch_missing_kernel(a, miss.data(), queue + 1); });
-        if (mode == 2) emu_launch(grid, 64, [&] { sketch_fixup_kernel<8>(a, miss.data(), queue + 1); });   // both experiments
-        else emu_launch(grid, 64, [&] { sketch_fixup_kernel<4>(a, miss.data(), queue + 1); });
+        emu_launch(grid, 64, [&] { sketch_fixup_kernel<4>(a, miss.data(), queue + 1); });
         *fixups = counters[0];
     } else {
         emu_launch(grid, 64, [&] { sketch_brute_kernel<8>(a); });

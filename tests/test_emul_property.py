@@ -1,6 +1,6 @@
 """Property tests (hypothesis, derandomised) of the emulated device code against the oracle: random small
 read sets with arbitrary bytes, every k in 1..31, any n up to 70, any filter density and tile size for the
-sketch kernels (filter + fix-up, balanced variant, brute force); random id lists and thresholds for the
+sketch kernels (filter + fix-up, brute force); random id lists and thresholds for the
 lookup body.  The oracle is pinned to the unmodified reference, so a counter-example is a kernel bug."""
 import ctypes as C
 import os
@@ -46,7 +46,7 @@ reads_strategy = st.lists(
 
 @settings(max_examples=120, **COMMON)
 @given(reads=reads_strategy, k=st.integers(1, 31), n=st.integers(1, 70), lam=st.integers(0, 8),
-       tile_words=st.sampled_from([64, 128, 640, 1024]), seed=st.integers(0, 2**32 - 1), mode=st.sampled_from([0, 1, 2]))
+       tile_words=st.sampled_from([64, 128, 640, 1024]), seed=st.integers(0, 2**32 - 1), mode=st.sampled_from([0, 1]))
 def test_sketch_kernels_any_input(sketch_emul, orc, reads, k, n, lam, tile_words, seed, mode):
     bases, offsets = reads_to_buffers(reads)
     rnd = ns.rand_from_seed(seed, n)

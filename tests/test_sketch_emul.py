@@ -62,27 +62,25 @@ def test_filter_and_brute_kernels_equal_oracle(emul, orc, k, n):
         assert fixups > 0, "the homopolymer / dinucleotide reads need the fix-up pass"
     got, _ = sketch(emul, bases, offsets, k, n, rnd, mode=1)
     assert (got == want).all(), "brute-force kernel"
-    got, fixups_bal = sketch(emul, bases, offsets, k, n, rnd, mode=2)
-    assert (got == want).all(), "filter kernel, balanced phase 2"
-    assert fixups_bal == fixups, "the balanced phase 2 processes the same hits"
 
 
-@pytest.mark.parametrize("tile_words,lam", [(64, 2), (128, 0), (4096, 5), (640, 8), (100, 3)])
+# (640, 8), (64, 6): nearly every position is a hit, so a step holds more hits than the list (the lane-by-lane
+# walk with atomics) and a tile needs several rounds of phase 2
+@pytest.mark.parametrize("tile_words,lam", [(64, 2), (128, 0), (4096, 5), (640, 8), (100, 3), (64, 6), (192, 5)])
 def test_tile_sizes_and_filter_density(emul, orc, tile_words, lam):
     k, n = 23, 60
     rng = np.random.default_rng(tile_words + lam)
     bases, offsets = read_set(rng, k)
     rnd = ns.rand_from_seed(20261017, n)
     want = orc.sketch_all(bases, offsets, k, n, rnd)
-    for mode in (0, 2):
-        got, _ = sketch(emul, bases, offsets, k, n, rnd, mode=mode, lam=lam, tile_words=tile_words, grid=3)
-        assert (got == want).all(), f"mode {mode}"
+    got, _ = sketch(emul, bases, offsets, k, n, rnd, mode=0, lam=lam, tile_words=tile_words, grid=3)
+    assert (got == want).all()
 
 
 def test_reference_static_kats_through_the_kernels(emul, orc):
     """string2KMers("ACGTTGCAAC", 4) = 45 181 215 94 120 224 130: with rand = 0 the sketch
     is the smallest k-mer; with rand = all-ones it is the complement of the largest."""
     bases, offsets = reads_to_buffers([b"ACGTTGCAAC"])
-    for mode in (0, 1, 2):
+    for mode in (0, 1):
         got, _ = sketch(emul, bases, offsets, 4, 2, np.array([0, 0xFF], dtype=np.uint64), mode=mode)
         assert got[0, 0] == 45 and got[0, 1] == (224 ^ 0xFF)
