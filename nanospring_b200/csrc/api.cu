@@ -656,8 +656,7 @@ int nsmh_build(nsmh_handle c) {
     NSMH_CK(cudaEventRecord(c->ev[6], c->stream));
     NSMH_TRY(build_tables(c));
     NSMH_CK(cudaEventRecord(c->ev[7], c->stream));
-    NSMH_CK(cudaStreamSynchronize(c->stream));
-    c->stats.build_ms = elapsed(c->ev[6], c->ev[7]);
+    c->build_timed = true;          // no host round trip here: nsmh_get_stats reads the events
     return NSMH_OK;
 }
 
@@ -675,9 +674,7 @@ int nsmh_query_all(nsmh_handle c, int rc_mode, uint64_t *total_ids) {
     QueryWs &ws = c->bulk;
     ws.stream = c->stream;
     c->bulk_valid = false;
-    cudaEvent_t e0, e1;
-    NSMH_CK(cudaEventCreate(&e0));
-    NSMH_CK(cudaEventCreate(&e1));
+    cudaEvent_t e0 = c->ev[8], e1 = c->ev[9];
     int rc = NSMH_OK;
     cudaEventRecord(e0, c->stream);
     const uint64_t *q = c->sketches.as<uint64_t>();
@@ -696,7 +693,7 @@ int nsmh_query_all(nsmh_handle c, int rc_mode, uint64_t *total_ids) {
     }
     if (!rc) rc = query_sketches_device(c, ws, q, c->reads.num_reads, c->stream);
     cudaEventRecord(e1, c->stream);
-    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream);       // e1 only: the lookup itself ended with its one read-back
     if (!rc) {
         c->stats.query_ms = elapsed(e0, e1);
         c->stats.query_pairs = ws.last_pairs;
@@ -705,8 +702,6 @@ int nsmh_query_all(nsmh_handle c, int rc_mode, uint64_t *total_ids) {
         c->bulk_valid = true;
         if (total_ids) *total_ids = ws.last_total;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     return rc;
 }
 
@@ -921,6 +916,7 @@ int nsmh_get_stats(nsmh_handle c, nsmh_stats *out) {
     NSMH_CK(cudaStreamSynchronize(c->stream));
     // device-resident loads return before the pack kernel has run: its events are read here
     if (c->reads.external_offsets && c->reads_loaded) c->stats.pack_ms = elapsed(c->ev[0], c->ev[1]);
+    if (c->build_timed) c->stats.build_ms = elapsed(c->ev[6], c->ev[7]);
     if (c->sketched) {
         c->stats.sketch_ms = elapsed(c->ev[2], c->ev[3]);
         c->stats.sketch_main_ms = elapsed(c->ev[4], c->ev[5]);

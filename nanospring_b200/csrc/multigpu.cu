@@ -300,15 +300,10 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
 
     NSMH_CK(cudaEventRecord(m->ev[0], s));
     if (rows) {
-        bool by4 = (c->n & 3) == 0;
-        for (uint32_t r = 0; r < m->world; ++r) by4 = by4 && (m->col_end[r] & 3) == 0;
-        if (by4) {
-            const int blocks = (int)std::min<uint64_t>(((uint64_t)rows * (c->n >> 2) + 255) / 256, (uint64_t)c->num_sms * 8);
-            mg_scatter_columns4_kernel<<<blocks, 256, 0, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
-        } else {
-            const int blocks = (int)std::min<uint64_t>(((uint64_t)rows + 7) / 8, (uint64_t)c->num_sms * 8);
-            mg_scatter_columns_kernel<<<blocks, 256, 0, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
-        }
+        const size_t smem = (size_t)kScatterRows * c->n * sizeof(uint64_t);
+        if (smem > 48 * 1024) NSMH_CK(cudaFuncSetAttribute(mg_scatter_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)rows + kScatterRows - 1) / kScatterRows, (uint64_t)c->num_sms * 8);
+        mg_scatter_columns_kernel<<<blocks, 256, smem, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
         ++c->launches;
         NSMH_CK(cudaGetLastError());
     }

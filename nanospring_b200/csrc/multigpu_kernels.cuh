@@ -11,16 +11,23 @@
 
 namespace nsmh {
 
+// dynamic shared memory of the kernels here: a parameter in the host emulation (like sketch_filter_kernel)
+#ifndef NSMH_HOST_EMUL
+#define NSMH_MG_SMEM_PARAM
+#define NSMH_MG_SMEM_DECL extern __shared__ __align__(16) uint8_t mg_smem[];
+#else
+#define NSMH_MG_SMEM_PARAM , uint8_t *mg_smem
+#define NSMH_MG_SMEM_DECL
+#endif
+
 // ---- who owns which hash functions -------------------------------------------------------------
-// Hash functions are handed out in units of 4 (one 32-byte sector of a sketch row) when possible.
-// col_end[r] = one past the last hash function of rank r.  false: more ranks than units.
+// col_end[r] = one past the last hash function of rank r; the first n % world ranks own one more than the
+// others (15/15/15/15 of 60 at 4 ranks, 8/8/8/8/7/7/7/7 at 8).  false: more ranks than hash functions.
 inline bool mg_split_columns(uint32_t n, uint32_t world, uint32_t *col_end) {
-    const uint32_t unit = (n % 4 == 0 && n / 4 >= world) ? 4 : 1;
-    const uint32_t units = n / unit;
-    if (units < world) return false;
+    if (n < world) return false;
     uint32_t cend = 0;
     for (uint32_t r = 0; r < world; ++r) {
-        cend += (units / world + (r < units % world ? 1u : 0u)) * unit;
+        cend += n / world + (r < n % world ? 1u : 0u);
         col_end[r] = cend;
     }
     return true;
@@ -28,7 +35,8 @@ inline bool mg_split_columns(uint32_t n, uint32_t world, uint32_t *col_end) {
 
 // ---- one rank's arena ----------------------------------------------------------------------------
 //   m      [total_rows][ncols] u64   sketch columns of the hash functions this rank owns, all reads
-//   pr     [rows][n_total]     u64   probe results of this rank's reads, blocked by table owner
+//   pr     [rows][n_total]     u64   probe results of this rank's reads, blocked by table owner and, inside an
+//                                    owner's block, by groups of kPeerCols hash functions (peer_result_index)
 //   ids    [total_rows*ncols]  u32   group members of the owned tables
 //   inbox  [world][inbox_cap]  u32   small groups pushed along by the table owners
 //   flags  2 x kMgMaxRanks epochs, error flag, kMgMaxRanks inbox cursors
@@ -67,46 +75,44 @@ struct ScatterArgs {
     uint32_t world, row0;             // row0: global row of local row 0
 };
 
-// One warp per local row (strided), a lane per hash function: loads are the contiguous sketch
-// row, stores are runs of ncols_o * 8 bytes in the owner's memory.
-__global__ void __launch_bounds__(256)
-mg_scatter_columns_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_t n, ScatterArgs a) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
-    const uint32_t w0 = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    for (uint32_t j = lane; j < n; j += 32) {
-        uint32_t o = 0;
-        while (o + 1 < a.world && j >= a.col_end[o]) ++o;
-        const uint32_t cb = o ? a.col_end[o - 1] : 0u, nc = a.col_end[o] - cb;
-        uint64_t *dst = a.m[o] + (size_t)a.row0 * nc + (j - cb);
-        uint32_t i = w0;
-        for (; i + 3 * warps < rows; i += 4 * warps) {          // four loads in flight per lane
-            const uint64_t v0 = __ldg(S + (size_t)i * n + j), v1 = __ldg(S + (size_t)(i + warps) * n + j);
-            const uint64_t v2 = __ldg(S + (size_t)(i + 2 * warps) * n + j), v3 = __ldg(S + (size_t)(i + 3 * warps) * n + j);
-            dst[(size_t)i * nc] = v0;
-            dst[(size_t)(i + warps) * nc] = v1;
-            dst[(size_t)(i + 2 * warps) * nc] = v2;
-            dst[(size_t)(i + 3 * warps) * nc] = v3;
-        }
-        for (; i < rows; i += warps) dst[(size_t)i * nc] = __ldg(S + (size_t)i * n + j);
-    }
-}
+// A block takes kScatterRows consecutive local rows: the tile [rows][n] is contiguous in the sketch matrix
+// and comes in with coalesced 128-bit loads; for every owner o the sub-block [rows][ncols_o] is contiguous in
+// the owner's column block too (M_o is row-major with ncols_o columns), so it leaves as a dense run of
+// 8-byte stores - full 128-byte lines over NVLink.  (The first version stored one 32-byte piece per thread
+// at a stride of ncols_o * 8 bytes: half-written lines, and twice the time at 8 ranks than at 2.)
+constexpr int kScatterRows = 32;
 
-// The same when every rank owns a multiple of 4 hash functions: a thread moves 4 adjacent
-// columns of one row = one 32-byte sector in (256-bit load) and one out (256-bit store).
 __global__ void __launch_bounds__(256)
-mg_scatter_columns4_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_t n, ScatterArgs a) {
-    const uint32_t groups = n >> 2;
-    const uint64_t total = (uint64_t)rows * groups, stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < total; t += stride) {
-        const uint32_t i = (uint32_t)(t / groups), j = (uint32_t)(t - (uint64_t)i * groups) << 2;
-        uint64_t v0, v1, v2, v3;
-        ldg256(S + t * 4, v0, v1, v2, v3);
-        uint32_t o = 0;
-        while (o + 1 < a.world && j >= a.col_end[o]) ++o;
-        const uint32_t cb = o ? a.col_end[o - 1] : 0u, nc = a.col_end[o] - cb;
-        uint64_t *d = a.m[o] + (size_t)(a.row0 + i) * nc + (j - cb);
-        stg256(d, v0, v1, v2, v3);
+mg_scatter_columns_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_t n, ScatterArgs a NSMH_MG_SMEM_PARAM) {
+    NSMH_MG_SMEM_DECL
+    uint64_t *tile = reinterpret_cast<uint64_t *>(mg_smem);        // [kScatterRows][n]
+    const uint32_t tiles = (rows + kScatterRows - 1) / kScatterRows;
+    for (uint32_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const uint32_t i0 = t * kScatterRows, nr = min((uint32_t)kScatterRows, rows - i0);
+        const uint32_t words = nr * n;
+        const uint64_t *src = S + (size_t)i0 * n;
+        __syncthreads();                    // the previous tile has left
+        if ((n & 1) == 0) {                 // rows are 16-byte aligned
+            for (uint32_t w = threadIdx.x * 2; w < words; w += blockDim.x * 2) {
+                const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(src + w);
+                tile[w] = v.x;
+                tile[w + 1] = v.y;
+            }
+        } else {
+            for (uint32_t w = threadIdx.x; w < words; w += blockDim.x) tile[w] = src[w];
+        }
+        __syncthreads();
+        uint32_t cb = 0;
+        for (uint32_t o = 0; o < a.world; ++o) {
+            const uint32_t nc = a.col_end[o] - cb;
+            uint64_t *dst = a.m[o] + (size_t)(a.row0 + i0) * nc;
+            const uint32_t cnt = nr * nc;
+            for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+                const uint32_t i = e / nc, c = e - i * nc;
+                dst[e] = tile[i * n + cb + c];
+            }
+            cb = a.col_end[o];
+        }
     }
 }
 

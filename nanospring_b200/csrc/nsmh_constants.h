@@ -40,10 +40,17 @@ __host__ __device__ __forceinline__ uint64_t region_stride(uint64_t cap) { retur
 // ---- multi-GPU over peer memory (kernels in query_kernels.cuh / multigpu_kernels.cuh) ----
 constexpr int kMgMaxRanks = NSMH_MG_MAX_RANKS;
 // Probe results travel as one u64 per (read, hash): {id | group start} | (group size) << 32.
-// In the arena of the rank that owns the reads they are blocked by table owner: block o holds
-// [local row][hash functions of rank o], starting at rows * col_begin(o); a probing thread
-// writes the results of 4 adjacent hash functions as ONE 32-byte store and consecutive threads
-// (rows) write consecutive sectors, so the NVLink traffic is a contiguous stream.
+// In the arena of the rank that owns the reads they are blocked by table owner (block o starts at
+// rows * col_begin(o)) and, inside an owner's block, by groups of kPeerCols hash functions: group b is a
+// dense array [local row][hash functions of the group].  A block of the probe kernel produces the tile
+// [256 rows][one group] in shared memory and writes it out as ONE contiguous run per read owner, so the
+// NVLink traffic is full 128-byte lines (peer_result_index below is the layout both sides use).
+constexpr int kPeerCols = 8;
+// index of (local row q, hash function jj of an owner with nc hash functions) inside that owner's block
+__host__ __device__ __forceinline__ size_t peer_result_index(uint32_t rows, uint32_t nc, uint32_t q, uint32_t jj) {
+    const uint32_t b = jj / kPeerCols, w = nc - b * kPeerCols < (uint32_t)kPeerCols ? nc - b * kPeerCols : (uint32_t)kPeerCols;
+    return (size_t)rows * (b * kPeerCols) + (size_t)q * w + (jj - b * kPeerCols);
+}
 constexpr int kInboxMaxGroup = 32;           // groups of up to this many ids are pushed to the read owner's inbox
 constexpr uint32_t kInboxFlag = 0x80000000u; // in the size field: "val is a position in your inbox"
 struct PeerDst {

@@ -111,7 +111,8 @@ struct nsmh_ctx {
     uint32_t k = 0, n = 0, thr = 0;
     std::vector<uint64_t> rand;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev[10] = {};
+    bool build_timed = false;
     int sketch_mode = 0;
     int num_sms = 148;
 

@@ -29,11 +29,12 @@ namespace nsmh {
 
 constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
 // count_kernel: query_kernels.cuh (count_body) - one warp per query, one pass
-template <typename Src>
+// RL = lists per lane kept in registers: 2 for n <= 64 (fewer registers, more warps per SM), else 4
+template <typename Src, int RL>
 __global__ void __launch_bounds__(kLookupWarps * 32)
 count_kernel(Src src, CountArgs a) {
     extern __shared__ __align__(16) uint32_t s_buf[];
-    count_body(src, a, s_buf);
+    count_body<Src, RL>(src, a, s_buf);
 }
 
 // tmp_ids (completion order) -> CSR (query order); 8 lanes per query
@@ -52,8 +53,8 @@ csr_place_kernel(CountArgs a, const uint32_t *__restrict__ mid_ids, const uint64
     }
 }
 
-// The same placement launched BEFORE the host has seen the counters (experiment,
-// NSMH_LOOKUP_SPECULATE=1): a query whose results did not fit tmp_ids, or whose place lies beyond
+// The same placement launched BEFORE the host has seen the counters (the default;
+// NSMH_LOOKUP_SPECULATE=0 switches it off): a query whose results did not fit tmp_ids, or whose place lies beyond
 // out_ids, is skipped - the host then repeats the placement on the general path.
 __global__ void __launch_bounds__(256)
 csr_place_guarded_kernel(CountArgs a, const uint64_t *__restrict__ out_off, uint32_t *__restrict__ out_ids,
@@ -151,10 +152,10 @@ static bool mid_tier_enabled() {
     return e && *e ? atoi(e) != 0 : kMidTierDefault;
 }
 
-// NSMH_LOOKUP_SPECULATE=1: see count_and_emit (experiment, off by default)
+// NSMH_LOOKUP_SPECULATE=0 switches the speculative placement off (see count_and_emit; A/B runs, tests)
 static bool speculate_enabled() {
     const char *e = getenv("NSMH_LOOKUP_SPECULATE");
-    return e && *e && atoi(e) != 0;
+    return e && *e ? atoi(e) != 0 : true;
 }
 
 static int grid_for(uint64_t items, int sms, int per_block = 256) {
@@ -264,14 +265,17 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     NSMH_TRY(ws.qpos.ensure((size_t)nq * sizeof(uint64_t), s));
     NSMH_TRY(ws.heavy_list.ensure((size_t)nq * sizeof(uint32_t), s));
     NSMH_TRY(ws.counters.ensure(8 * sizeof(uint64_t), s));
-    // results land in tmp_ids in completion order; its size is a guess that the kernel checks
-    // (the cursor keeps counting past the end), so at most one repeat with the exact size
-    if (ws.tmp_ids.cap < (size_t)nq * 16 * sizeof(uint32_t))
-        NSMH_TRY(ws.tmp_ids.ensure((size_t)nq * 16 * sizeof(uint32_t), s));
+    // results land in tmp_ids: kFixedIds per query at a fixed place, larger result lists behind them in
+    // completion order; the size of that part is a guess that the kernel checks (the cursor keeps counting
+    // past the end), so at most one repeat with the exact size
+    const size_t fixed_ids = (size_t)nq * kFixedIds;
+    if (ws.tmp_ids.cap < (fixed_ids + (size_t)nq * 8) * sizeof(uint32_t))
+        NSMH_TRY(ws.tmp_ids.ensure((fixed_ids + (size_t)nq * 8) * sizeof(uint32_t), s));
 
     const size_t smem = (size_t)kLookupWarps * kWarpWords * sizeof(uint32_t);
     // function attributes are per device: set on every call (cheap) rather than once per process
-    NSMH_CK(cudaFuncSetAttribute(count_kernel<Src>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kernel = subs <= 64 ? count_kernel<Src, 2> : count_kernel<Src, kRegListsMax>;
+    NSMH_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CountArgs a;
     a.qcount = ws.qcount.as<uint32_t>();
     a.qpos = ws.qpos.as<uint64_t>();
@@ -280,12 +284,12 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     a.nq = nq;
     a.thr = c->thr ? c->thr : 1;    // thr 0 and 1 both emit every gathered id once (ReadFilter.cpp:76-82)
     int occ = 0;
-    NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, count_kernel<Src>, kLookupWarps * 32, smem));
+    NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kLookupWarps * 32, smem));
     const int blocks = (int)std::min<uint64_t>(((uint64_t)nq + kLookupWarps - 1) / kLookupWarps,
                                                (uint64_t)c->num_sms * (occ > 0 ? occ : 1));
-    unsigned long long cnt[3] = {0, 0, 0};
-    // Experiment (NSMH_LOOKUP_SPECULATE=1): prefix sum and placement are queued right behind the counting
-    // kernel, before the host knows whether a query overflowed; when none did and the results fit
+    unsigned long long cnt[4] = {0, 0, 0, 0};
+    // Prefix sum and placement are queued right behind the counting kernel (measured on B200: 0.235 ->
+    // 0.221 ms for the benchmark's lookup; NSMH_LOOKUP_SPECULATE=0 switches it off), before the host knows whether a query overflowed; when none did and the results fit
     // (the common case) the single read-back below is the only host round trip of the lookup.
     const bool speculate = speculate_enabled();
     size_t spec_tmp_bytes = 0;
@@ -299,7 +303,7 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
         a.tmp_cap = ws.tmp_ids.cap / sizeof(uint32_t);
         NSMH_CK(cudaMemsetAsync(ws.counters.p, 0, 8 * sizeof(uint64_t), s));
         NSMH_CK(cudaMemsetAsync(ws.qcount.as<uint32_t>() + nq, 0, sizeof(uint32_t), s));
-        count_kernel<Src><<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
+        kernel<<<blocks, kLookupWarps * 32, smem, s>>>(src, a);
         ++ws.launches;
         NSMH_CK(cudaGetLastError());
         uint64_t spec_total = 0;
@@ -313,21 +317,22 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
         }
         NSMH_CK(cudaMemcpyAsync(cnt, ws.counters.p, sizeof cnt, cudaMemcpyDeviceToHost, s));
         NSMH_CK(cudaStreamSynchronize(s));
-        if (speculate && attempt == 0 && cnt[0] == 0 && cnt[2] <= a.tmp_cap &&
+        if (speculate && attempt == 0 && cnt[0] == 0 && fixed_ids + cnt[3] <= a.tmp_cap &&
             spec_total <= ws.out_ids.cap / sizeof(uint32_t)) {
             ws.last_pairs = cnt[1];
             ws.last_total = spec_total;          // == cnt[2]: nothing was skipped by the guards
             return NSMH_OK;
         }
-        if (cnt[2] <= a.tmp_cap) break;
-        NSMH_TRY(ws.tmp_ids.ensure((size_t)cnt[2] * sizeof(uint32_t), s));
+        if (fixed_ids + cnt[3] <= a.tmp_cap) break;
+        NSMH_TRY(ws.tmp_ids.ensure((fixed_ids + (size_t)cnt[3]) * sizeof(uint32_t), s));
     }
     uint32_t nh = (uint32_t)cnt[0];
     const uint32_t *hl = ws.heavy_list.as<uint32_t>();
     ws.last_pairs = cnt[1];
     ws.last_heavy = nh;
-    // a result id needs at least one gathered id, so their number bounds the output size
-    NSMH_TRY(ws.out_ids.ensure((size_t)std::max<uint64_t>(cnt[1], 1) * sizeof(uint32_t), s));
+    // output size: the results counted so far are exact (cnt[2]); a query handed on to the next tiers emits
+    // at most (its gathered ids) / thr, and those ids are part of cnt[1]
+    NSMH_TRY(ws.out_ids.ensure((size_t)(cnt[2] + cnt[1] / a.thr + 1) * sizeof(uint32_t), s));
     if (nh && mid_tier_enabled()) {
         // counting-filter tier: resolves the heavy queries that have few ids above the threshold
         // (query_kernels.cuh); what it cannot resolve goes on to the global sort.  A result needs thr
@@ -424,6 +429,14 @@ static int probe_all(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32
 int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s) {
     Tables &T = c->tables;
     if (!T.built) return fail(NSMH_ESTATE, "query: tables not built (call nsmh_build)");
+    const char *e_split = getenv("NSMH_LOOKUP_SPLIT");
+    if (e_split && atoi(e_split) != 0) {
+        // probe kernel (thread per query x 4 hash functions, ordered by hash function so the region being
+        // probed is L2 resident) + counting kernel over the stored results
+        StoredSrc stored;
+        NSMH_TRY(probe_all(c, ws, d_qsketch, nq, s, stored));
+        return count_and_emit(c, ws, stored, c->n, nq, s);
+    }
     ProbeSrc src;
     src.qsk = d_qsketch;
     src.slots = T.slots.as<Slot>();
@@ -497,7 +510,7 @@ int probe_to_peers_device(nsmh_ctx *sub, const uint64_t *d_qsketch, uint32_t nq,
     src.pcnt = nullptr;
     src.cap = T.cap;
     src.n = sub->n;
-    const uint64_t units = (uint64_t)((nq + kProbeRows - 1) / kProbeRows) * ((sub->n + kProbeCols - 1) / kProbeCols);
+    const uint64_t units = (uint64_t)((nq + kProbeRows - 1) / kProbeRows) * ((sub->n + kPeerCols - 1) / kPeerCols);
     int occ = 0;
     NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, probe_to_peers_kernel, kProbeRows, 0));
     const int blocks = (int)std::min<uint64_t>(units, (uint64_t)sub->num_sms * (occ > 0 ? occ : 1));

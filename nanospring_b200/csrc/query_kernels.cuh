@@ -54,6 +54,9 @@ struct ProbeSrc {
         uint32_t j;
     };
     __device__ __forceinline__ uint32_t subs() const { return n; }
+    __device__ __forceinline__ void prefetch(uint32_t q, int lane) const {      // row q of the sketches: n * 8 bytes
+        if ((uint32_t)lane * 16 < n) l2_prefetch_line(qsk + (size_t)q * n + lane * 16);
+    }
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
         p.j = j;
@@ -92,6 +95,14 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
         if (lane >= o) v += t;
     }
     return v;
+}
+
+// `need` ids of inbox space from a 32-bit cursor.  A full inbox is not asked again (the cursor would wrap
+// after 2^32 ids and hand out ranges that earlier results already point to): what does not fit stays behind
+// and is read remotely, the cursor overshoots the capacity (<= 2^30) by what is in flight at most.
+__device__ __forceinline__ uint32_t inbox_take(uint32_t *cursor, uint32_t need, uint32_t cap) {
+    if (*reinterpret_cast<volatile uint32_t *>(cursor) >= cap) return cap;
+    return atomicAdd(cursor, need);
 }
 
 constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
@@ -156,93 +167,103 @@ probe_items_kernel(ProbeSrc src, uint32_t nq) {
 }
 
 // The same probe, for the tables this rank owns (src.n hash functions starting at dst.col0) and
-// the reads of ALL ranks (q = global row).  The results are stored straight into the memory of
-// the rank that owns read q (peer mapping over NVLink).  Groups of 2..kInboxMaxGroup members
-// are pushed along: their ids are copied into this rank's segment of the read owner's inbox
-// (space comes from a LOCAL cursor, one warp-aggregated atomic per warp), so the counting
-// kernel over there finds them in its own memory instead of paying an NVLink round trip per
-// list.  Larger groups and anything beyond the inbox capacity stay behind and are read
-// remotely on demand.
+// the reads of ALL ranks (q = global row).  A block takes 256 rows x one group of up to kPeerCols hash
+// functions (two passes of 4 per thread), collects the results in shared memory and writes the tile out
+// as ONE dense run per read owner into that owner's memory (peer mapping over NVLink): consecutive threads
+// store consecutive 8-byte words, i.e. full 128-byte lines.  (The first version stored 32 bytes per thread
+// at a stride of ncols * 8 bytes - half-written lines - and its time tripled from 2 to 8 ranks.)
+// Groups of 2..kInboxMaxGroup members are pushed along: their ids are copied into this rank's segment of
+// the read owner's inbox (space comes from a LOCAL cursor, one warp-aggregated atomic per warp), so the
+// counting kernel over there finds them in its own memory instead of paying an NVLink round trip per
+// list.  Larger groups and anything beyond the inbox capacity stay behind and are read remotely on demand.
 __global__ void __launch_bounds__(kProbeRows, 4)
 probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
+    __shared__ uint64_t s_tile[kProbeRows * kPeerCols];
     const int lane = threadIdx.x & 31;
     const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
-    const uint32_t colgroups = (src.n + kProbeCols - 1) / kProbeCols;
-    const uint32_t units = chunks * colgroups;
+    const uint32_t colblocks = (src.n + kPeerCols - 1) / kPeerCols;
+    const uint32_t units = chunks * colblocks;
     const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
     const bool vec_in = (src.n & 3) == 0;
-    const bool vec_out = ((dst.col0 | dst.ncols) & 3) == 0 && vec_in;   // then every destination is 32-byte aligned
     for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t cg = u / chunks;
-        const uint32_t q = (u - cg * chunks) * kProbeRows + threadIdx.x;
-        const uint32_t l0 = cg * kProbeCols;
+        const uint32_t cbk = u / chunks, chunk = u - cbk * chunks;
+        const uint32_t q = chunk * kProbeRows + threadIdx.x;
+        const uint32_t c0 = cbk * kPeerCols, w = min((uint32_t)kPeerCols, src.n - c0);     // this group's hash functions
         const bool active = q < nq;
-        uint32_t val[kProbeCols], cnt[kProbeCols];
-        uint32_t o = 0, need = 0;
-        if (active) {
-            const size_t t0 = (size_t)q * src.n + l0;
-            uint64_t key[kProbeCols];
-            if (vec_in) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
-            else {
-#pragma unroll
-                for (int j = 0; j < kProbeCols; ++j) key[j] = l0 + j < src.n ? __ldg(src.qsk + t0 + j) : 0;
-            }
-            uint64_t b[kProbeCols], sa[kProbeCols], sb[kProbeCols], sc[kProbeCols], sd[kProbeCols];
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) {
-                b[j] = key[j] == kEmptyKey ? nb : slot_index(key[j], nb);
-                const uint32_t l = min(l0 + j, src.n - 1);
-                ldg256(src.slots + (uint64_t)l * rstride + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
-            }
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) {
-                const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
-                for (;;) {
-                    if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
-                    if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                    if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
-                    if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                    b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
-                    ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
-                }
-                if (l0 + j >= src.n) cnt[j] = 0;
-                if (cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) need += cnt[j];
-            }
+        uint32_t o = 0;
+        if (active)
             while (o + 1 < dst.world && q >= dst.row_end[o]) ++o;        // owner of read q
-        }
-        // inbox space: one atomic per warp for the lanes that share the first lane's destination
-        const uint32_t o_lead = __shfl_sync(0xffffffffu, o, 0);
-        const bool agg = active && o == o_lead;
-        const uint32_t incl = warp_incl_scan(agg ? need : 0u, lane);
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        uint32_t base = 0;
-        if (tot) {
-            if (lane == 31) base = atomicAdd(dst.cursor + o_lead, tot);
-            base = __shfl_sync(0xffffffffu, base, 31);
-        }
-        if (!active) continue;
-        uint32_t pos = agg ? base + incl - need : (need ? atomicAdd(dst.cursor + o, need) : 0u);
-        const bool fits = need && (uint64_t)pos + need <= dst.inbox_cap[o];
-        const uint32_t r0 = o ? dst.row_end[o - 1] : 0u, rows_o = dst.row_end[o] - r0;
-        uint64_t *d = dst.pr[o] + (size_t)rows_o * dst.col0 + (size_t)(q - r0) * dst.ncols + l0;
-        uint64_t out[kProbeCols];
+        for (uint32_t l0 = c0; l0 < c0 + w; l0 += kProbeCols) {
+            uint32_t val[kProbeCols], cnt[kProbeCols];
+            uint32_t need = 0;
+            if (active) {
+                const size_t t0 = (size_t)q * src.n + l0;
+                uint64_t key[kProbeCols];
+                if (vec_in) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
+                else {
 #pragma unroll
-        for (int j = 0; j < kProbeCols; ++j) {
-            out[j] = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
-            if (fits && cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
-                uint32_t *box = dst.inbox[o] + pos;
-                for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
-                out[j] = (uint64_t)pos | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
-                pos += cnt[j];
+                    for (int j = 0; j < kProbeCols; ++j) key[j] = l0 + j < src.n ? __ldg(src.qsk + t0 + j) : 0;
+                }
+                uint64_t b[kProbeCols], sa[kProbeCols], sb[kProbeCols], sc[kProbeCols], sd[kProbeCols];
+#pragma unroll
+                for (int j = 0; j < kProbeCols; ++j) {
+                    b[j] = key[j] == kEmptyKey ? nb : slot_index(key[j], nb);
+                    const uint32_t l = min(l0 + j, src.n - 1);
+                    ldg256(src.slots + (uint64_t)l * rstride + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < kProbeCols; ++j) {
+                    const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
+                    for (;;) {
+                        if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
+                        if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                        if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
+                        if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                        b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
+                        ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
+                    }
+                    if (l0 + j >= c0 + w) cnt[j] = 0;
+                    if (cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) need += cnt[j];
+                }
+            }
+            // inbox space: one atomic per warp for the lanes that share the first lane's destination
+            const uint32_t o_lead = __shfl_sync(0xffffffffu, o, 0);
+            const bool agg = active && o == o_lead;
+            const uint32_t incl = warp_incl_scan(agg ? need : 0u, lane);
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t base = 0;
+            if (tot) {
+                if (lane == 31) base = inbox_take(dst.cursor + o_lead, tot, dst.inbox_cap[o_lead]);
+                base = __shfl_sync(0xffffffffu, base, 31);
+            }
+            if (active) {
+                uint32_t pos = agg ? base + incl - need : (need ? inbox_take(dst.cursor + o, need, dst.inbox_cap[o]) : 0u);
+                const bool fits = need && (uint64_t)pos + need <= dst.inbox_cap[o];
+#pragma unroll
+                for (int j = 0; j < kProbeCols; ++j) {
+                    if (l0 + j >= c0 + w) continue;
+                    uint64_t out = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
+                    if (fits && cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
+                        uint32_t *box = dst.inbox[o] + pos;
+                        for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
+                        out = (uint64_t)pos | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
+                        pos += cnt[j];
+                    }
+                    s_tile[threadIdx.x * w + (l0 - c0) + j] = out;
+                }
             }
         }
-        if (vec_out) {
-            stg256(d, out[0], out[1], out[2], out[3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j)
-                if (l0 + j < src.n) d[j] = out[j];
+        __syncthreads();
+        // ---- the tile [rows of the chunk][w] leaves: a dense run per read owner ----
+        const uint32_t q0 = chunk * kProbeRows, nr = min((uint32_t)kProbeRows, nq - q0);
+        for (uint32_t e = threadIdx.x; e < nr * w; e += kProbeRows) {
+            const uint32_t r = e / w, c = e - r * w, qq = q0 + r;
+            uint32_t oo = 0;
+            while (oo + 1 < dst.world && qq >= dst.row_end[oo]) ++oo;
+            const uint32_t r0 = oo ? dst.row_end[oo - 1] : 0u, rows_o = dst.row_end[oo] - r0;
+            dst.pr[oo][(size_t)rows_o * dst.col0 + peer_result_index(rows_o, dst.ncols, qq - r0, c0 + c)] = s_tile[e];
         }
+        __syncthreads();                    // the tile is free again
     }
 }
 
@@ -255,6 +276,12 @@ struct StoredSrc {
         uint32_t val, c;
     };
     __device__ __forceinline__ uint32_t subs() const { return n; }
+    __device__ __forceinline__ void prefetch(uint32_t q, int lane) const {
+        if ((uint32_t)lane * 32 < n) {
+            l2_prefetch_line(pval + (size_t)q * n + lane * 32);
+            l2_prefetch_line(pcnt + (size_t)q * n + lane * 32);
+        }
+    }
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
         p.val = __ldg(pval + (size_t)q * n + j);
@@ -280,6 +307,7 @@ struct PartsSrc {
         uint32_t j;
     };
     __device__ __forceinline__ uint32_t subs() const { return parts; }
+    __device__ __forceinline__ void prefetch(uint32_t, int) const {}
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
         p.j = j;
@@ -307,13 +335,14 @@ struct PeerSrc {
         uint32_t o;
     };
     __device__ __forceinline__ uint32_t subs() const { return L.n; }
+    __device__ __forceinline__ void prefetch(uint32_t, int) const {}
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
         uint32_t o = 0;
         while (o + 1 < L.world && j >= L.col_end[o]) ++o;
         const uint32_t cb = o ? L.col_end[o - 1] : 0u, nc = L.col_end[o] - cb;
         p.o = o;
-        p.v = __ldg(L.pr + (size_t)L.rows * cb + (size_t)q * nc + (j - cb));
+        p.v = __ldg(L.pr + (size_t)L.rows * cb + peer_result_index(L.rows, nc, q, j - cb));
         return p;
     }
     __device__ __forceinline__ ListRef finish(Pending p) const {
@@ -351,7 +380,7 @@ __device__ __forceinline__ void warp_bitonic_smem(uint32_t *buf, uint32_t P, int
 
 // ------------------------------------------------------------------ counting filter, in place --
 // The same idea for the ids a warp has already laid out in its sort buffer (count_kernel's sort path,
-// 256 < gathered ids <= kLookupCap): count them into 512 16-bit counters, keep the ids whose bucket
+// 128 < gathered ids <= kLookupCap): count them into 512 16-bit counters, keep the ids whose bucket
 // reaches the threshold (stable, in place), and let the bitonic sort run on the survivors only -
 // typically tens instead of a thousand.  Exact for the same reason as below; T <= 65535.
 constexpr int kWarpFilterBuckets = 512;     // two per word: c16 = kWarpFilterBuckets / 2 words
@@ -387,150 +416,112 @@ __device__ __forceinline__ uint32_t warp_filter_ids(uint32_t *buf, uint32_t T, u
 
 // ------------------------------------------------------------------ the lookup kernel's body --
 constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer
-constexpr int kHashSlots = 512;      // counting table of the common path: 512 keys + 512 counters (same buffer)
-constexpr int kHashMaxIds = 256;     // ... for up to this many gathered ids (load factor <= 0.5)
-static_assert(kHashMaxIds >= kWarpFilterBuckets / 2, "the sort path keeps its filter counters in the result area");
-constexpr int kWarpWords = kLookupCap + kHashMaxIds + 32;   // + result list + a few scalars
+constexpr int kResWords = 256;       // result list of the register path / filter counters of the sort path
+constexpr int kRegListsMax = 4;      // lists per lane that are probed once and kept in registers (n <= 128; 2 for n <= 64)
+static_assert(kResWords >= kWarpFilterBuckets / 2, "the sort path keeps its filter counters in the result area");
+static_assert(kResWords >= 32 * kRegListsMax, "thr <= 1: every gathered id is a result");
+constexpr int kWarpWords = kLookupCap + kResWords + 32;
 constexpr int kLookupWarps = 8;
+
+constexpr int kFixedIds = 16;        // result ids per query that have a fixed place in tmp_ids
 
 struct CountArgs {
     uint32_t *qcount;        // [nq+1] result ids per query
     uint64_t *qpos;          // [nq]   where the query's results start in tmp_ids (~0: heavy query)
-    uint32_t *tmp_ids;       // results in completion order
-    uint64_t tmp_cap;
+    // Results before the prefix sum: query q owns tmp_ids[q * kFixedIds ..); a query with more results
+    // takes a range behind those nq * kFixedIds entries from a cursor.  (With one cursor for everything every
+    // query waited for the round trip of an atomic on ONE address before it could store its results.)
+    uint32_t *tmp_ids;
+    uint64_t tmp_cap;        // entries, >= nq * kFixedIds
     uint32_t *heavy_list;    // [nq]
-    unsigned long long *counters;   // [0] heavy queries, [1] gathered ids, [2] result ids (tmp cursor)
+    unsigned long long *counters;   // [0] heavy queries, [1] gathered ids, [2] result ids, [3] cursor behind the fixed places
     uint32_t nq, thr;
 };
 
-// counting table: one more occurrence of `id`; the lane that brings the count to `thr` emits it
-__device__ __forceinline__ void count_id(uint32_t *keys, uint32_t *cnts, uint32_t *res, uint32_t *rcount,
-                                         uint32_t id, uint32_t thr) {
-    uint32_t h = (id * 0x9E3779B1u) >> 23;      // 9 bits = kHashSlots
-    for (;;) {
-        const uint32_t prev = atomicCAS(keys + h, kNoId, id);
-        if (prev == kNoId || prev == id) break;
-        h = (h + 1) & (kHashSlots - 1);
-    }
-    if (atomicAdd(cnts + h, 1u) + 1u == thr) res[atomicAdd(rcount, 1u)] = id;
-}
-
-// One warp per query, ONE pass.  Common case (<= kHashMaxIds gathered ids): the ids are counted
-// in a warp-private shared-memory hash table as they arrive and an id is emitted the moment its
-// count reaches the threshold; the handful of results is sorted with warp shuffles.  Larger
-// queries (<= kLookupCap ids) are laid out, sorted with a bitonic network and run-length
-// thresholded.  Results go to tmp_ids in completion order; a prefix sum over qcount and
-// csr_place_kernel then produce the CSR.  Queries beyond kLookupCap take the global path.
-template <typename Src>
+// One warp per query, ONE pass.
+//   gather     up to 32 * kRegLists lists are probed once, kRegLists per lane, all loads in flight together
+//   registers  <= 32 * kRegLists gathered ids (every list a single id, or laid out through the buffer): counted
+//              with warp votes - the lowest lane that still holds an id broadcasts it, one ballot per
+//              register says who else holds it, the population count is its multiplicity; one round
+//              per DISTINCT id, no shared-memory traffic (the first version counted in a shared-memory
+//              hash table: 2 atomics per id at 2 cycles per lane made the shared-memory pipe, not the
+//              DRAM latency of the probes, the kernel's bound)
+//   sort path  <= kLookupCap ids: laid out, counting filter in place, bitonic sort, run lengths
+//   beyond     handed to the counting-filter tier / the global path
+// Results go to tmp_ids in completion order; a prefix sum over qcount and csr_place_kernel then
+// produce the CSR.
+template <typename Src, int kRegLists = kRegListsMax>
 __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf) {
+    constexpr int kRegMaxIds = 32 * kRegLists;   // gathered ids that are counted in registers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *buf = s_buf + (size_t)warp * kWarpWords;
-    uint32_t *keys = buf, *cnts = buf + kHashSlots;
-    uint32_t *res = buf + kLookupCap;           // kHashMaxIds entries
-    uint32_t *rcount = res + kHashMaxIds;
+    uint32_t *res = buf + kLookupCap;           // kResWords entries
     const uint32_t total_warps = gridDim.x * kLookupWarps;
     const uint32_t subs = src.subs();
-    unsigned long long pairs_local = 0;
+    const bool keep_lists = subs <= (uint32_t)kRegMaxIds;
+    unsigned long long pairs_local = 0, results_local = 0;
 
     for (uint32_t q = blockIdx.x * kLookupWarps + warp; q < a.nq; q += total_warps) {
-        // ---- common path: count while gathering ----
-        {
-            uint4 *k4 = reinterpret_cast<uint4 *>(keys);
-            uint4 *c4 = reinterpret_cast<uint4 *>(cnts);
+        if (q + total_warps < a.nq) src.prefetch(q + total_warps, lane);    // the next query's keys, into L2
+        ListRef r[kRegLists];
+        uint32_t v[kRegLists];
+        uint32_t T = 0xFFFFFFFFu;           // gathered ids (saturating)
+        bool in_regs = false;
+        if (keep_lists) {
+            typename Src::Pending pend[kRegLists];
 #pragma unroll
-            for (int i = 0; i < kHashSlots / 4 / 32; ++i) {
-                k4[i * 32 + lane] = make_uint4(kNoId, kNoId, kNoId, kNoId);
-                c4[i * 32 + lane] = make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < kRegLists; ++c)
+                if (c * 32 + lane < (int)subs) pend[c] = src.begin(q, c * 32 + lane);
+            unsigned long long mine = 0;
+            bool multi = false;
+#pragma unroll
+            for (int c = 0; c < kRegLists; ++c) {
+                r[c] = c * 32 + lane < (int)subs ? src.finish(pend[c]) : empty_list();
+                mine += r[c].c;
+                multi |= r[c].c > 1;
+                v[c] = r[c].c == 1 ? (r[c].ptr ? r[c].ptr[0] : r[c].one) : kNoId;
             }
-            if (lane == 0) *rcount = 0;
-        }
-        __syncwarp();
-        uint32_t T = 0;
-        bool small = true;
-        for (uint32_t j0 = 0; j0 < subs && small; j0 += 64) {
-            const uint32_t ja = j0 + lane, jb = j0 + 32 + lane;
-            typename Src::Pending pa, pb;
-            if (ja < subs) pa = src.begin(q, ja);
-            if (jb < subs) pb = src.begin(q, jb);
-            ListRef r[2];
-            r[0] = ja < subs ? src.finish(pa) : empty_list();
-            r[1] = jb < subs ? src.finish(pb) : empty_list();
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint32_t rt = r[h].c;
-#pragma unroll
-                for (int o = 16; o; o >>= 1) rt += __shfl_xor_sync(0xffffffffu, rt, o);
-                T = (uint64_t)T + rt > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + rt;
-                if (T > kHashMaxIds) { small = false; break; }
-                if (r[h].c == 1) count_id(keys, cnts, res, rcount, r[h].ptr ? r[h].ptr[0] : r[h].one, a.thr);
-                else if (r[h].c > 1 && r[h].c <= 8)
-                    for (uint32_t i = 0; i < r[h].c; ++i) count_id(keys, cnts, res, rcount, r[h].ptr[i], a.thr);
-                uint32_t big = __ballot_sync(0xffffffffu, r[h].c > 8);
-                while (big) {
-                    const int sl = __ffs(big) - 1;
-                    big &= big - 1;
-                    const uint32_t *bp = reinterpret_cast<const uint32_t *>(
-                        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r[h].ptr), sl));
-                    const uint32_t bc = __shfl_sync(0xffffffffu, r[h].c, sl);
-                    for (uint32_t i = lane; i < bc; i += 32) count_id(keys, cnts, res, rcount, bp[i], a.thr);
-                }
-            }
+            for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+            T = mine > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)mine;
+            in_regs = T <= (uint32_t)kRegMaxIds && !__any_sync(0xffffffffu, multi);
         }
-        __syncwarp();
         uint32_t R = 0;
         const uint32_t *out = res;
-        if (small) {
-            R = *rcount;
-            if (R > 1 && R <= 32) {
-                // shuffle bitonic sort of up to 32 results
-                uint32_t v = lane < (int)R ? res[lane] : kNoId;
-#pragma unroll
-                for (int kk = 2; kk <= 32; kk <<= 1) {
-#pragma unroll
-                    for (int j = kk >> 1; j > 0; j >>= 1) {
-                        const uint32_t o = __shfl_xor_sync(0xffffffffu, v, j);
-                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
-                        v = (lower == up) ? min(v, o) : max(v, o);
-                    }
-                }
-                __syncwarp();
-                if (lane < (int)R) res[lane] = v;
-                __syncwarp();
-            } else if (R > 32) {
-                uint32_t P = 64;
-                while (P < R) P <<= 1;
-                for (uint32_t i = R + lane; i < P; i += 32) res[i] = kNoId;
-                __syncwarp();
-                warp_bitonic_smem(res, P, lane);
-            }
-        } else {
-            // ---- sort path: lay the lists out in the buffer (the counting table is abandoned) ----
+        if (!in_regs) {
+            // ---- lay the lists out in the buffer ----
             T = 0;
-            for (uint32_t j0 = 0; j0 < subs; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                const ListRef r = j < subs ? src.get(q, j) : empty_list();
-                const uint32_t incl = warp_incl_scan(r.c, lane);
+            __syncwarp();                   // the previous query's results have left the buffer
+            auto lay = [&](const ListRef &rr) {
+                const uint32_t incl = warp_incl_scan(rr.c, lane);
                 const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
-                const uint32_t off = T + incl - r.c;
+                const uint32_t off = T + incl - rr.c;
                 if ((uint64_t)T + round_total <= kLookupCap) {
-                    if (r.c == 1) buf[off] = r.ptr ? r.ptr[0] : r.one;
-                    else if (r.c > 1 && r.c <= 8)
-                        for (uint32_t i = 0; i < r.c; ++i) buf[off + i] = r.ptr[i];
-                    uint32_t big = __ballot_sync(0xffffffffu, r.c > 8);
+                    if (rr.c == 1) buf[off] = rr.ptr ? rr.ptr[0] : rr.one;
+                    else if (rr.c > 1 && rr.c <= 8)
+                        for (uint32_t i = 0; i < rr.c; ++i) buf[off + i] = rr.ptr[i];
+                    uint32_t big = __ballot_sync(0xffffffffu, rr.c > 8);
                     while (big) {
                         const int sl = __ffs(big) - 1;
                         big &= big - 1;
                         const uint32_t *bp = reinterpret_cast<const uint32_t *>(
-                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(r.ptr), sl));
-                        const uint32_t bc = __shfl_sync(0xffffffffu, r.c, sl);
+                            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(rr.ptr), sl));
+                        const uint32_t bc = __shfl_sync(0xffffffffu, rr.c, sl);
                         const uint32_t bo = __shfl_sync(0xffffffffu, off, sl);
                         for (uint32_t i = lane; i < bc; i += 32) buf[bo + i] = bp[i];
                     }
                 }
                 // saturate: the sum of the list sizes can exceed 32 bits only in theory
                 T = (uint64_t)T + round_total > 0xFFFFFFFFull ? 0xFFFFFFFFu : T + round_total;
+            };
+            if (keep_lists) {
+#pragma unroll
+                for (int c = 0; c < kRegLists; ++c)
+                    if (c * 32 < (int)subs) lay(r[c]);
+            } else {
+                for (uint32_t j0 = 0; j0 < subs; j0 += 32) lay(j0 + lane < subs ? src.get(q, j0 + lane) : empty_list());
             }
-            if (T > kLookupCap) {                     // global path handles this query
+            if (T > kLookupCap) {                     // the next tier handles this query
                 pairs_local += lane == 0 ? T : 0;
                 if (lane == 0) {
                     a.qcount[q] = 0;
@@ -540,13 +531,64 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
                 __syncwarp();
                 continue;
             }
-            // ids whose counting-filter bucket stays below the threshold cannot qualify: drop them
-            // before sorting (query_kernels.cuh; `res` is unused on this path and holds the counters)
-            uint32_t Ts = T;
-            if (a.thr > 1 && T > 64) {
-                __syncwarp();
-                Ts = warp_filter_ids(buf, T, a.thr, res, lane);
+            __syncwarp();
+            if (T <= (uint32_t)kRegMaxIds) {
+#pragma unroll
+                for (int c = 0; c < kRegLists; ++c) v[c] = c * 32 + lane < (int)T ? buf[c * 32 + lane] : kNoId;
+                in_regs = true;
             }
+        }
+        if (in_regs) {
+            // ---- count in registers: one round per distinct id ----
+            uint32_t rem[kRegLists];
+#pragma unroll
+            for (int c = 0; c < kRegLists; ++c) rem[c] = __ballot_sync(0xffffffffu, v[c] != kNoId);
+#pragma unroll
+            for (int c = 0; c < kRegLists; ++c) {
+                while (rem[c]) {
+                    const uint32_t id = __shfl_sync(0xffffffffu, v[c], __ffs(rem[c]) - 1);
+                    uint32_t cnt = 0;
+#pragma unroll
+                    for (int d = c; d < kRegLists; ++d) {       // earlier registers hold no id that is still uncounted
+                        const uint32_t eq = __ballot_sync(0xffffffffu, v[d] == id);
+                        cnt += __popc(eq);
+                        rem[d] &= ~eq;
+                    }
+                    if (cnt >= a.thr) {
+                        if (lane == 0) res[R] = id;
+                        ++R;
+                    }
+                }
+            }
+            __syncwarp();
+            if (R > 1 && R <= 32) {
+                // shuffle bitonic sort of up to 32 results
+                uint32_t w = lane < (int)R ? res[lane] : kNoId;
+#pragma unroll
+                for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+                    for (int j = kk >> 1; j > 0; j >>= 1) {
+                        const uint32_t o = __shfl_xor_sync(0xffffffffu, w, j);
+                        const bool up = (lane & kk) == 0, lower = (lane & j) == 0;
+                        w = (lower == up) ? min(w, o) : max(w, o);
+                    }
+                }
+                __syncwarp();
+                if (lane < (int)R) res[lane] = w;
+                __syncwarp();
+            } else if (R > 32) {
+                uint32_t P = 64;
+                while (P < R) P <<= 1;
+                for (uint32_t i = R + lane; i < P; i += 32) res[i] = kNoId;
+                __syncwarp();
+                warp_bitonic_smem(res, P, lane);
+            }
+        } else {
+            // ---- sort path ----
+            // ids whose counting-filter bucket stays below the threshold cannot qualify: drop them
+            // before sorting (`res` holds the counters)
+            uint32_t Ts = T;
+            if (a.thr > 1 && T > 64) Ts = warp_filter_ids(buf, T, a.thr, res, lane);
             uint32_t P = 32;
             while (P < Ts) P <<= 1;
             for (uint32_t i = Ts + lane; i < P; i += 32) buf[i] = kNoId;
@@ -556,15 +598,15 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
             for (uint32_t i0 = 0; i0 < Ts; i0 += 32) {
                 const uint32_t i = i0 + lane;
                 bool ok = false;
-                uint32_t v = 0;
+                uint32_t w = 0;
                 if (i < Ts) {
-                    v = buf[i];
-                    const bool head = i == 0 || buf[i - 1] != v;
-                    ok = head && (a.thr <= 1 || (i + a.thr - 1 < Ts && buf[i + a.thr - 1] == v));
+                    w = buf[i];
+                    const bool head = i == 0 || buf[i - 1] != w;
+                    ok = head && (a.thr <= 1 || (i + a.thr - 1 < Ts && buf[i + a.thr - 1] == w));
                 }
                 const uint32_t m = __ballot_sync(0xffffffffu, ok);
                 __syncwarp();       // every read of this round happens before its writes (R <= i0)
-                if (ok) buf[R + __popc(m & ((1u << lane) - 1))] = v;
+                if (ok) buf[R + __popc(m & ((1u << lane) - 1))] = w;
                 R += __popc(m);
                 __syncwarp();
             }
@@ -572,18 +614,22 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
         }
         pairs_local += lane == 0 ? T : 0;
         // ---- hand the results over ----
-        unsigned long long base = 0;
+        unsigned long long base = (unsigned long long)q * kFixedIds;
+        if (R > (uint32_t)kFixedIds) {
+            if (lane == 0) base = (unsigned long long)a.nq * kFixedIds + atomicAdd(a.counters + 3, (unsigned long long)R);
+            base = __shfl_sync(0xffffffffu, base, 0);
+        }
         if (lane == 0) {
-            if (R) base = atomicAdd(a.counters + 2, (unsigned long long)R);
             a.qcount[q] = R;
             a.qpos[q] = base;
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
+        results_local += lane == 0 ? R : 0;
         if (base + R <= a.tmp_cap)
             for (uint32_t i = lane; i < R; i += 32) a.tmp_ids[base + i] = out[i];
         __syncwarp();
     }
     if (lane == 0 && pairs_local) atomicAdd(a.counters + 1, pairs_local);
+    if (lane == 0 && results_local) atomicAdd(a.counters + 2, results_local);
 }
 
 // ------------------------------------------------------------------ counting-filter tier --

@@ -74,12 +74,12 @@ int build_tables(nsmh_ctx *c) {
     NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_insert_kernel, kBuildRows, 0));
     const uint64_t units = (uint64_t)((rows + kBuildRows - 1) / kBuildRows) * ((n + kBuildCols - 1) / kBuildCols);
     const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(units, (uint64_t)c->num_sms * (occ > 0 ? occ : 1)));
-    const uint32_t seg_cap = (uint32_t)((units + blocks - 1) / blocks) * kBuildRows * kBuildCols;
-    const size_t nseg = (size_t)blocks * seg_cap;
+    const uint32_t seg_cap = kBuildRows * kBuildCols;           // one segment per work unit
+    const size_t nseg = (size_t)units * seg_cap;
     NSMH_TRY(T.slots.ensure(nslots * sizeof(Slot), s));
     NSMH_TRY(T.ids.ensure(ni * sizeof(uint32_t), s));
     NSMH_TRY(c->build_multi.ensure(std::max<size_t>(nseg, 1) * 4 * sizeof(uint32_t), s));
-    NSMH_TRY(c->build_tmp.ensure((8 + 2 * (size_t)blocks) * sizeof(unsigned int), s));
+    NSMH_TRY(c->build_tmp.ensure((8 + 2 * (size_t)units) * sizeof(unsigned int), s));
     if (!(c->precleared_rows == rows && c->precleared_ptr == T.slots.p))         // else: cleared during nsmh_sketch
         NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), s));
     c->precleared_rows = 0;
@@ -99,12 +99,12 @@ int build_tables(nsmh_ctx *c) {
         a.rows = rows;
         a.n = n;
         a.seg_cap = seg_cap;
-        a.segments = blocks;
+        a.segments = (uint32_t)units;
         table_insert_kernel<<<blocks, kBuildRows, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
-        table_groups_kernel<<<c->num_sms * 2, 256, 0, s>>>(a);
+        table_groups_kernel<<<c->num_sms * 4, 256, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
-        table_fill_kernel<<<c->num_sms * 2, 256, 0, s>>>(a);
+        table_fill_kernel<<<c->num_sms * 4, 256, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
         c->launches += 3;
     }

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "nsmh_constants.h"
+#include "nsmh_ldst.cuh"
 
 namespace nsmh {
 
@@ -17,12 +18,12 @@ struct BuildArgs {
     const uint64_t *sk;     // [rows][n]
     Slot *slots;            // [n][cap+1]
     uint32_t *ids;
-    // Members that arrived second or later, and the slots of their groups.  Every block of
+    // Members that arrived second or later, and the slots of their groups.  Every work unit of
     // the insert kernel appends to its own segment of seg_cap entries (shared-memory cursor):
     // a single global cursor would serialise ~10^5 same-address atomics per build.
     uint32_t *m_slot, *m_id, *m_rank;
     uint32_t *g_slot;
-    unsigned int *counters;             // [0] ids cursor
+    unsigned int *counters;             // [0] ids cursor, [1] next work unit of the insert kernel
     unsigned int *seg_count;            // [2*segments] members, groups of every segment
     uint64_t cap;
     uint32_t rows, n, seg_cap, segments;
@@ -94,11 +95,28 @@ table_insert_kernel(BuildArgs a) {
     const uint32_t units = chunks * colgroups;     // < 2^32: checked by build_tables
     const uint64_t nb = a.cap >> 1;
     const uint64_t stride = region_stride(a.cap);
-    const size_t seg0 = (size_t)blockIdx.x * a.seg_cap;
+    __shared__ unsigned int s_unit;
     if (threadIdx.x < 2) s_count[threadIdx.x] = 0;
-    __syncthreads();
 
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+    // Units are handed out dynamically, in order (the regions in use at any time stay few and L2 resident;
+    // a static round-robin left 17 % of the warp samples of the first version waiting at the exit).
+    // Every unit appends to its own segment of seg_cap = rows x columns entries.
+    uint32_t prev = 0xFFFFFFFFu;
+    for (;;) {
+        __syncthreads();                    // the previous unit's appends are done, everybody has read s_unit
+        if (threadIdx.x == 0) {
+            if (prev != 0xFFFFFFFFu) {
+                a.seg_count[2 * (size_t)prev] = s_count[0];
+                a.seg_count[2 * (size_t)prev + 1] = s_count[1];
+                s_count[0] = s_count[1] = 0;
+            }
+            s_unit = atomicAdd(a.counters + 1, 1u);
+        }
+        __syncthreads();
+        const uint32_t u = s_unit;
+        if (u >= units) break;
+        prev = u;
+        const size_t seg0 = (size_t)u * a.seg_cap;
         const uint32_t cg = u / chunks;
         const uint32_t row = (u - cg * chunks) * kBuildRows + threadIdx.x;
         const uint32_t l0 = cg * kBuildCols;
@@ -107,7 +125,82 @@ table_insert_kernel(BuildArgs a) {
 #pragma unroll
         for (int j = 0; j < kBuildCols; ++j)
             keys[j] = (uint32_t)j < nj ? __ldg(a.sk + (size_t)row * a.n + l0 + j) : 0;
+        // ---- fast round: the home buckets of all keys are peeked together, then all claims go out together,
+        // so a thread waits for two memory round trips per unit instead of two per key (the kernel is bound
+        // by the latency of these dependent accesses, not by their number).  What the round cannot settle
+        // (home bucket full, a slot lost to another key meanwhile) is left to the loop below.
+        bool done[kBuildCols];
+        uint32_t frank[kBuildCols], fslot[kBuildCols];
+        {
+            uint64_t hk0[kBuildCols], hk1[kBuildCols], got[kBuildCols];
+            uint32_t hb[kBuildCols];
+            int state[kBuildCols];          // 0 nothing, 1 claim sent, 2 the key is there already
+#pragma unroll
+            for (int jj = 0; jj < kBuildCols; ++jj) {
+                done[jj] = false;
+                frank[jj] = fslot[jj] = 0;
+                state[jj] = 0;
+                hk0[jj] = hk1[jj] = 0;
+                hb[jj] = 0;
+                if ((uint32_t)jj < nj && keys[jj] != kEmptyKey) {
+                    uint64_t v0, v1;
+                    hb[jj] = (uint32_t)slot_index(keys[jj], nb);
+                    bucket_now(a.slots + (uint64_t)(l0 + jj) * stride + 2 * (uint64_t)hb[jj], hk0[jj], v0, hk1[jj], v1);
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < kBuildCols; ++jj) {
+                got[jj] = 0;
+                if ((uint32_t)jj < nj && keys[jj] != kEmptyKey) {
+                    const uint64_t key = keys[jj];
+                    const int t = (hk0[jj] == key || hk0[jj] == kEmptyKey) ? 0 : (hk1[jj] == key || hk1[jj] == kEmptyKey) ? 1 : 2;
+                    if (t != 2) {
+                        Slot *p = a.slots + (uint64_t)(l0 + jj) * stride + 2 * (uint64_t)hb[jj] + t;
+                        fslot[jj] = (uint32_t)(p - a.slots);
+                        if ((t ? hk1[jj] : hk0[jj]) == kEmptyKey) {
+                            uint64_t old_hi;
+                            slot_cas(p, ~0ULL, ~0ULL, key, (uint64_t)row, got[jj], old_hi);   // {key, val = id, cnt-1 = 0}
+                            state[jj] = 1;
+                        } else {
+                            state[jj] = 2;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < kBuildCols; ++jj) {
+                if (state[jj] == 1) {
+                    if (got[jj] == kEmptyKey) done[jj] = true;                 // rank 0: first of its group
+                    else if (got[jj] == keys[jj]) state[jj] = 2;               // the same key arrived meanwhile
+                }
+                if (state[jj] == 2) {
+                    frank[jj] = atomicAdd(&a.slots[fslot[jj]].cntm1, 1u) + 1u;
+                    done[jj] = true;
+                }
+            }
+        }
+        // members that were not first in their group (warp-aggregated append, as in the loop below)
+#pragma unroll
+        for (int jj = 0; jj < kBuildCols; ++jj) {
+            const bool member = done[jj] && frank[jj] >= 1;
+            const uint32_t m = __ballot_sync(0xffffffffu, member);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(&s_count[0], (unsigned int)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (member) {
+                    const size_t pos = seg0 + base + __popc(m & ((1u << lane) - 1));
+                    a.m_slot[pos] = fslot[jj];
+                    a.m_id[pos] = row;
+                    a.m_rank[pos] = frank[jj];
+                    if (frank[jj] == 1) a.g_slot[seg0 + atomicAdd(&s_count[1], 1u)] = fslot[jj];
+                }
+            }
+        }
         uint32_t j = 0;
+        while (j < nj && (j == 0 ? done[0] : j == 1 ? done[1] : j == 2 ? done[2] : done[3])) ++j;
+        if (__all_sync(0xffffffffu, j >= nj)) continue;
         bool fresh = true;        // the current key has not been probed yet
         uint64_t key = 0, b = 0;
         Slot *region = a.slots;
@@ -156,7 +249,7 @@ table_insert_kernel(BuildArgs a) {
                 }
                 if (completed) {
                     s = (uint32_t)(p - a.slots);
-                    ++j;
+                    do ++j; while (j < nj && (j == 1 ? done[1] : j == 2 ? done[2] : j == 3 ? done[3] : false));
                     fresh = true;
                 }
             }
@@ -178,20 +271,19 @@ table_insert_kernel(BuildArgs a) {
             if (__all_sync(0xffffffffu, j >= nj)) break;
         }
     }
-    __syncthreads();
-    if (threadIdx.x < 2) a.seg_count[2 * blockIdx.x + threadIdx.x] = s_count[threadIdx.x];
 }
 
-// groups of two or more: allocate the id range, move the inlined first id into it
+// groups of two or more: allocate the id range, move the inlined first id into it.
+// A warp per segment (one per work unit of the insert kernel, most of them nearly empty).
 __global__ void __launch_bounds__(256)
 table_groups_kernel(BuildArgs a) {
     const int lane = threadIdx.x & 31;
-    for (uint32_t seg = blockIdx.x; seg < a.segments; seg += gridDim.x) {
-        const uint32_t groups = a.seg_count[2 * seg + 1];
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < a.segments; seg += warps) {
+        const uint32_t groups = a.seg_count[2 * (size_t)seg + 1];
         const uint32_t *g_slot = a.g_slot + (size_t)seg * a.seg_cap;
-        const uint32_t rounds = (groups + blockDim.x - 1) / blockDim.x;
-        uint32_t g = threadIdx.x;
-        for (uint32_t r = 0; r < rounds; ++r, g += blockDim.x) {   // whole warps stay in the loop for the shuffles
+        for (uint32_t g0 = 0; g0 < groups; g0 += 32) {        // whole warps stay in the loop for the shuffles
+            const uint32_t g = g0 + lane;
             uint32_t need = 0, s = 0;
             if (g < groups) {
                 s = g_slot[g];
@@ -220,10 +312,12 @@ table_groups_kernel(BuildArgs a) {
 
 __global__ void __launch_bounds__(256)
 table_fill_kernel(BuildArgs a) {
-    for (uint32_t seg = blockIdx.x; seg < a.segments; seg += gridDim.x) {
-        const uint32_t members = a.seg_count[2 * seg];
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t seg = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); seg < a.segments; seg += warps) {
+        const uint32_t members = a.seg_count[2 * (size_t)seg];
         const size_t seg0 = (size_t)seg * a.seg_cap;
-        for (uint32_t i = threadIdx.x; i < members; i += blockDim.x)
+        for (uint32_t i = lane; i < members; i += 32)
             a.ids[a.slots[a.m_slot[seg0 + i]].val + a.m_rank[seg0 + i]] = a.m_id[seg0 + i];
     }
 }

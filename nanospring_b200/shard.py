@@ -168,14 +168,19 @@ class PartitionedFilter:
         for r in range(world):
             pieces.append(counts[int(bounds[r]):int(bounds[r + 1])])
             pieces.append(sizes[r:r + 1])
-        send_cnt = torch.cat(pieces).to(torch.int32)
-        cnt_recv = torch.empty(world * (n_local + 1), dtype=torch.int32, device=dev)
+        # int64 on the wire: a segment's total can pass 2^31 ids long before a single read's count does
+        # (k = 15, n = 120 gathers ~800 ids per read), and a wrapped total would give the ranks
+        # disagreeing split sizes for the id exchange below
+        send_cnt = torch.cat(pieces).to(torch.int64)
+        cnt_recv = torch.empty(world * (n_local + 1), dtype=torch.int64, device=dev)
         dist.all_to_all_single(cnt_recv, send_cnt, [n_local + 1] * world, [r + 1 for r in rows], group=self.group)
         cnt_recv = cnt_recv.view(world, n_local + 1)
-        both = torch.cat([sizes, cnt_recv[:, n_local].to(torch.int64)]).cpu().tolist()
+        both = torch.cat([sizes.to(torch.int64), cnt_recv[:, n_local]]).cpu().tolist()
         send_sizes, recv_sizes = both[:world], both[world:]
         part_offs = torch.zeros((world, n_local + 1), dtype=torch.int64, device=dev)
         torch.cumsum(cnt_recv[:, :n_local], dim=1, out=part_offs[:, 1:])
+        if max([0] + [int(x) for x in send_sizes + recv_sizes]) >= 2**31:
+            raise ValueError("id exchange: more than 2^31-1 ids between one pair of ranks; use more ranks or the peer-memory path")
         ids_recv = torch.empty(max(int(sum(recv_sizes)), 1), dtype=torch.int32, device=dev)
         dist.all_to_all_single(ids_recv[:int(sum(recv_sizes))], ids, [int(x) for x in recv_sizes],
                                [int(x) for x in send_sizes], group=self.group)

@@ -23,7 +23,7 @@ extern "C" {
 
 // S [total_rows][n]: the global sketch matrix, rows of rank r = [sum(rows[:r]), ...).  Per-rank outputs are
 // concatenated in rank order: qcount [total_rows + world] (rank r's block has rows[r] + 1 entries),
-// qpos [total_rows], tmp [world][tmp_cap], heavy [total_rows + world], counters [world][3].
+// qpos [total_rows], tmp [world][tmp_cap], heavy [total_rows + world], counters [world][4].
 // Returns 0; -1 when the world does not fit (more ranks than hash functions).
 int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_t n, uint32_t thr,
                 long long inbox_cap_override, unsigned grid, uint32_t *qcount, uint64_t *qpos, uint32_t *tmp,
@@ -49,8 +49,6 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         memset(arena[r] + lay[r].off_flags, 0, (3 * kMgMaxRanks + 8) * sizeof(uint32_t));   // ... but the flags / cursors
     }
     // ---- stage 1: scatter the sketch columns to their owners ----
-    bool by4 = (n & 3) == 0;
-    for (uint32_t r = 0; r < world; ++r) by4 = by4 && (col_end[r] & 3) == 0;
     for (uint32_t r = 0; r < world; ++r) {
         if (!rows[r]) continue;
         ScatterArgs sa;
@@ -61,8 +59,8 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         sa.world = world;
         sa.row0 = r ? row_end[r - 1] : 0u;
         const uint64_t *Sr = S + (size_t)sa.row0 * n;
-        if (by4) emu_launch(grid, 256, [&] { mg_scatter_columns4_kernel(Sr, rows[r], n, sa); });
-        else emu_launch(grid, 256, [&] { mg_scatter_columns_kernel(Sr, rows[r], n, sa); });
+        std::vector<uint64_t> tile((size_t)kScatterRows * n + 2, 0xA5A5A5A5A5A5A5A5ull);
+        emu_launch_block(grid, 256, [&] { mg_scatter_columns_kernel(Sr, rows[r], n, sa, reinterpret_cast<uint8_t *>(tile.data())); });
     }
     // ---- stage 2: every owner builds its tables over all rows ----
     const uint64_t cap = std::max<uint64_t>(16, 2ULL * total_rows);
@@ -74,10 +72,10 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         if (!total_rows) continue;
         const uint64_t units = (uint64_t)((total_rows + kBuildRows - 1) / kBuildRows) * ((ncols + kBuildCols - 1) / kBuildCols);
         const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(units, 3));
-        const uint32_t seg_cap = (uint32_t)((units + blocks - 1) / blocks) * kBuildRows * kBuildCols;
-        const size_t nseg = (size_t)blocks * seg_cap;
+        const uint32_t seg_cap = kBuildRows * kBuildCols;           // one segment per work unit
+        const size_t nseg = (size_t)units * seg_cap;
         std::vector<uint32_t> multi(std::max<size_t>(nseg, 1) * 4, 0);
-        std::vector<unsigned int> btmp(8 + 2 * (size_t)blocks, 0);
+        std::vector<unsigned int> btmp(8 + 2 * (size_t)units, 0);
         BuildArgs a;
         a.sk = reinterpret_cast<const uint64_t *>(arena[r] + lay[r].off_m);
         a.slots = slots[r].data();
@@ -92,7 +90,7 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         a.rows = total_rows;
         a.n = ncols;
         a.seg_cap = seg_cap;
-        a.segments = blocks;
+        a.segments = (uint32_t)units;
         emu_launch_block(blocks, kBuildRows, [&] { table_insert_kernel(a); });
         emu_launch(2, 256, [&] { table_groups_kernel(a); });
         emu_launch(2, 256, [&] { table_fill_kernel(a); });
@@ -120,7 +118,7 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         pd.world = world;
         pd.col0 = col0;
         pd.ncols = ncols;
-        emu_launch(grid, kProbeRows, [&] { probe_to_peers_kernel(src, total_rows, pd); });
+        emu_launch_block(grid, kProbeRows, [&] { probe_to_peers_kernel(src, total_rows, pd); });
     }
     // ---- stage 4: every rank thresholds its own reads ----
     size_t qc_off = 0, q_off = 0;
@@ -142,7 +140,7 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         a.tmp_ids = tmp + (size_t)r * tmp_cap;
         a.tmp_cap = tmp_cap;
         a.heavy_list = heavy + qc_off;
-        a.counters = counters + 3 * (size_t)r;
+        a.counters = counters + 4 * (size_t)r;
         a.nq = rows[r];
         a.thr = thr ? thr : 1;
         if (rows[r]) {

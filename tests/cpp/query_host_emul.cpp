@@ -18,6 +18,7 @@ struct CsrSrc {
     const uint32_t *ids;
     uint32_t nsubs;
     uint32_t subs() const { return nsubs; }
+    void prefetch(uint32_t, int) const {}
     struct Pending {
         uint32_t q, j;
     };
@@ -74,7 +75,10 @@ void mid_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, ui
 }
 
 // The whole lookup kernel body (count_body = what count_kernel in query.cu wraps), blocks of
-// kLookupWarps warps.  qcount [nq+1], qpos [nq], heavy_list [nq], counters [3] zeroed by the caller.
+// kLookupWarps warps.  qcount [nq+1], qpos [nq], heavy_list [nq], counters [4] zeroed by the caller;
+// tmp_cap >= nq * kFixedIds (the fixed places), lookup_fixed_ids() returns kFixedIds.
+uint32_t lookup_fixed_ids() { return kFixedIds; }
+
 void count_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, uint32_t subs, uint32_t thr,
                     unsigned grid, uint32_t *qcount, uint64_t *qpos, uint32_t *tmp_ids, uint64_t tmp_cap,
                     uint32_t *heavy_list, unsigned long long *counters) {

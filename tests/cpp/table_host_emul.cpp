@@ -42,10 +42,10 @@ int table_emul_build(const uint64_t *sk, uint32_t rows, uint32_t n, unsigned max
     if (!items) return 0;
     const uint64_t units = (uint64_t)((rows + kBuildRows - 1) / kBuildRows) * ((n + kBuildCols - 1) / kBuildCols);
     const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(units, max_blocks));
-    const uint32_t seg_cap = (uint32_t)((units + blocks - 1) / blocks) * kBuildRows * kBuildCols;
-    const size_t nseg = (size_t)blocks * seg_cap;
+    const uint32_t seg_cap = kBuildRows * kBuildCols;           // one segment per work unit
+    const size_t nseg = (size_t)units * seg_cap;
     std::vector<uint32_t> multi(std::max<size_t>(nseg, 1) * 4, 0);
-    std::vector<unsigned int> tmp(8 + 2 * (size_t)blocks, 0);
+    std::vector<unsigned int> tmp(8 + 2 * (size_t)units, 0);
     BuildArgs a;
     a.sk = sk;
     a.slots = g_t.slots.data();
@@ -60,7 +60,7 @@ int table_emul_build(const uint64_t *sk, uint32_t rows, uint32_t n, unsigned max
     a.rows = rows;
     a.n = n;
     a.seg_cap = seg_cap;
-    a.segments = blocks;
+    a.segments = (uint32_t)units;
     emu_launch_block(blocks, kBuildRows, [&] { table_insert_kernel(a); });
     emu_launch(2, 256, [&] { table_groups_kernel(a); });
     emu_launch(2, 256, [&] { table_fill_kernel(a); });
@@ -76,7 +76,7 @@ uint32_t table_emul_num_keys(uint32_t j) {
 }
 
 // nq query sketches [nq][n] against the tables through the lookup kernel's body.  Outputs as in
-// count_emul_run (query_host_emul.cpp); counters [3] zeroed by the caller.
+// count_emul_run (query_host_emul.cpp); counters [4] zeroed by the caller.
 void table_emul_query(const uint64_t *qsk, uint32_t nq, uint32_t thr, unsigned grid, uint32_t *qcount, uint64_t *qpos,
                       uint32_t *tmp_ids, uint64_t tmp_cap, uint32_t *heavy_list, unsigned long long *counters) {
     ProbeSrc src;

@@ -193,22 +193,26 @@ def run_count(L, queries, subs, thr, grid=1, tmp_cap=None):
             off.append(off[-1] + len(l))
     ids = np.concatenate(flat + [np.zeros(1, np.uint32)])
     off = np.asarray(off, dtype=np.uint64)
-    cap = int(off[-1]) + 1 if tmp_cap is None else tmp_cap
+    L.lookup_fixed_ids.restype = C.c_uint32
+    fixed = nq * L.lookup_fixed_ids()       # every query owns kFixedIds entries, larger result lists follow
+    cap = fixed + (int(off[-1]) + 1 if tmp_cap is None else tmp_cap)
     qcount = np.full(nq + 1, 0xEEEEEEEE, dtype=np.uint32)
     qpos = np.full(nq, 0x1234, dtype=np.uint64)
     tmp = np.full(cap + 8, 0xDEADBEEF, dtype=np.uint32)
     heavy = np.full(nq + 1, 0xFFFFFFFF, dtype=np.uint32)
-    counters = (C.c_ulonglong * 3)(0, 0, 0)
+    counters = (C.c_ulonglong * 4)(0, 0, 0, 0)
     L.count_emul_run(off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p), nq, subs, thr, grid, qcount.ctypes.data_as(u32p),
                      qpos.ctypes.data_as(u64p), tmp.ctypes.data_as(u32p), cap, heavy.ctypes.data_as(u32p), counters)
     assert (tmp[cap:] == 0xDEADBEEF).all(), "wrote past tmp_cap"
     return qcount, qpos, tmp, heavy, counters
 
 
-@pytest.mark.parametrize("subs,thr", [(60, 6), (60, 1), (24, 2), (120, 12), (7, 7), (33, 0)])
+@pytest.mark.parametrize("subs,thr", [(60, 6), (60, 1), (24, 2), (120, 12), (7, 7), (33, 0), (128, 3), (200, 4)])
 def test_lookup_kernel_body_all_paths(emul, subs, thr):
-    """count_body: counting table (<= 256 gathered ids), filter + sort path (<= 1024), hand-over of larger
-    queries; results per query ascending and equal to sort-and-count; the counters add up."""
+    """count_body: counting in registers with warp votes (<= 128 gathered ids: straight from the probes when
+    every list is a single id, through the buffer otherwise), filter + sort path (<= 1024), hand-over of
+    larger queries, more than 128 lists per query (nothing kept in registers); results per query ascending
+    and equal to sort-and-count; the counters add up."""
     rng = np.random.default_rng(subs * 7 + thr)
     specs = [(0, 0, 0), (1, 1, subs), (3, 4, max(thr, 1)), (4, 40, max(thr, 1) + 1), (8, 3, subs // 2 + 1), (12, 0, 0),
              (16, 6, max(thr, 1)), (30, 2, subs), (90, 1, 1), (2, 45, subs), (1, 70, 3)]
@@ -231,9 +235,9 @@ def test_lookup_kernel_body_all_paths(emul, subs, thr):
         got = tmp[int(qpos[q]):int(qpos[q]) + int(qcount[q])]
         assert got.size == want.size and (got == want).all(), f"query {q} (T = {T[q]})"
         emitted += want.size
-        paths.add("table" if T[q] <= 256 else "sort")
+        paths.add("registers" if T[q] <= 128 else "sort")
     assert counters[2] == emitted
-    assert {"table", "sort"} <= paths
+    assert {"registers", "sort"} <= paths
 
 
 def test_lookup_kernel_body_result_buffer_too_small(emul):
@@ -243,8 +247,10 @@ def test_lookup_kernel_body_result_buffer_too_small(emul):
     subs, thr = 20, 1
     qs = [chance_query(rng, subs, 10, [], 0) for _ in range(6)]
     total = sum(expected(l, thr).size for l in qs)
-    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, tmp_cap=total // 3)
-    assert counters[2] == total and counters[0] == 0
-    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, tmp_cap=total)
+    big = sum(expected(l, thr).size for l in qs if expected(l, thr).size > emul.lookup_fixed_ids())
+    assert big > 0, "the case needs result lists beyond the fixed places"
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, tmp_cap=big // 3)
+    assert counters[2] == total and counters[3] == big and counters[0] == 0
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, tmp_cap=big)
     for q, lists in enumerate(qs):
         assert (tmp[int(qpos[q]):int(qpos[q]) + int(qcount[q])] == expected(lists, thr)).all()

@@ -33,15 +33,15 @@ def emul():
 
 def query_all(L, qsk, thr, grid=2):
     nq, n = qsk.shape
-    cap = max(nq * 64, nq * nq) + 1024           # every row can match every row of a small table
+    cap = 16 * nq + max(nq * 64, nq * nq) + 1024   # fixed places + every row can match every row of a small table
     qcount = np.zeros(nq + 1, dtype=np.uint32)
     qpos = np.zeros(nq, dtype=np.uint64)
     tmp = np.zeros(cap, dtype=np.uint32)
     heavy = np.zeros(nq + 1, dtype=np.uint32)
-    counters = (C.c_ulonglong * 3)(0, 0, 0)
+    counters = (C.c_ulonglong * 4)(0, 0, 0, 0)
     L.table_emul_query(np.ascontiguousarray(qsk).ctypes.data_as(u64p), nq, thr, grid, qcount.ctypes.data_as(u32p),
                        qpos.ctypes.data_as(u64p), tmp.ctypes.data_as(u32p), cap, heavy.ctypes.data_as(u32p), counters)
-    assert counters[2] <= cap
+    assert 16 * nq + counters[3] <= cap         # the fixed places + the larger result lists
     out = []
     handed_on = set(int(x) for x in heavy[:counters[0]])
     for q in range(nq):
