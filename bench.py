@@ -38,14 +38,16 @@ READS_PER_GPU = 100_000
 MEAN_LEN = 10_000
 RAND_SEED = 20261017
 GENOME_LEN = 50_000_000
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel on exactly this
-# workload (rank-0 shard, k=23 n=60), from the `ncu --set full` capture summarised in
-# profiles/r1_ncu_full_s4_summary.txt.  A recorded figure, not measured by this run.
-NCU_TRAFFIC_BYTES = {"sketch_filter_kernel": 300_792_000 + 38_677_504}
-NCU_TRAFFIC_SOURCE = "profiles/r1_ncu_full_s4_summary.txt (ncu --set full, one launch)"
-# smsp__inst_executed.sum of the same launch (the kernel is deterministic on this workload): with the
-# live kernel time it gives the fraction of the SMs' warp-instruction issue slots the kernel uses.
-NCU_WARP_INSTRUCTIONS = {"sketch_filter_kernel": 341_098_925}
+# Counters of ONE launch of the dominant kernel on exactly this workload (rank-0 shard, k=23 n=60) from an
+# `ncu --set full` capture: recorded figures, not measured by this run.  They live in a committed file that
+# names the commit and the capture they come from (profiles/ncu_counters.json); the kernel is deterministic
+# on this workload, so with the live kernel time they give utilisations.
+def recorded_counters():
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_counters.json")) as fh:
+            return json.load(fh)
+    except (OSError, ValueError):
+        return {}
 
 
 def log(*a):
@@ -260,6 +262,39 @@ def ingest_leg(local_rank, d_bases, offsets, steps, hbm_peak):
     return out
 
 
+def dnabitset_host(d_bases, offsets, chunk_reads=8192):
+    """The reads in the reference's DnaBitset form (dnaToBits.cpp:11-36: code (c&2)|((c&4)>>2), 4 bases per byte,
+    first base in bits 7..6, every read starts on a byte), built on the device and copied to pinned host memory.
+    Returns (uint8 numpy view of the pinned buffer, uint32 lengths)."""
+    import torch
+    n = offsets.size - 1
+    lens = np.diff(offsets.astype(np.int64))
+    nbytes = (lens + 3) // 4
+    boff = np.zeros(n + 1, dtype=np.int64)
+    boff[1:] = np.cumsum(nbytes)
+    out = torch.zeros(int(boff[-1]) + 4, dtype=torch.uint8, device="cuda")
+    for r0 in range(0, n, chunk_reads):
+        r1 = min(n, r0 + chunk_reads)
+        b0, b1 = int(offsets[r0]), int(offsets[r1])
+        if b1 == b0:
+            continue
+        c = d_bases[b0:b1].to(torch.int32)
+        code = (c & 2) | ((c & 4) >> 2)
+        L = torch.from_numpy(lens[r0:r1]).cuda()
+        # position of every base in the padded layout (4 * byte offset of its read + index inside the read)
+        shift = torch.from_numpy(4 * (boff[r0:r1] - boff[r0]) - (offsets[r0:r1].astype(np.int64) - b0)).cuda()
+        pos = torch.arange(b1 - b0, dtype=torch.int64, device="cuda") + torch.repeat_interleave(shift, L)
+        padded = torch.zeros(4 * int(boff[r1] - boff[r0]), dtype=torch.int32, device="cuda")
+        padded[pos] = code
+        q = padded.view(-1, 4)
+        out[int(boff[r0]):int(boff[r1])] = ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).to(torch.uint8)
+        del c, code, pos, padded, q
+    h = torch.empty(int(boff[-1]), dtype=torch.uint8, pin_memory=True)
+    h.copy_(out[:int(boff[-1])])
+    torch.cuda.synchronize()
+    return h.numpy(), lens.astype(np.uint32)
+
+
 # ------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -271,6 +306,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTQ-ingest side measurement (N=1 only)")
+    ap.add_argument("--no-legs", action="store_true", help="skip the side legs (other BASELINE configs, brute-force roofline)")
+    ap.add_argument("--no-parity", action="store_true", help="N>1: skip the parity checks of the multi-GPU result")
     ap.add_argument("--multi", default="auto", choices=["auto", "peer", "replicated", "partitioned"],
                     help="N>1: tables partitioned by hash function with exchanges over NVLink peer memory inside the "
                          "kernels (peer, default), the same with NCCL all-to-alls (partitioned), or NCCL all-gather "
@@ -450,6 +487,99 @@ def main():
     h2d = total_bases + offsets.nbytes
     d2h = off.nbytes + ids.nbytes
 
+    # ---- e2e with the reads 2-bit packed on the host, the reference's own in-memory / temp-file form
+    #      (DnaBitset, dnaToBits.cpp:11-36: 4 bases per byte, first base in bits 7..6, every read byte-aligned):
+    #      what the real caller's ReadData holds (ReadData.cpp:156-235), 4x fewer bytes over PCIe ----
+    e2e_packed = None
+    if not args.no_e2e and world == 1:
+        try:
+            h_packed, len32 = dnabitset_host(d_bases, offsets)
+
+            def e2e_packed_step():
+                f.load_dnabitset(h_packed, len32)
+                f.sketch()
+                f.build()
+                return f.queryAll(False, fetch=True)
+
+            for _ in range(2):
+                e2e_packed_step()
+            ms_p, (off_p, ids_p), _, _ = timed(e2e_packed_step, args.steps)
+            e2e_packed = {"value": all_bases * args.steps / (ms_p * 1e-3) / 1e9, "unit": "Gbases/s",
+                          "h2d_bytes_per_step": int(h_packed.nbytes + len32.nbytes), "d2h_bytes_per_step": int(off_p.nbytes + ids_p.nbytes),
+                          "ms_per_step": ms_p / args.steps, "same_csr_as_ascii_path": bool((off_p == off).all() and (ids_p == ids).all()),
+                          "input": "DnaBitset bytes + u32 lengths in host memory (nsmh_load_reads_dnabitset)"}
+            del h_packed
+        except Exception as e:  # noqa: BLE001
+            e2e_packed = {"error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- N > 1: is the multi-GPU result the single-GPU result?  (bench_legs.parity_of) ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        import types
+        import bench_legs
+        total_now = device_step()
+        view = types.SimpleNamespace(f=f, pf=pf, d_bases=d_bases, d_off=d_off, offsets=offsets, bases=total_bases, k=K, n=NHASH,
+                                     thr=THR, rnd=f.randNumbers, rank=rank, world=world, local_rank=local_rank,
+                                     row_base=rank * READS_PER_GPU, rows_per_rank=rows_per_rank)
+        if pf is not None:
+            view.csr = lambda total: pf.result(lengths.size, total)
+        else:
+            view.csr = lambda total: f.queryAll(False, fetch=True)
+        try:
+            parity = bench_legs.parity_of(view, total_now, dist, replicated_check=pf is not None)
+        except Exception as e:  # noqa: BLE001
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+
+    # ---- side legs: the other BASELINE configs (never part of `value`) ----
+    legs = {}
+    if not args.no_legs and not args.no_e2e:
+        import bench_legs
+        low_err = dict(genome_len=GENOME_LEN, p_ins=0.006, p_del=0.006, p_sub=0.008)
+        plan = []
+        if world == 1:
+            plan.append(("rich", "the headline's 100 000 reads at 2 % error (0.6 % ins, 0.6 % del, 0.8 % sub): real candidate lists",
+                         READS_PER_GPU, MEAN_LEN, K, NHASH, THR, 1000, low_err))
+            plan.append(("c4_k15_n120", "BASELINE configs[3] corner: synthetic 1M reads (~10 kb mean), k=15 n=120 thr=12, 1 GPU",
+                         1_000_000, MEAN_LEN, 15, 120, 12, 31, dict(genome_len=GENOME_LEN)))
+        else:
+            plan.append(("c3", f"BASELINE configs[2]: synthetic 1M reads (~10 Gbases), k=23 n=60 thr=6, split by bases over {world} GPUs",
+                         1_000_000, MEAN_LEN, K, NHASH, THR, 31, dict(genome_len=GENOME_LEN)))
+        plan.append(("c5", f"BASELINE configs[4]: synthetic ultra-long reads (100 kb mean, ~5 Gbases), k=23 n=60 thr=6, "
+                           f"{'1 GPU' if world == 1 else f'split by bases over {world} GPUs'}",
+                     50_000, 100_000, K, NHASH, THR, 41, dict(genome_len=GENOME_LEN)))
+        for name, what, nreads, mean, k_, n_, thr_, lseed, skw in plan:
+            leg = None
+            try:
+                leg = bench_legs.Leg(name, what, nreads, mean, k_, n_, thr_, rank, world, local_rank, RAND_SEED, lseed, skw)
+                legs[name] = bench_legs.run_leg(leg, 3, dist, with_parity=not args.no_parity)
+            except Exception as e:  # noqa: BLE001
+                legs[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            finally:
+                if leg is not None:
+                    try:
+                        leg.close()
+                    except Exception:  # noqa: BLE001
+                        pass
+                torch.cuda.empty_cache()
+
+    # ---- the kernel the INT32 roof describes: brute force, every k-mer against every hash (N=1 only) ----
+    roofline_brute = None
+    if world == 1 and not args.no_legs and not args.no_e2e and args.sketch_mode == 0:
+        try:
+            f.sketchMode = 1
+            check(lib().nsmh_set_sketch_mode(f._h, 1))
+            for _ in range(2):
+                f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
+                f.sketch()
+            bms = f.stats()["sketch_main_ms"]
+            f.sketchMode = 0
+            check(lib().nsmh_set_sketch_mode(f._h, 0))
+            f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
+            f.sketch()
+            roofline_brute = {"kernel": "sketch_brute_kernel", "kernel_ms": bms}
+        except Exception as e:  # noqa: BLE001
+            roofline_brute = {"error": f"{type(e).__name__}: {e}"[:300]}
+
     # ---- roofline of the dominant kernel (sketch_filter_kernel / sketch_brute_kernel) ----
     hbm_peak, peak_src, sm_max = peaks()
     mean_len = total_bases / lengths.size
@@ -466,29 +596,43 @@ def main():
     except (OSError, ValueError, IndexError):
         pass
     dominant = "sketch_filter_kernel" if args.sketch_mode == 0 else "sketch_brute_kernel"
-    if args.sketch_mode == 0 and os.environ.get("NSMH_SKETCH_BALANCED", "0") not in ("", "0"):
-        dominant = "sketch_filter_kernel<balanced>"      # experiment: the recorded ncu figures do not apply
+    rec = recorded_counters().get(dominant, {}) if rank == 0 else {}
+    cyc_per_s = 148 * sm_max * 1e6
+    int_xormin = (int_measured or {}).get("xormin64_lane_tops_survey_count")
+    achieved_tops = int_ops / (sk_ms * 1e-3) / 1e12 if sk_ms > 0 else None
     roofline = {"bound": "hbm", "kernel": dominant,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                "peak_source": peak_src, "traffic": NCU_TRAFFIC_BYTES.get(dominant) if rank == 0 else None,
-                "traffic_source": NCU_TRAFFIC_SOURCE if dominant in NCU_TRAFFIC_BYTES else None,
+                "peak_source": peak_src,
+                "traffic": rec.get("dram_bytes_read", 0) + rec.get("dram_bytes_write", 0) if rec else None,
+                "traffic_source": rec.get("source"),
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": sk_ms,
-                "issue_slots": ({"warp_instructions": NCU_WARP_INSTRUCTIONS[dominant],
-                                 "peak_per_s": 148 * 4 * sm_max * 1e6,
-                                 "frac": NCU_WARP_INSTRUCTIONS[dominant] / (sk_ms * 1e-3) / (148 * 4 * sm_max * 1e6),
-                                 "note": "the kernel is bound by instruction issue, not DRAM: recorded "
-                                         "smsp__inst_executed.sum / live kernel time / (148 SMs x 4 schedulers x max SM clock)"}
-                                if dominant in NCU_WARP_INSTRUCTIONS and sk_ms > 0 and rank == 0 else None),
                 "kernel_gbases_per_s": total_bases / (sk_ms * 1e-3) / 1e9 if sk_ms > 0 else None,
-                "int32_reference_count": {"lane_ops_per_base": 6 * NHASH + 6,
-                                          "achieved_tops": int_ops / (sk_ms * 1e-3) / 1e12 if sk_ms > 0 else None,
-                                          "nominal_alu_peak_tops": int_peak / 1e12,
-                                          "measured_xormin64_lane_tops": (int_measured or {}).get("xormin64_lane_tops_survey_count"),
-                                          "frac_of_measured": ((int_ops / (sk_ms * 1e-3) / 1e12) / int_measured["xormin64_lane_tops_survey_count"]
-                                                               if int_measured and sk_ms > 0 and int_measured.get("xormin64_lane_tops_survey_count") else None),
-                                          "frac": (int_ops / (sk_ms * 1e-3)) / int_peak if sk_ms > 0 else None,
-                                          "note": "filter kernel skips most (k-mer,hash) pairs exactly; >1 means faster than the brute-force INT32 roof"}}
+                # what actually binds the filter kernel (ncu): the shared-memory data pipe, then instruction issue
+                "binding_resource": ({"name": "shared-memory data pipe (l1tex wavefronts, 1 per SM and clock)",
+                                      "wavefronts_per_launch": rec["smem_wavefronts"],
+                                      "frac": rec["smem_wavefronts"] / (sk_ms * 1e-3) / cyc_per_s,
+                                      "ncu_pct_of_peak_at_capture": rec.get("l1tex_data_pipe_pct")}
+                                     if rec.get("smem_wavefronts") and sk_ms > 0 else None),
+                "issue_slots": ({"warp_instructions": rec["warp_instructions"], "peak_per_s": 4 * cyc_per_s,
+                                 "frac": rec["warp_instructions"] / (sk_ms * 1e-3) / (4 * cyc_per_s)}
+                                if rec.get("warp_instructions") and sk_ms > 0 else None),
+                # the reference's operation count, (6n+6) INT32 lane-ops per base, against the
+                # MEASURED rate of the 64-bit XOR+MIN pair (tools/micro/int_roof.cu on a B200)
+                "int32_reference_count": {"lane_ops_per_base": 6 * NHASH + 6, "achieved_tops": achieved_tops,
+                                          "nominal_alu_pipe_tops": int_peak / 1e12,
+                                          "measured_xormin64_lane_tops": int_xormin,
+                                          "frac_of_measured": achieved_tops / int_xormin if int_xormin and achieved_tops else None,
+                                          "note": ("brute-force kernel: this is its utilisation of the integer roof" if args.sketch_mode else
+                                                   "the filter kernel skips most (k-mer, hash) pairs exactly: > 1 means faster than any "
+                                                   "brute-force kernel could be; see roofline_brute for the kernel this roof describes")}}
 
+    if roofline_brute and roofline_brute.get("kernel_ms"):
+        bt = int_ops / (roofline_brute["kernel_ms"] * 1e-3) / 1e12
+        roofline_brute.update({"bound": "int32", "achieved": bt, "unit": "T lane-ops/s (6n+6 per base, SURVEY 8(d))",
+                               "peak": int_xormin, "peak_source": "profiles/int_roof.json: tools/micro/int_roof.cu on a B200, "
+                               "the 64-bit XOR + unsigned MIN pair at 6 lane-ops (2 399 G pairs/s)",
+                               "frac": bt / int_xormin if int_xormin else None,
+                               "gbases_per_s": total_bases / (roofline_brute["kernel_ms"] * 1e-3) / 1e9})
     if dist is not None:
         dist.barrier()
     if isinstance(pf, shard.PeerPartitionedFilter):
@@ -515,6 +659,14 @@ def main():
         "roofline": roofline,
         "clocks": clocks,
     }
+    if e2e_packed is not None:
+        line["e2e_packed"] = e2e_packed
+    if parity is not None:
+        line["parity"] = parity
+    if roofline_brute is not None:
+        line["roofline_brute"] = roofline_brute
+    if legs:
+        line["legs"] = legs
 
     # ---- FASTQ ingest: a side measurement, never part of `value` ----
     if n_gpus == 1 and not args.no_ingest and not args.no_e2e:

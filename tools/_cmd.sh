@@ -1,12 +1,15 @@
 set -u
-OUT=gpurun_out; TAG=r2g
-(timeout 600 python -m pytest tests -m gpu -x -q) > $OUT/pytest_gpu_$TAG.log 2>&1; tail -n 3 $OUT/pytest_gpu_$TAG.log
-timeout 120 python bench.py --steps 10 --no-cpu-baseline --no-e2e --no-ingest > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+OUT=gpurun_out; TAG=r2i
+(time timeout 600 python bench.py) > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+tail -5 $OUT/bench_$TAG.err
 python - $OUT/bench_$TAG.json <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 p = d["phases_last_step"]
-print(f"ms/step {d['ms_per_step']:.4f} pack {p['pack_ms']:.4f} sketch {p['sketch_ms']:.4f} (main {p['sketch_main_kernel_ms']:.4f}) build {p['build_ms']:.4f} query {p['query_ms']:.4f} launches {d['gpu_launches']}")
+print(f"value {d['value']:.1f} ms/step {d['ms_per_step']:.4f} e2e {d['e2e']['value']:.1f} ({d['e2e']['ms_per_step']:.2f} ms)")
+print("e2e_packed", json.dumps(d.get("e2e_packed")))
+print("roofline", json.dumps({k:v for k,v in d["roofline"].items() if k in ("frac","binding_resource","issue_slots","kernel_ms")}))
+print("roofline_brute", json.dumps(d.get("roofline_brute")))
+for k,v in (d.get("legs") or {}).items():
+    print(k, json.dumps(v)[:900])
 PY
-timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/launches_$TAG.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-ingest > $OUT/bench_under_ncu_$TAG.log 2>&1
-python tools/launch_list.py $OUT/launches_$TAG.csv 40 | tail -14
