@@ -151,7 +151,8 @@ int nsmh_mg_init(nsmh_handle c, uint32_t rank, uint32_t world, const uint32_t *r
     }
     int rc = NSMH_OK;
     do {
-        if (total >= (1ULL << 32) - 1) { rc = fail(NSMH_EINVAL, "mg_init: more than 2^32-2 reads"); break; }
+        // read ids travel in 31 bits when a group of two is sent inside a probe result (kPairFlag)
+        if (total >= (1ULL << 30)) { rc = fail(NSMH_EINVAL, "mg_init: more than 2^30 reads"); break; }
         m->total_rows = (uint32_t)total;
         m->col0 = rank ? m->col_end[rank - 1] : 0u;
         m->ncols = m->col_end[rank] - m->col0;
@@ -164,7 +165,9 @@ int nsmh_mg_init(nsmh_handle c, uint32_t rank, uint32_t world, const uint32_t *r
         uint32_t max_cols = 0;
         for (uint32_t r = 0; r < world; ++r) max_cols = std::max(max_cols, m->col_end[r] - (r ? m->col_end[r - 1] : 0u));
         const char *ic = getenv("NSMH_MG_INBOX_CAP");        // tests: force the overflow path
-        const MgLayout lay = mg_layout(m->total_rows, m->ncols, m->rows[rank], m->n_total, max_cols, world,
+        uint32_t pcol[kMgMaxRanks];
+        const uint32_t pr_cols = mg_padded_offsets(m->col_end, world, pcol);
+        const MgLayout lay = mg_layout(m->total_rows, m->ncols, m->rows[rank], pr_cols, max_cols, world,
                                        ic && *ic ? atoll(ic) : 0);
         t.off_m = lay.off_m;
         t.off_pr = lay.off_pr;
@@ -282,12 +285,26 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
         pl.ids[r] = in ? reinterpret_cast<const uint32_t *>(base + m->peers[r].off_ids) : nullptr;
         pl.col_end[r] = in ? m->col_end[r] : 0u;
     }
+    if (const char *dbg = getenv("NSMH_MG_DEBUG_LOCAL_STORES")) {
+        // timing experiment only (results are wrong): the probe results of ALL reads go to this rank's own arena
+        if (atoi(dbg) != 0)
+            for (uint32_t r = 0; r < m->world; ++r) {
+                pd.pr[r] = reinterpret_cast<uint64_t *>(m->arena + m->self.off_pr);
+                pd.inbox[r] = reinterpret_cast<uint32_t *>(m->arena + m->self.off_inbox) + (size_t)m->rank * m->self.inbox_cap;
+            }
+    }
     ba.world = sa.world = pd.world = pl.world = m->world;
     ba.rank = m->rank;
     ba.timeout_ns = m->timeout_ns;
     sa.row0 = m->rank ? m->row_end[m->rank - 1] : 0u;
     pd.col0 = m->col0;
     pd.ncols = m->ncols;
+    {
+        uint32_t pcol[kMgMaxRanks];
+        mg_padded_offsets(m->col_end, m->world, pcol);
+        pd.pcol0 = pcol[m->rank];
+    }
+    pd.chunk0 = m->total_rows ? std::min<uint32_t>(sa.row0, m->total_rows - 1) / kProbeRows : 0u;
     pl.pr = reinterpret_cast<const uint64_t *>(m->arena + m->self.off_pr);
     pl.n = m->n_total;
     pl.rows = rows;

@@ -33,10 +33,21 @@ inline bool mg_split_columns(uint32_t n, uint32_t world, uint32_t *col_end) {
     return true;
 }
 
+// padded column offset of every owner's block in pr (pcol[o]) and their total
+inline uint32_t mg_padded_offsets(const uint32_t *col_end, uint32_t world, uint32_t *pcol) {
+    uint32_t acc = 0;
+    for (uint32_t o = 0; o < world; ++o) {
+        pcol[o] = acc;
+        acc += peer_padded_cols(col_end[o] - (o ? col_end[o - 1] : 0u));
+    }
+    return acc;
+}
+
 // ---- one rank's arena ----------------------------------------------------------------------------
 //   m      [total_rows][ncols] u64   sketch columns of the hash functions this rank owns, all reads
-//   pr     [rows][n_total]     u64   probe results of this rank's reads, blocked by table owner and, inside an
-//                                    owner's block, by groups of kPeerCols hash functions (peer_result_index)
+//   pr     [rows][pr_cols]     u64   probe results of this rank's reads, blocked by table owner and, inside an
+//                                    owner's block, by groups of kPeerCols hash functions (nsmh_constants.h);
+//                                    pr_cols = sum over owners of their hash functions rounded up to kPeerCols
 //   ids    [total_rows*ncols]  u32   group members of the owned tables
 //   inbox  [world][inbox_cap]  u32   small groups pushed along by the table owners
 //   flags  2 x kMgMaxRanks epochs, error flag, kMgMaxRanks inbox cursors
@@ -45,13 +56,13 @@ struct MgLayout {
     uint32_t inbox_cap;
 };
 
-inline MgLayout mg_layout(uint32_t total_rows, uint32_t ncols, uint32_t my_rows, uint32_t n_total, uint32_t max_cols,
+inline MgLayout mg_layout(uint32_t total_rows, uint32_t ncols, uint32_t my_rows, uint32_t pr_cols, uint32_t max_cols,
                           uint32_t world, long long inbox_cap_override) {
     auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
     auto max_sz = [](size_t a, size_t b) { return a > b ? a : b; };
     MgLayout t;
     const size_t items = max_sz((size_t)total_rows * ncols, 1);
-    const size_t local = max_sz((size_t)my_rows * n_total, 1);
+    const size_t local = max_sz((size_t)my_rows * pr_cols, 1);
     size_t off = 0;
     t.off_m = off;      off = align256(off + items * sizeof(uint64_t));
     t.off_pr = off;     off = align256(off + local * sizeof(uint64_t));

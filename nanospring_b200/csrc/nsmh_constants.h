@@ -40,19 +40,23 @@ __host__ __device__ __forceinline__ uint64_t region_stride(uint64_t cap) { retur
 // ---- multi-GPU over peer memory (kernels in query_kernels.cuh / multigpu_kernels.cuh) ----
 constexpr int kMgMaxRanks = NSMH_MG_MAX_RANKS;
 // Probe results travel as one u64 per (read, hash): {id | group start} | (group size) << 32.
-// In the arena of the rank that owns the reads they are blocked by table owner (block o starts at
-// rows * col_begin(o)) and, inside an owner's block, by groups of kPeerCols hash functions: group b is a
-// dense array [local row][hash functions of the group].  A block of the probe kernel produces the tile
-// [256 rows][one group] in shared memory and writes it out as ONE contiguous run per read owner, so the
-// NVLink traffic is full 128-byte lines (peer_result_index below is the layout both sides use).
+// In the arena of the rank that owns the reads they are blocked by table owner and, inside an owner's
+// block, by groups of kPeerCols hash functions: group b is a dense array [local row][kPeerCols] (an owner
+// whose number of hash functions is not a multiple of kPeerCols leaves the last columns of its last group
+// unused).  A block of the probe kernel produces the tile [256 rows][kPeerCols] in shared memory and sends
+// it as ONE contiguous, 64-byte-aligned run per read owner - a bulk copy (cp.async.bulk shared -> global)
+// when the tile has one owner - so the NVLink traffic is full 128-byte lines.
+constexpr int kProbeCols = 4;      // probe kernels: adjacent hash functions per thread (4 x 8 B of keys = one sector)
+constexpr int kProbeRows = 256;    // ... and queries per block = threads per block
 constexpr int kPeerCols = 8;
-// index of (local row q, hash function jj of an owner with nc hash functions) inside that owner's block
-__host__ __device__ __forceinline__ size_t peer_result_index(uint32_t rows, uint32_t nc, uint32_t q, uint32_t jj) {
-    const uint32_t b = jj / kPeerCols, w = nc - b * kPeerCols < (uint32_t)kPeerCols ? nc - b * kPeerCols : (uint32_t)kPeerCols;
-    return (size_t)rows * (b * kPeerCols) + (size_t)q * w + (jj - b * kPeerCols);
+__host__ __device__ __forceinline__ uint32_t peer_padded_cols(uint32_t nc) { return (nc + kPeerCols - 1) / kPeerCols * kPeerCols; }
+// index of (local row q, hash function jj of an owner) inside that owner's block of a rank with `rows` reads
+__host__ __device__ __forceinline__ size_t peer_result_index(uint32_t rows, uint32_t q, uint32_t jj) {
+    return (size_t)rows * (jj / kPeerCols * kPeerCols) + (size_t)q * kPeerCols + jj % kPeerCols;
 }
 constexpr int kInboxMaxGroup = 32;           // groups of up to this many ids are pushed to the read owner's inbox
 constexpr uint32_t kInboxFlag = 0x80000000u; // in the size field: "val is a position in your inbox"
+constexpr uint32_t kPairFlag = 0x40000000u;  // in the size field: a group of two, ids in bits 0..30 and 31..61 of the word
 struct PeerDst {
     uint64_t *pr[kMgMaxRanks];        // probe-result area in rank r's arena
     uint32_t *inbox[kMgMaxRanks];     // this rank's segment of rank r's inbox
@@ -60,6 +64,8 @@ struct PeerDst {
     uint32_t *cursor;                 // [kMgMaxRanks] local: ids pushed to rank r so far (zeroed per run)
     uint32_t row_end[kMgMaxRanks];    // global row index one past rank r's rows
     uint32_t world, col0, ncols;      // hash functions this rank owns: [col0, col0 + ncols)
+    uint32_t pcol0;                   // where this rank's block starts in a destination's pr, in (padded) columns
+    uint32_t chunk0;                  // first 256-row chunk that holds a read of this rank (< number of chunks)
 };
 // Probe results stored locally by the table owners + where the owners keep their group ids.
 struct PeerLists {

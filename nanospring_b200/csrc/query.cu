@@ -105,7 +105,7 @@ heavy_gather_kernel(Src src, const uint32_t *__restrict__ heavy_list, uint64_t i
         const ListRef r = src.get(heavy_list[h], (uint32_t)(t % subs));
         uint64_t *dst = pairs + (hoff[t] - pair0);
         const uint64_t tag = (h - h0) << 32;
-        if (!r.ptr) { if (lane == 0 && r.c) dst[0] = tag | r.one; }
+        if (!r.ptr) { if (lane == 0 && r.c) { dst[0] = tag | r.one; if (r.c == 2) dst[1] = tag | r.two; } }
         else for (uint32_t i = lane; i < r.c; i += 32) dst[i] = tag | r.ptr[i];
     }
 }

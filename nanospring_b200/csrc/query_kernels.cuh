@@ -21,17 +21,17 @@ namespace nsmh {
 constexpr int kMaxParts = 16;        // PartsSrc: at most this many partial lists per query
 constexpr uint32_t kNoId = 0xFFFFFFFFu;   // read ids are < 2^32-1 (ReadData.cpp:122-124)
 
-// one id list: c ids at ptr, or (ptr == nullptr, c == 1) the single id `one`
+// one id list: c ids at ptr, or (ptr == nullptr) the single id `one` (c == 1) / the two ids `one`, `two` (c == 2)
 struct ListRef {
     const uint32_t *ptr;
-    uint32_t c, one;
+    uint32_t c, one, two;
 };
 
 __device__ __forceinline__ ListRef empty_list() {
     ListRef r;
     r.ptr = nullptr;
     r.c = 0;
-    r.one = 0;
+    r.one = r.two = 0;
     return r;
 }
 
@@ -39,6 +39,7 @@ __device__ __forceinline__ ListRef empty_list() {
 // (query, hash) item and stores {val, group size}; everything downstream reads those.
 
 struct ProbeSrc {
+    static constexpr bool kInlinePairs = false;
     const uint64_t *qsk;     // [nq][n]
     const Slot *slots;
     const uint32_t *ids;
@@ -57,14 +58,20 @@ struct ProbeSrc {
     __device__ __forceinline__ void prefetch(uint32_t q, int lane) const {      // row q of the sketches: n * 8 bytes
         if ((uint32_t)lane * 16 < n) l2_prefetch_line(qsk + (size_t)q * n + lane * 16);
     }
-    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
+    // what does not change from query to query for list j (kept in registers across the query loop)
+    struct Ctx {
+        const Slot *region;
+    };
+    __device__ __forceinline__ Ctx context(uint32_t j) const { return Ctx{slots + (uint64_t)j * region_stride(cap)}; }
+    __device__ __forceinline__ Pending begin(const Ctx &x, uint32_t q, uint32_t j) const {
         Pending p;
         p.j = j;
         p.key = __ldg(qsk + (size_t)q * n + j);
         p.b = p.key == kEmptyKey ? (cap >> 1) : slot_index(p.key, cap >> 1);   // key ~0 lives in the extra slot
-        ldg256(slots + (uint64_t)j * region_stride(cap) + 2 * p.b, p.sa, p.sb, p.sc, p.sd);
+        ldg256(x.region + 2 * p.b, p.sa, p.sb, p.sc, p.sd);
         return p;
     }
+    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const { return begin(context(j), q, j); }
     // group size (0 = absent) and val (the id itself for a group of one, else the start in ids)
     __device__ __forceinline__ ListRef finish(Pending p) const {
         const Slot *region = slots + (uint64_t)p.j * region_stride(cap);
@@ -82,6 +89,7 @@ struct ProbeSrc {
         ListRef r;
         r.c = found ? (uint32_t)(hit >> 32) + 1u : 0u;     // untouched extra slot: 0xFFFFFFFF + 1 = 0
         r.one = (uint32_t)hit;
+        r.two = 0;
         r.ptr = r.c == 1 ? nullptr : ids + r.one;
         return r;
     }
@@ -105,8 +113,6 @@ __device__ __forceinline__ uint32_t inbox_take(uint32_t *cursor, uint32_t need, 
     return atomicAdd(cursor, need);
 }
 
-constexpr int kProbeCols = 4;      // adjacent hash functions per thread (4 x 8 B of keys = one sector)
-constexpr int kProbeRows = 256;    // queries per block = threads per block
 
 // One thread per (query, 4 adjacent hash functions): the four keys are one 32-byte sector of the
 // sketch row, every probe fetches one bucket = the two slots of one sector with ONE 256-bit
@@ -172,31 +178,42 @@ probe_items_kernel(ProbeSrc src, uint32_t nq) {
 // as ONE dense run per read owner into that owner's memory (peer mapping over NVLink): consecutive threads
 // store consecutive 8-byte words, i.e. full 128-byte lines.  (The first version stored 32 bytes per thread
 // at a stride of ncols * 8 bytes - half-written lines - and its time tripled from 2 to 8 ranks.)
-// Groups of 2..kInboxMaxGroup members are pushed along: their ids are copied into this rank's segment of
+// A group of two travels inside the result word; groups of 3..kInboxMaxGroup members are pushed along: their ids are copied into this rank's segment of
 // the read owner's inbox (space comes from a LOCAL cursor, one warp-aggregated atomic per warp), so the
 // counting kernel over there finds them in its own memory instead of paying an NVLink round trip per
 // list.  Larger groups and anything beyond the inbox capacity stay behind and are read remotely on demand.
 __global__ void __launch_bounds__(kProbeRows, 4)
 probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
-    __shared__ uint64_t s_tile[kProbeRows * kPeerCols];
+    __align__(128) __shared__ uint64_t s_tile[2][kProbeRows * kPeerCols];     // two tiles: one may still be leaving
     const int lane = threadIdx.x & 31;
     const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
     const uint32_t colblocks = (src.n + kPeerCols - 1) / kPeerCols;
     const uint32_t units = chunks * colblocks;
     const uint64_t nb = src.cap >> 1, rstride = region_stride(src.cap);
     const bool vec_in = (src.n & 3) == 0;
-    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        const uint32_t cbk = u / chunks, chunk = u - cbk * chunks;
+    uint32_t round = 0;
+    for (uint32_t u = blockIdx.x; u < units; u += gridDim.x, ++round) {
+        uint64_t *tile = s_tile[round & 1];
+        // every rank starts with the chunks of its own reads and walks on from there: at any time the ranks
+        // store into DIFFERENT peers (all of them starting at row 0 put 7 senders on one receiver's links)
+        const uint32_t cbk = u / chunks;
+        uint32_t chunk = u - cbk * chunks + dst.chunk0;
+        chunk = chunk >= chunks ? chunk - chunks : chunk;
         const uint32_t q = chunk * kProbeRows + threadIdx.x;
         const uint32_t c0 = cbk * kPeerCols, w = min((uint32_t)kPeerCols, src.n - c0);     // this group's hash functions
         const bool active = q < nq;
         uint32_t o = 0;
         if (active)
             while (o + 1 < dst.world && q >= dst.row_end[o]) ++o;        // owner of read q
-        for (uint32_t l0 = c0; l0 < c0 + w; l0 += kProbeCols) {
+        // the copy that took this buffer two rounds ago has read it (the issuing thread waits, the barrier tells the rest)
+        if (threadIdx.x == 0) bulk_store_wait_read<1>();
+        __syncthreads();
+        for (uint32_t l0 = c0; l0 < c0 + kPeerCols; l0 += kProbeCols) {
             uint32_t val[kProbeCols], cnt[kProbeCols];
             uint32_t need = 0;
-            if (active) {
+#pragma unroll
+            for (int j = 0; j < kProbeCols; ++j) val[j] = cnt[j] = 0;
+            if (active && l0 < c0 + w) {
                 const size_t t0 = (size_t)q * src.n + l0;
                 uint64_t key[kProbeCols];
                 if (vec_in) ldg256(src.qsk + t0, key[0], key[1], key[2], key[3]);
@@ -222,8 +239,8 @@ probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
                         b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
                         ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
                     }
-                    if (l0 + j >= c0 + w) cnt[j] = 0;
-                    if (cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) need += cnt[j];
+                    if (l0 + j >= c0 + w) val[j] = cnt[j] = 0;
+                    if (cnt[j] >= 3 && cnt[j] <= (uint32_t)kInboxMaxGroup) need += cnt[j];
                 }
             }
             // inbox space: one atomic per warp for the lanes that share the first lane's destination
@@ -236,39 +253,55 @@ probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
                 if (lane == 31) base = inbox_take(dst.cursor + o_lead, tot, dst.inbox_cap[o_lead]);
                 base = __shfl_sync(0xffffffffu, base, 31);
             }
-            if (active) {
-                uint32_t pos = agg ? base + incl - need : (need ? inbox_take(dst.cursor + o, need, dst.inbox_cap[o]) : 0u);
-                const bool fits = need && (uint64_t)pos + need <= dst.inbox_cap[o];
+            uint32_t pos = agg ? base + incl - need : (need ? inbox_take(dst.cursor + o, need, dst.inbox_cap[o]) : 0u);
+            const bool fits = need && (uint64_t)pos + need <= dst.inbox_cap[o];
 #pragma unroll
-                for (int j = 0; j < kProbeCols; ++j) {
-                    if (l0 + j >= c0 + w) continue;
-                    uint64_t out = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
-                    if (fits && cnt[j] >= 2 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
-                        uint32_t *box = dst.inbox[o] + pos;
-                        for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
-                        out = (uint64_t)pos | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
-                        pos += cnt[j];
-                    }
-                    s_tile[threadIdx.x * w + (l0 - c0) + j] = out;
+            for (int j = 0; j < kProbeCols; ++j) {
+                uint64_t out = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
+                if (cnt[j] == 2) {
+                    // a group of two travels inside the result word (ids < 2^31: checked by nsmh_mg_init)
+                    const uint32_t i0 = src.ids[val[j]], i1 = src.ids[val[j] + 1];
+                    out = (uint64_t)i0 | ((uint64_t)i1 << 31) | ((uint64_t)kPairFlag << 32);
+                } else if (fits && cnt[j] >= 3 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
+                    uint32_t *box = dst.inbox[o] + pos;
+                    for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
+                    out = (uint64_t)pos | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
+                    pos += cnt[j];
                 }
+                tile[threadIdx.x * kPeerCols + (l0 - c0) + j] = out;        // rows past nq / unused columns: zeroes
             }
         }
-        __syncthreads();
-        // ---- the tile [rows of the chunk][w] leaves: a dense run per read owner ----
+        // ---- the tile [rows of the chunk][kPeerCols] leaves: a dense, 64-byte-aligned run per read owner ----
         const uint32_t q0 = chunk * kProbeRows, nr = min((uint32_t)kProbeRows, nq - q0);
-        for (uint32_t e = threadIdx.x; e < nr * w; e += kProbeRows) {
-            const uint32_t r = e / w, c = e - r * w, qq = q0 + r;
-            uint32_t oo = 0;
-            while (oo + 1 < dst.world && qq >= dst.row_end[oo]) ++oo;
-            const uint32_t r0 = oo ? dst.row_end[oo - 1] : 0u, rows_o = dst.row_end[oo] - r0;
-            dst.pr[oo][(size_t)rows_o * dst.col0 + peer_result_index(rows_o, dst.ncols, qq - r0, c0 + c)] = s_tile[e];
+        uint32_t o_first = 0;
+        while (o_first + 1 < dst.world && q0 >= dst.row_end[o_first]) ++o_first;
+        const bool one_owner = q0 + nr <= dst.row_end[o_first];
+        bulk_store_fence();                 // the tile's stores are visible to the copy engine
+        __syncthreads();
+        if (one_owner) {
+            if (threadIdx.x == 0) {
+                const uint32_t r0 = o_first ? dst.row_end[o_first - 1] : 0u, rows_o = dst.row_end[o_first] - r0;
+                bulk_store(dst.pr[o_first] + (size_t)rows_o * dst.pcol0 + peer_result_index(rows_o, q0 - r0, c0),
+                           tile, nr * kPeerCols * (uint32_t)sizeof(uint64_t));
+                bulk_store_commit();
+            }
+        } else {
+            for (uint32_t e = threadIdx.x; e < nr * kPeerCols; e += kProbeRows) {
+                const uint32_t r = e / kPeerCols, c = e % kPeerCols, qq = q0 + r;
+                uint32_t oo = 0;
+                while (oo + 1 < dst.world && qq >= dst.row_end[oo]) ++oo;
+                const uint32_t r0 = oo ? dst.row_end[oo - 1] : 0u, rows_o = dst.row_end[oo] - r0;
+                dst.pr[oo][(size_t)rows_o * dst.pcol0 + peer_result_index(rows_o, qq - r0, c0 + c)] = tile[e];
+            }
+            if (threadIdx.x == 0) bulk_store_commit();          // an empty group keeps the two-round bookkeeping uniform
         }
-        __syncthreads();                    // the tile is free again
     }
+    if (threadIdx.x == 0) bulk_store_wait_all();        // the shared memory must outlive the copies
 }
 
 // id lists from stored probe results
 struct StoredSrc {
+    static constexpr bool kInlinePairs = false;
     const uint32_t *pval, *pcnt;   // [nq][n]
     const uint32_t *ids;
     uint32_t n;
@@ -282,6 +315,9 @@ struct StoredSrc {
             l2_prefetch_line(pcnt + (size_t)q * n + lane * 32);
         }
     }
+    struct Ctx {};
+    __device__ __forceinline__ Ctx context(uint32_t) const { return Ctx{}; }
+    __device__ __forceinline__ Pending begin(const Ctx &, uint32_t q, uint32_t j) const { return begin(q, j); }
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
         p.val = __ldg(pval + (size_t)q * n + j);
@@ -292,6 +328,7 @@ struct StoredSrc {
         ListRef r;
         r.c = p.c;
         r.one = p.val;
+        r.two = 0;
         r.ptr = p.c == 1 ? nullptr : ids + p.val;
         return r;
     }
@@ -299,6 +336,7 @@ struct StoredSrc {
 };
 
 struct PartsSrc {
+    static constexpr bool kInlinePairs = false;
     const uint64_t *offs[kMaxParts];   // each [nq+1]
     const uint32_t *ids[kMaxParts];
     uint32_t parts;
@@ -308,6 +346,9 @@ struct PartsSrc {
     };
     __device__ __forceinline__ uint32_t subs() const { return parts; }
     __device__ __forceinline__ void prefetch(uint32_t, int) const {}
+    struct Ctx {};
+    __device__ __forceinline__ Ctx context(uint32_t) const { return Ctx{}; }
+    __device__ __forceinline__ Pending begin(const Ctx &, uint32_t q, uint32_t j) const { return begin(q, j); }
     __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
         Pending p;
         p.j = j;
@@ -319,7 +360,7 @@ struct PartsSrc {
         ListRef r;
         r.ptr = ids[p.j] + p.o0;
         r.c = (uint32_t)(p.o1 - p.o0);
-        r.one = 0;
+        r.one = r.two = 0;
         return r;
     }
     __device__ __forceinline__ ListRef get(uint32_t q, uint32_t j) const { return finish(begin(q, j)); }
@@ -329,30 +370,48 @@ struct PartsSrc {
 // rank that owns the hash function's table; the ids of groups with two or more members stay
 // in the owner's memory and are read through the NVLink peer mapping.
 struct PeerSrc {
+    static constexpr bool kInlinePairs = true;     // groups of two travel inside the probe result (kPairFlag)
     PeerLists L;
     struct Pending {
         uint64_t v;
         uint32_t o;
     };
+    // list j of every query: which rank owns the hash function, and where its results for row 0 are
+    struct Ctx {
+        const uint64_t *p;
+        uint32_t o;
+    };
     __device__ __forceinline__ uint32_t subs() const { return L.n; }
     __device__ __forceinline__ void prefetch(uint32_t, int) const {}
-    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const {
+    __device__ __forceinline__ Ctx context(uint32_t j) const {
+        uint32_t o = 0, pcol = 0;
+        while (o + 1 < L.world && j >= L.col_end[o]) {
+            pcol += peer_padded_cols(L.col_end[o] - (o ? L.col_end[o - 1] : 0u));
+            ++o;
+        }
+        const uint32_t cb = o ? L.col_end[o - 1] : 0u;
+        return Ctx{L.pr + (size_t)L.rows * pcol + peer_result_index(L.rows, 0, j - cb), o};
+    }
+    __device__ __forceinline__ Pending begin(const Ctx &x, uint32_t q, uint32_t) const {
         Pending p;
-        uint32_t o = 0;
-        while (o + 1 < L.world && j >= L.col_end[o]) ++o;
-        const uint32_t cb = o ? L.col_end[o - 1] : 0u, nc = L.col_end[o] - cb;
-        p.o = o;
-        p.v = __ldg(L.pr + (size_t)L.rows * cb + peer_result_index(L.rows, nc, q, j - cb));
+        p.o = x.o;
+        p.v = __ldg(x.p + (size_t)q * kPeerCols);
         return p;
     }
+    __device__ __forceinline__ Pending begin(uint32_t q, uint32_t j) const { return begin(context(j), q, j); }
     __device__ __forceinline__ ListRef finish(Pending p) const {
         ListRef r;
         r.c = (uint32_t)(p.v >> 32);
         r.one = (uint32_t)p.v;
+        r.two = 0;
         r.ptr = nullptr;
         if (r.c & kInboxFlag) {                  // the owner pushed the ids into our inbox
             r.c &= ~kInboxFlag;
             r.ptr = L.inbox + (size_t)p.o * L.inbox_cap + r.one;
+        } else if (r.c & kPairFlag) {            // a group of two, both ids inside the result word
+            r.c = 2;
+            r.one = (uint32_t)p.v & 0x7FFFFFFFu;
+            r.two = (uint32_t)(p.v >> 31) & 0x7FFFFFFFu;
         } else if (r.c > 1) {
             r.ptr = L.ids[p.o] + r.one;          // NVLink read from the owner
         }
@@ -419,7 +478,7 @@ constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer
 constexpr int kResWords = 256;       // result list of the register path / filter counters of the sort path
 constexpr int kRegListsMax = 4;      // lists per lane that are probed once and kept in registers (n <= 128; 2 for n <= 64)
 static_assert(kResWords >= kWarpFilterBuckets / 2, "the sort path keeps its filter counters in the result area");
-static_assert(kResWords >= 32 * kRegListsMax, "thr <= 1: every gathered id is a result");
+static_assert(kResWords >= 2 * 32 * kRegListsMax, "thr <= 1: every gathered id is a result");
 constexpr int kWarpWords = kLookupCap + kResWords + 32;
 constexpr int kLookupWarps = 8;
 
@@ -452,7 +511,8 @@ struct CountArgs {
 // produce the CSR.
 template <typename Src, int kRegLists = kRegListsMax>
 __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf) {
-    constexpr int kRegMaxIds = 32 * kRegLists;   // gathered ids that are counted in registers
+    constexpr int kRegIds = Src::kInlinePairs ? 2 * kRegLists : kRegLists;      // ids per lane held in registers
+    constexpr int kRegMaxIds = 32 * kRegIds;     // gathered ids that are counted in registers
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t *buf = s_buf + (size_t)warp * kWarpWords;
     uint32_t *res = buf + kLookupCap;           // kResWords entries
@@ -460,26 +520,35 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
     const uint32_t subs = src.subs();
     const bool keep_lists = subs <= (uint32_t)kRegMaxIds;
     unsigned long long pairs_local = 0, results_local = 0;
+    typename Src::Ctx ctx[kRegLists];
+#pragma unroll
+    for (int c = 0; c < kRegLists; ++c) ctx[c] = src.context(min((uint32_t)(c * 32 + lane), subs ? subs - 1 : 0u));
 
     for (uint32_t q = blockIdx.x * kLookupWarps + warp; q < a.nq; q += total_warps) {
         if (q + total_warps < a.nq) src.prefetch(q + total_warps, lane);    // the next query's keys, into L2
         ListRef r[kRegLists];
-        uint32_t v[kRegLists];
+        uint32_t v[kRegIds];
         uint32_t T = 0xFFFFFFFFu;           // gathered ids (saturating)
         bool in_regs = false;
         if (keep_lists) {
             typename Src::Pending pend[kRegLists];
 #pragma unroll
             for (int c = 0; c < kRegLists; ++c)
-                if (c * 32 + lane < (int)subs) pend[c] = src.begin(q, c * 32 + lane);
+                if (c * 32 + lane < (int)subs) pend[c] = src.begin(ctx[c], q, c * 32 + lane);
             unsigned long long mine = 0;
             bool multi = false;
 #pragma unroll
             for (int c = 0; c < kRegLists; ++c) {
                 r[c] = c * 32 + lane < (int)subs ? src.finish(pend[c]) : empty_list();
                 mine += r[c].c;
-                multi |= r[c].c > 1;
-                v[c] = r[c].c == 1 ? (r[c].ptr ? r[c].ptr[0] : r[c].one) : kNoId;
+                if (Src::kInlinePairs) {
+                    multi |= r[c].c > 2 || (r[c].c == 2 && r[c].ptr);
+                    v[2 * c] = r[c].c == 1 ? (r[c].ptr ? r[c].ptr[0] : r[c].one) : r[c].c == 2 ? r[c].one : kNoId;
+                    v[2 * c + 1] = r[c].c == 2 ? r[c].two : kNoId;
+                } else {
+                    multi |= r[c].c > 1;
+                    v[c] = r[c].c == 1 ? (r[c].ptr ? r[c].ptr[0] : r[c].one) : kNoId;
+                }
             }
 #pragma unroll
             for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
@@ -498,9 +567,10 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
                 const uint32_t off = T + incl - rr.c;
                 if ((uint64_t)T + round_total <= kLookupCap) {
                     if (rr.c == 1) buf[off] = rr.ptr ? rr.ptr[0] : rr.one;
+                    else if (rr.c == 2 && !rr.ptr) { buf[off] = rr.one; buf[off + 1] = rr.two; }
                     else if (rr.c > 1 && rr.c <= 8)
                         for (uint32_t i = 0; i < rr.c; ++i) buf[off + i] = rr.ptr[i];
-                    uint32_t big = __ballot_sync(0xffffffffu, rr.c > 8);
+                    uint32_t big = __ballot_sync(0xffffffffu, rr.c > 8);       // lists that long are never inline
                     while (big) {
                         const int sl = __ffs(big) - 1;
                         big &= big - 1;
@@ -534,22 +604,22 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
             __syncwarp();
             if (T <= (uint32_t)kRegMaxIds) {
 #pragma unroll
-                for (int c = 0; c < kRegLists; ++c) v[c] = c * 32 + lane < (int)T ? buf[c * 32 + lane] : kNoId;
+                for (int c = 0; c < kRegIds; ++c) v[c] = c * 32 + lane < (int)T ? buf[c * 32 + lane] : kNoId;
                 in_regs = true;
             }
         }
         if (in_regs) {
             // ---- count in registers: one round per distinct id ----
-            uint32_t rem[kRegLists];
+            uint32_t rem[kRegIds];
 #pragma unroll
-            for (int c = 0; c < kRegLists; ++c) rem[c] = __ballot_sync(0xffffffffu, v[c] != kNoId);
+            for (int c = 0; c < kRegIds; ++c) rem[c] = __ballot_sync(0xffffffffu, v[c] != kNoId);
 #pragma unroll
-            for (int c = 0; c < kRegLists; ++c) {
+            for (int c = 0; c < kRegIds; ++c) {
                 while (rem[c]) {
                     const uint32_t id = __shfl_sync(0xffffffffu, v[c], __ffs(rem[c]) - 1);
                     uint32_t cnt = 0;
 #pragma unroll
-                    for (int d = c; d < kRegLists; ++d) {       // earlier registers hold no id that is still uncounted
+                    for (int d = c; d < kRegIds; ++d) {         // earlier registers hold no id that is still uncounted
                         const uint32_t eq = __ballot_sync(0xffffffffu, v[d] == id);
                         cnt += __popc(eq);
                         rem[d] &= ~eq;
@@ -672,6 +742,7 @@ __device__ __forceinline__ void mid_for_each_id(const Src &src, uint32_t q, uint
         const uint32_t j = j0 + lane;
         const ListRef r = j < subs ? src.get(q, j) : empty_list();
         if (r.c == 1) f(r.ptr ? r.ptr[0] : r.one);
+        else if (r.c == 2 && !r.ptr) { f(r.one); f(r.two); }
         else if (r.c > 1 && r.c <= 4)
             for (uint32_t i = 0; i < r.c; ++i) f(r.ptr[i]);
         uint32_t big = __ballot_sync(0xffffffffu, r.c > 4);

@@ -27,6 +27,7 @@
 // atomics instead of spreading random sectors over the whole table.
 // Inside a group the id order is arbitrary; every consumer sorts (ReadFilter.cpp:73).
 #include <algorithm>
+#include <cstdlib>
 
 #include "nsmh_internal.cuh"
 #include "table_kernels.cuh"
@@ -36,12 +37,24 @@ namespace nsmh {
 // Clear the tables for `rows` reads on the copy stream, so that the (bandwidth-bound) memset
 // overlaps whatever the main stream does next (nsmh_sketch calls this before sketching: the
 // tables do not depend on the sketches until the first insert).
+// slots per read in every table region (even).  2 = load factor 0.5: 10 % of the keys do not fit their home
+// bucket, so nearly every query (60 probes) pays a second dependent bucket access; NSMH_TABLE_SLOTS_PER_READ
+// changes it for A/B runs.
+static uint64_t table_cap(uint32_t rows) {
+    static const uint64_t per_read = [] {
+        const char *e = getenv("NSMH_TABLE_SLOTS_PER_READ");
+        const long v = e && *e ? atol(e) : 2;
+        return (uint64_t)(v < 2 ? 2 : (v > 16 ? 16 : v)) & ~1ULL;
+    }();
+    return std::max<uint64_t>(16, per_read * rows);
+}
+
 int preclear_tables(nsmh_ctx *c, uint32_t rows) {
     Tables &T = c->tables;
     // an earlier clear may still run on the copy stream: nothing below may free the buffer under it
     if (c->precleared_rows) NSMH_CK(cudaStreamWaitEvent(c->stream, c->ev_cleared, 0));
     c->precleared_rows = 0;
-    const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);
+    const uint64_t cap = table_cap(rows);
     const uint64_t nslots = (uint64_t)c->n * region_stride(cap);
     if (rows == 0 || nslots >= (1ULL << 32)) return NSMH_OK;      // build_tables reports the error
     NSMH_TRY(T.slots.ensure(nslots * sizeof(Slot), c->stream));
@@ -60,7 +73,7 @@ int build_tables(nsmh_ctx *c) {
     const uint32_t n = c->n, rows = c->table_reads;
     T.built = false;
     if (c->precleared_rows) NSMH_CK(cudaStreamWaitEvent(s, c->ev_cleared, 0));   // see preclear_tables
-    const uint64_t cap = std::max<uint64_t>(16, 2ULL * rows);   // even; load factor <= 0.5
+    const uint64_t cap = table_cap(rows);   // even; load factor <= 0.5
     const uint64_t nslots = (uint64_t)n * region_stride(cap);
     const uint64_t items = (uint64_t)rows * n;
     if (nslots >= (1ULL << 32) || items >= (1ULL << 32) - (1ULL << 22))

@@ -39,11 +39,13 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
     const uint32_t total_rows = (uint32_t)total64;
     uint32_t max_cols = 0;
     for (uint32_t r = 0; r < world; ++r) max_cols = std::max(max_cols, col_end[r] - (r ? col_end[r - 1] : 0u));
+    uint32_t pcol[kMgMaxRanks] = {0};
+    const uint32_t pr_cols = mg_padded_offsets(col_end, world, pcol);
     std::vector<MgLayout> lay(world);
     std::vector<uint8_t *> arena(world, nullptr);
     for (uint32_t r = 0; r < world; ++r) {
         const uint32_t ncols = col_end[r] - (r ? col_end[r - 1] : 0u);
-        lay[r] = mg_layout(total_rows, ncols, rows[r], n, max_cols, world, inbox_cap_override);
+        lay[r] = mg_layout(total_rows, ncols, rows[r], pr_cols, max_cols, world, inbox_cap_override);
         arena[r] = static_cast<uint8_t *>(aligned_alloc(256, (lay[r].arena_bytes + 255) & ~(size_t)255));
         memset(arena[r], 0xA5, lay[r].arena_bytes);                               // nothing may rely on zeroes ...
         memset(arena[r] + lay[r].off_flags, 0, (3 * kMgMaxRanks + 8) * sizeof(uint32_t));   // ... but the flags / cursors
@@ -118,6 +120,8 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         pd.world = world;
         pd.col0 = col0;
         pd.ncols = ncols;
+        pd.pcol0 = pcol[r];
+        pd.chunk0 = std::min<uint32_t>(r ? row_end[r - 1] : 0u, total_rows - 1) / kProbeRows;
         emu_launch_block(grid, kProbeRows, [&] { probe_to_peers_kernel(src, total_rows, pd); });
     }
     // ---- stage 4: every rank thresholds its own reads ----

@@ -17,18 +17,22 @@ struct CsrSrc {
     const uint64_t *list_off;
     const uint32_t *ids;
     uint32_t nsubs;
+    static constexpr bool kInlinePairs = false;
     uint32_t subs() const { return nsubs; }
     void prefetch(uint32_t, int) const {}
     struct Pending {
         uint32_t q, j;
     };
+    struct Ctx {};
+    Ctx context(uint32_t) const { return Ctx{}; }
+    Pending begin(const Ctx &, uint32_t q, uint32_t j) const { return Pending{q, j}; }
     Pending begin(uint32_t q, uint32_t j) const { return Pending{q, j}; }
     ListRef finish(Pending p) const { return get(p.q, p.j); }
     ListRef get(uint32_t q, uint32_t j) const {
         const uint64_t o0 = list_off[(uint64_t)q * nsubs + j], o1 = list_off[(uint64_t)q * nsubs + j + 1];
         ListRef r;
         r.c = (uint32_t)(o1 - o0);
-        r.one = 0;
+        r.one = r.two = 0;
         r.ptr = ids + o0;
         if (r.c == 1 && (j & 1)) {
             r.one = ids[o0];
