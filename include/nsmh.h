@@ -196,6 +196,38 @@ int nsmh_mg_stage_ms(nsmh_handle h, float *out /* [6] */);
  * must have finished their last nsmh_mg_run before any rank calls this. */
 int nsmh_mg_shutdown(nsmh_handle h);
 
+/* ---- one process, several GPUs (multidev.cu) ------------------------------------------------
+ * The reference is ONE process with OpenMP threads (main.cpp:35, Compressor.cpp:55): initialize()
+ * once (Compressor.cpp:69-76), getFilteredReads() concurrently from every thread (Consensus.cpp:29,189).
+ * A multi handle gives that caller all GPUs of the box: the reads are split by bases over `ndev`
+ * devices and sketched in parallel, every device then pulls the other shards' sketch rows over
+ * NVLink and builds the FULL tables (global read ids), so that ANY device answers an online query
+ * alone - callers are spread over the devices round robin - and the bulk query of shard d runs on
+ * device d.  Results are those of one device holding all reads.  devices[] may name a device more
+ * than once (tests on one GPU). */
+typedef struct nsmh_multi *nsmh_multi_handle;
+int nsmh_multi_create(uint32_t k, uint32_t n, uint32_t overlap_sketch_thr, const uint64_t *rand_numbers,
+                      const int *devices, int ndev, nsmh_multi_handle *out);
+int nsmh_multi_destroy(nsmh_multi_handle m);
+int nsmh_multi_num_devices(nsmh_multi_handle m, int *ndev);
+/* same inputs as nsmh_load_reads_ascii / _dnabitset; shard boundaries: nsmh_multi_shards */
+int nsmh_multi_load_reads_ascii(nsmh_multi_handle m, const char *bases, const uint64_t *offsets,
+                                uint32_t num_reads);
+int nsmh_multi_load_reads_dnabitset(nsmh_multi_handle m, const uint8_t *packed, const uint32_t *lengths,
+                                    uint32_t num_reads);
+int nsmh_multi_num_reads(nsmh_multi_handle m, uint32_t *num_reads, uint64_t *total_bases);
+int nsmh_multi_shards(nsmh_multi_handle m, uint32_t *first_read /* [ndev + 1] */);
+int nsmh_multi_sketch(nsmh_multi_handle m);
+int nsmh_multi_get_sketches(nsmh_multi_handle m, uint64_t *out /* [num_reads * n], host */);
+int nsmh_multi_build(nsmh_multi_handle m);
+/* nsmh_query_string on one of the devices; thread-safe, re-entrant */
+int nsmh_multi_query_string(nsmh_multi_handle m, const char *s, size_t len, uint32_t *out, size_t cap,
+                            size_t *count);
+/* nsmh_query_all / _result over all shards: one CSR in global read order */
+int nsmh_multi_query_all(nsmh_multi_handle m, int rc, uint64_t *total_ids);
+int nsmh_multi_query_all_result(nsmh_multi_handle m, uint64_t *offsets /* [num_reads+1] host */,
+                                uint32_t *ids /* [total_ids] host */);
+
 /* ---- online query: ReadFilter::getFilteredReads(const std::string&, std::vector<read_t>&)
  *      (ReadFilter.h:24-25, ReadFilter.cpp:85-97).  Thread-safe, re-entrant. -------------
  * Writes min(count, cap) ids to out and the full count to *count; returns NSMH_ERANGE

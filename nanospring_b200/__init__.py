@@ -9,5 +9,5 @@ Layout:
   shard.py   read sharding + sketch all-gather across GPUs (torch.distributed plumbing)
 """
 from ._lib import NsmhError, build, lib  # noqa: F401
-from .filter import (GpuReadData, MinHashReadFilter, ReadData, rand_from_seed, reverse_complement,  # noqa: F401
+from .filter import (GpuReadData, MinHashReadFilter, MultiGpuMinHashReadFilter, ReadData, rand_from_seed, reverse_complement,  # noqa: F401
                      synth_lengths, synth_params, synth_reads_host)

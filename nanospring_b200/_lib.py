@@ -82,6 +82,19 @@ _SIGS = {
     "nsmh_mg_run": [C.c_void_p, u64p],
     "nsmh_mg_stage_ms": [C.c_void_p, C.POINTER(C.c_float)],
     "nsmh_mg_shutdown": [C.c_void_p],
+    "nsmh_multi_create": [C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)],
+    "nsmh_multi_destroy": [C.c_void_p],
+    "nsmh_multi_num_devices": [C.c_void_p, C.POINTER(C.c_int)],
+    "nsmh_multi_load_reads_ascii": [C.c_void_p, C.c_void_p, u64p, C.c_uint32],
+    "nsmh_multi_load_reads_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
+    "nsmh_multi_num_reads": [C.c_void_p, u32p, u64p],
+    "nsmh_multi_shards": [C.c_void_p, u32p],
+    "nsmh_multi_sketch": [C.c_void_p],
+    "nsmh_multi_get_sketches": [C.c_void_p, u64p],
+    "nsmh_multi_build": [C.c_void_p],
+    "nsmh_multi_query_string": [C.c_void_p, C.c_char_p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)],
+    "nsmh_multi_query_all": [C.c_void_p, C.c_int, u64p],
+    "nsmh_multi_query_all_result": [C.c_void_p, u64p, u32p],
     "nsmh_query_string": [C.c_void_p, C.c_char_p, C.c_size_t, u32p, C.c_size_t, C.POINTER(C.c_size_t)],
     "nsmh_query_strings": [C.c_void_p, C.c_void_p, u64p, C.c_uint32, u64p, u32p, C.c_size_t],
     "nsmh_query_sketches": [C.c_void_p, u64p, C.c_uint32, u64p, u32p, C.c_size_t],

@@ -17,9 +17,11 @@
 #ifndef GPU_MINHASH_READ_FILTER_H_
 #define GPU_MINHASH_READ_FILTER_H_
 
+#include <cstdio>
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ReadFilter.h"   // the reference's header: ReadFilter, ReadData, read_t, kMer_t
@@ -35,6 +37,11 @@ public:
     std::string tempDir;
     /** CUDA device ordinal **/
     int device = 0;
+    /** Optional: several GPUs for this ONE process (the reference is one process with OpenMP threads,
+     *  main.cpp:35).  With two or more entries initialize() splits the reads by bases over the devices,
+     *  every device sketches its shard and builds the tables of all reads, and getFilteredReads() sends
+     *  each calling thread to one of them (include/nsmh.h, nsmh_multi_*).  Empty: `device` alone. */
+    std::vector<int> devices;
     /** Optional: fix the n random numbers (tests / reproducible runs).  Left empty, they
      *  are drawn exactly like MinHashReadFilter::generateRandomNumbers (ReadFilter.cpp:49-63). */
     std::vector<kMer_t> randNumbers;
@@ -42,16 +49,14 @@ public:
     GpuMinHashReadFilter() = default;
     GpuMinHashReadFilter(const GpuMinHashReadFilter &) = delete;
     GpuMinHashReadFilter &operator=(const GpuMinHashReadFilter &) = delete;
-    ~GpuMinHashReadFilter() override { nsmh_destroy(h_); }
+    ~GpuMinHashReadFilter() override { release(); }
 
-    /** ReadFilter.cpp:11-47: sketch every read of rD and build the n tables, on the GPU. */
+    /** ReadFilter.cpp:11-47: sketch every read of rD and build the n tables, on the GPU(s).
+     *  The reads come from rD's own 2-bit store when ReadData exposes it (the two accessors of
+     *  a quarter of the bytes, no unpacking, no getRead() mutex), else through
+     *  getRead() as ASCII. */
     void initialize(ReadData &rD) override {
-        nsmh_destroy(h_);
-        h_ = nullptr;
-        hostOffsets_.clear();
-        if (randNumbers.size() != n) generateRandomNumbers(n);
-        check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
-                          device, &h_));
+        if (initializeFromStore(rD, 0)) return;
         const read_t numReads = rD.getNumReads();
         // Pull the reads once, sequentially (in the CLI's low-memory mode getRead() takes a global
         // mutex, ReadData.cpp:225-235), into one pinned ASCII buffer + offsets.
@@ -76,9 +81,10 @@ public:
                 used += s.size();
                 offsets[i + 1] = used;
             }
-            check(nsmh_load_reads_ascii(h_, bases, offsets.data(), numReads));
-            check(nsmh_sketch(h_));
-            check(nsmh_build(h_));
+            create();
+            if (m_) check(nsmh_multi_load_reads_ascii(m_, bases, offsets.data(), numReads));
+            else check(nsmh_load_reads_ascii(h_, bases, offsets.data(), numReads));
+            sketchAndBuild();
         } catch (...) {
             nsmh_host_free(bases);
             throw;
@@ -86,14 +92,51 @@ public:
         nsmh_host_free(bases);
     }
 
+    /** initialize() from reads that are already 2-bit packed the reference's way (DnaBitset,
+     *  dnaToBits.cpp:11-36): `packed` = the concatenated byte-aligned bitsets, lengths[i] = bases of read i.
+     *  This is what ReadData holds in memory (readData, high-memory mode) and in tempDir/readBitset
+     *  (low-memory mode, the CLI's only mode: main.cpp:40, ReadData.cpp:156-221). */
+    template <typename Len>
+    void initializeFromBitset(const uint8_t *packed, const Len *lengths, read_t numReads) {
+        std::vector<uint32_t> len32((size_t)numReads);
+        for (read_t i = 0; i < numReads; ++i) len32[i] = (uint32_t)lengths[i];
+        create();
+        if (m_) check(nsmh_multi_load_reads_dnabitset(m_, packed, len32.data(), numReads));
+        else check(nsmh_load_reads_dnabitset(h_, packed, len32.data(), numReads));
+        sketchAndBuild();
+    }
+
+    /** The same from the low-memory temp file (ReadData.cpp:181-204 writes it read after read). */
+    template <typename Len>
+    void initializeFromBitsetFile(const std::string &path, const std::vector<Len> &lengths) {
+        size_t bytes = 0;
+        for (auto l : lengths) bytes += ((size_t)l + 3) / 4;
+        uint8_t *buf = nullptr;
+        check(nsmh_host_alloc(bytes ? bytes : 1, reinterpret_cast<void **>(&buf)));
+        FILE *fp = std::fopen(path.c_str(), "rb");
+        const size_t got = fp ? std::fread(buf, 1, bytes, fp) : 0;
+        if (fp) std::fclose(fp);
+        try {
+            if (got != bytes) throw std::runtime_error("GpuMinHashReadFilter: cannot read " + path);
+            initializeFromBitset(buf, lengths.data(), (read_t)lengths.size());
+        } catch (...) {
+            nsmh_host_free(buf);
+            throw;
+        }
+        nsmh_host_free(buf);
+    }
+
     /** ReadFilter.cpp:85-97.  Re-entrant; called concurrently by all OpenMP threads. */
     void getFilteredReads(const std::string &s, std::vector<read_t> &results) override {
         results.clear();
-        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::getFilteredReads before initialize");
-        results.resize(64);
+        if (!h_ && !m_) throw std::runtime_error("GpuMinHashReadFilter::getFilteredReads before initialize");
+        // a consensus window at 30-60x coverage has tens to hundreds of candidates: start large enough that the
+        // query is not repeated (NSMH_ERANGE reports the size needed)
+        results.resize(results.capacity() > 1024 ? results.capacity() : 1024);
         for (;;) {
             size_t count = 0;
-            int rc = nsmh_query_string(h_, s.data(), s.size(), results.data(), results.size(), &count);
+            const int rc = m_ ? nsmh_multi_query_string(m_, s.data(), s.size(), results.data(), results.size(), &count)
+                              : nsmh_query_string(h_, s.data(), s.size(), results.data(), results.size(), &count);
             if (rc == NSMH_ERANGE) {
                 results.resize(count);
                 continue;
@@ -108,10 +151,10 @@ public:
      *  Consensus.cpp:185-191).  Optional fast path; results as the two single calls give. */
     void getFilteredReadsPair(const std::string &fwd, const std::string &rev, std::vector<read_t> &resFwd,
                               std::vector<read_t> &resRev) {
-        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::getFilteredReadsPair before initialize");
+        if (!h_) throw std::runtime_error("GpuMinHashReadFilter::getFilteredReadsPair before initialize (single device only)");
         std::string both = fwd + rev;
         uint64_t off[3] = {0, fwd.size(), fwd.size() + rev.size()}, out_off[3] = {0, 0, 0};
-        std::vector<read_t> ids(256);
+        std::vector<read_t> ids(2048);
         for (;;) {
             int rc = nsmh_query_strings(h_, both.data(), off, 2, out_off, ids.data(), ids.size());
             if (rc == NSMH_ERANGE) {
@@ -145,12 +188,15 @@ public:
     void initializeFromFile(const char *fileName, ReadData::Filetype filetype) {
         if (filetype != ReadData::FASTQ && filetype != ReadData::GZIP)
             throw std::runtime_error("GpuMinHashReadFilter::initializeFromFile: FASTQ or GZIP input only");
-        nsmh_destroy(h_);
-        h_ = nullptr;
-        hostOffsets_.clear();
-        if (randNumbers.size() != n) generateRandomNumbers(n);
-        check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
-                          device, &h_));
+        const std::vector<int> keep = devices;
+        devices.clear();                    // the device-side read store lives on one device
+        try {
+            create();
+        } catch (...) {
+            devices = keep;
+            throw;
+        }
+        devices = keep;
         check(nsmh_load_fastq_file(h_, fileName, filetype == ReadData::GZIP ? 1 : 0));
         check(nsmh_sketch(h_));
         check(nsmh_build(h_));
@@ -184,10 +230,48 @@ public:
     }
 
     nsmh_handle handle() const { return h_; }
+    nsmh_multi_handle multiHandle() const { return m_; }
 
 private:
     nsmh_handle h_ = nullptr;
+    nsmh_multi_handle m_ = nullptr;
     std::vector<uint64_t> hostOffsets_;     // filled by the first getRead()
+
+    void release() {
+        nsmh_destroy(h_);
+        nsmh_multi_destroy(m_);
+        h_ = nullptr;
+        m_ = nullptr;
+        hostOffsets_.clear();
+    }
+    void create() {
+        release();
+        if (randNumbers.size() != n) generateRandomNumbers(n);
+        if (devices.size() > 1)
+            check(nsmh_multi_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
+                                    devices.data(), (int)devices.size(), &m_));
+        else
+            check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
+                              devices.empty() ? device : devices[0], &h_));
+    }
+    void sketchAndBuild() {
+        if (m_) {
+            check(nsmh_multi_sketch(m_));
+            check(nsmh_multi_build(m_));
+        } else {
+            check(nsmh_sketch(h_));
+            check(nsmh_build(h_));
+        }
+    }
+    // rD's own 2-bit store, when ReadData has the accessors of INTEGRATION.md section 2 (chosen at compile time)
+    template <typename RD>
+    auto initializeFromStore(RD &rD, int) -> decltype(rD.getBitsetFilePath(), rD.getReadLengths(), bool()) {
+        if (rD.getBitsetFilePath().empty()) return false;          // high-memory mode: no temp file
+        initializeFromBitsetFile(rD.getBitsetFilePath(), rD.getReadLengths());
+        return true;
+    }
+    template <typename RD>
+    bool initializeFromStore(RD &, long) { return false; }
 
     static void check(int rc) {
         if (rc != NSMH_OK) throw std::runtime_error(std::string("nsmh: ") + nsmh_last_error());

@@ -392,6 +392,92 @@ def reverse_complement(s):
 
 
 # ---- synthetic reads (createData.py recipe; see csrc/synth.cu) -------------------------
+class MultiGpuMinHashReadFilter:
+    """MinHashReadFilter over several GPUs of ONE process (include/nsmh.h, nsmh_multi_*): the reference's
+    own process model - initialize() once (Compressor.cpp:69-76), getFilteredReads() from many threads
+    (Consensus.cpp:29,189).  Reads are split by bases and sketched in parallel, every device then holds
+    the tables of ALL reads and online queries are spread over the devices."""
+
+    def __init__(self, devices=(0,)):
+        self.k, self.n, self.overlapSketchThreshold = 23, 60, 6
+        self.tempDir = ""
+        self.devices = [int(d) for d in devices]
+        self.randNumbers = None
+        self._m = None
+
+    def close(self):
+        if self._m is not None:
+            lib().nsmh_multi_destroy(self._m)
+            self._m = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def initialize(self, rD, packed=None):
+        """rD: ReadData (ASCII) - or packed=(DnaBitset bytes, u32 lengths), the reference's 2-bit store."""
+        self.close()
+        if self.randNumbers is None:
+            self.randNumbers = rand_from_seed(int.from_bytes(os.urandom(4), "little"), self.n)
+        rnd = np.ascontiguousarray(self.randNumbers, dtype=np.uint64)
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        m = C.c_void_p()
+        check(lib().nsmh_multi_create(self.k, self.n, self.overlapSketchThreshold, rnd.ctypes.data_as(u64p), dev,
+                                      len(self.devices), C.byref(m)))
+        self._m = m
+        if packed is not None:
+            pk = np.ascontiguousarray(packed[0], dtype=np.uint8)
+            ln = np.ascontiguousarray(packed[1], dtype=np.uint32)
+            check(lib().nsmh_multi_load_reads_dnabitset(m, pk.ctypes.data, ln.ctypes.data_as(u32p), ln.size))
+        else:
+            check(lib().nsmh_multi_load_reads_ascii(m, rD.bases.ctypes.data, rD.offsets.ctypes.data_as(u64p), rD.numReads))
+        check(lib().nsmh_multi_sketch(m))
+        check(lib().nsmh_multi_build(m))
+
+    def numReads(self):
+        nr = C.c_uint32(0)
+        check(lib().nsmh_multi_num_reads(self._m, C.byref(nr), None))
+        return nr.value
+
+    def shards(self):
+        out = np.zeros(len(self.devices) + 1, dtype=np.uint32)
+        check(lib().nsmh_multi_shards(self._m, out.ctypes.data_as(u32p)))
+        return out
+
+    def sketches(self):
+        out = np.zeros((self.numReads(), self.n), dtype=np.uint64)
+        check(lib().nsmh_multi_get_sketches(self._m, out.ctypes.data_as(u64p)))
+        return out
+
+    def getFilteredReads(self, s, results=None):
+        s = s.encode() if isinstance(s, str) else bytes(s)
+        cap = 1024
+        while True:
+            out = np.empty(cap, dtype=np.uint32)
+            cnt = C.c_size_t(0)
+            rc = lib().nsmh_multi_query_string(self._m, s, len(s), out.ctypes.data_as(u32p), cap, C.byref(cnt))
+            if rc == NSMH_ERANGE:
+                cap = cnt.value
+                continue
+            check(rc)
+            break
+        res = out[:cnt.value].copy()
+        if results is not None:
+            results.clear()
+            results.extend(int(x) for x in res)
+        return res
+
+    def queryAll(self, reverseComplement=False):
+        total = C.c_uint64(0)
+        check(lib().nsmh_multi_query_all(self._m, int(bool(reverseComplement)), C.byref(total)))
+        off = np.zeros(self.numReads() + 1, dtype=np.uint64)
+        ids = np.zeros(max(total.value, 1), dtype=np.uint32)
+        check(lib().nsmh_multi_query_all_result(self._m, off.ctypes.data_as(u64p), ids.ctypes.data_as(u32p)))
+        return off, ids[:total.value]
+
+
 def synth_params(genome_len=50_000_000, genome_seed=1, read_seed=2, p_ins=0.03, p_del=0.03,
                  p_sub=0.04, p_rc=0.5):
     return SynthParams(genome_len, genome_seed, read_seed, p_ins, p_del, p_sub, p_rc)

@@ -36,6 +36,24 @@ def unpack_dnabitset(packed, lengths):
     return np.ascontiguousarray(bases), offsets
 
 
+def pack_dnabitset(bases, offsets):
+    """ASCII bases + offsets -> DnaBitset bytes + u32 lengths (dnaToBits.cpp:11-36: code (c&2)|((c&4)>>2),
+    4 bases per byte, first base in bits 7..6, every read starts on a byte)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    lengths = np.diff(offsets)
+    nbytes = (lengths + 3) // 4
+    boff = np.concatenate([[0], np.cumsum(nbytes)])
+    c = np.asarray(bases[:offsets[-1]], dtype=np.uint8)
+    code = ((c & 2) | ((c & 4) >> 2)).astype(np.uint8)
+    padded = np.zeros(4 * int(boff[-1]), dtype=np.uint8)
+    if code.size:
+        pos = np.arange(code.size, dtype=np.int64) + np.repeat(4 * boff[:-1] - offsets[:-1], lengths)
+        padded[pos] = code
+    q = padded.reshape(-1, 4)
+    packed = ((q[:, 0] << 6) | (q[:, 1] << 4) | (q[:, 2] << 2) | q[:, 3]).astype(np.uint8)
+    return np.ascontiguousarray(packed), lengths.astype(np.uint32)
+
+
 @pytest.fixture(scope="session")
 def c1_raw():
     z = np.load(os.path.join(GOLDEN, "c1_reads.npz"))

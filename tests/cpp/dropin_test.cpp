@@ -49,8 +49,41 @@ int main(int argc, char **argv) {
     gpu.tempDir = argv[5];
     gpu.randNumbers.resize(n);
     nsmh_rand_from_seed(20261017u, (uint32_t)n, gpu.randNumbers.data());
+    // DROPIN_DEVICES="0,0": several devices behind the one filter (the same device named twice on a 1-GPU box)
+    if (const char *dv = std::getenv("DROPIN_DEVICES"))
+        for (const char *p = dv; *p;) {
+            gpu.devices.push_back(std::atoi(p));
+            while (*p && *p != ',') ++p;
+            if (*p == ',') ++p;
+        }
+    const bool multi = gpu.devices.size() > 1;
     ReadFilter *rF = &gpu;                 // the caller only ever holds a ReadFilter* (Consensus.h:41)
-    rF->initialize(rD);
+    const char *mode = std::getenv("DROPIN_MODE");
+    if (mode && std::string(mode) == "bitset") {
+        // the reads as ReadData holds them: DnaBitset bytes (dnaToBits.cpp:46-71), every read byte aligned
+        std::vector<uint8_t> packed;
+        std::vector<size_t> lens(numReads);
+        for (uint32_t i = 0; i < numReads; ++i) {
+            const size_t len = offsets[i + 1] - offsets[i];
+            lens[i] = len;
+            for (size_t b = 0; b < len; b += 4) {
+                uint8_t byte = 0;
+                for (size_t j = 0; j < 4 && b + j < len; ++j) {
+                    const uint8_t c = (uint8_t)bases[offsets[i] + b + j];
+                    byte |= (uint8_t)(((c & 2) | ((c & 4) >> 2)) << (6 - 2 * j));
+                }
+                packed.push_back(byte);
+            }
+        }
+        const std::string path = std::string(argv[5]) + "/readBitset";      // ReadData.h:127
+        {
+            std::ofstream bf(path, std::ios::binary);
+            bf.write(reinterpret_cast<const char *>(packed.data()), (std::streamsize)packed.size());
+        }
+        gpu.initializeFromBitsetFile(path, lens);
+    } else {
+        rF->initialize(rD);
+    }
 
     void *ref = nsref_create(bases.data(), offsets.data(), numReads, (uint32_t)k, (uint32_t)n, (uint32_t)thr,
                              gpu.randNumbers.data(), 0, argv[5], nullptr, nullptr);
@@ -76,7 +109,7 @@ int main(int argc, char **argv) {
             if (c != resRc.size() || !std::equal(resRc.begin(), resRc.end(), want.begin())) ++mismatches;
             total += (long)c;
             queries += 2;
-            if (i % 16 == 0) {   // the paired fast path gives the same two answers
+            if (i % 16 == 0 && !multi) {   // the paired fast path gives the same two answers
                 std::vector<read_t> a, b;
                 gpu.getFilteredReadsPair(s, rc, a, b);
                 if (a != res || b != resRc) ++mismatches;
