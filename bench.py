@@ -692,6 +692,7 @@ def main():
             line["rc_query"] = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     # ---- CPU baseline: the reference's own code on this box's host cores, bounded sample ----
+    ref_for_online = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         from oracle.oracle import Oracle, RefLib
         cores = os.cpu_count() or 1
@@ -703,7 +704,7 @@ def main():
             rf = RefLib.get().create(sub.bases, sub.offsets, K, NHASH, THR, rnd, threads=cores)
             c_off, c_ids = rf.query_all(0, threads=cores)
             detail = {"sketch_ms": rf.sketch_ms, "build_ms": rf.build_ms, "query_ms": rf.query_ms}
-            rf.close()
+            ref_for_online = rf
             kind = "reference"
         else:
             orc = Oracle.get()
@@ -719,6 +720,19 @@ def main():
                                 "sample": f"first {sample_reads} reads of the workload ({sb / 1e9:.3f} Gbases), "
                                           f"sketch + tables + forward lookup, {cores} OpenMP threads",
                                 "seconds": dt, **detail}
+    # ---- online query latency: one window per call, as the consensus builder asks ----
+    if n_gpus == 1 and not args.no_legs and not args.no_e2e:
+        try:
+            import bench_legs
+            f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
+            f.sketch()
+            f.build()
+            f.synchronize()
+            line["online_query"] = bench_legs.online_leg(f, host_rd, ref_filter=ref_for_online)
+        except Exception as e:  # noqa: BLE001
+            line["online_query"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if ref_for_online is not None:
+        ref_for_online.close()
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -240,3 +240,90 @@ def run_leg(leg, steps, dist, with_parity=True):
         res["parity"] = parity_of(leg, total, dist)
         res["parity"]["seconds"] = round(time.perf_counter() - t0, 2)
     return res
+
+
+# ------------------------------------------------------------------------------------------
+def online_leg(f, host_rd, n_windows=256, window_len=10_000, thread_counts=(1, 8, 32), ref_filter=None):
+    """the production query, one consensus window per call (Consensus.cpp:168-191), through
+    nsmh_query_string from 1 / 8 / 32 host threads; latency percentiles per call and queries per second.
+    ref_filter: the reference's own MinHashReadFilter (oracle/_ref) for the same windows on one host core."""
+    import threading
+    import torch
+    from nanospring_b200 import shard
+    from nanospring_b200._lib import lib, u32p
+    from oracle.oracle import Oracle
+    L = lib()
+    rng = np.random.default_rng(5)
+    lens = np.diff(host_rd.offsets.astype(np.int64))
+    long_reads = np.flatnonzero(lens >= window_len)
+    pick = rng.choice(long_reads, size=min(n_windows, long_reads.size), replace=False)
+    windows = []
+    for r in pick:
+        s0 = int(host_rd.offsets[r]) + int(rng.integers(0, lens[r] - window_len + 1))
+        windows.append(host_rd.bases[s0:s0 + window_len].tobytes())
+
+    def run_thread(idx, reps, out_lat):
+        buf = np.empty(4096, dtype=np.uint32)
+        cnt = C.c_size_t(0)
+        p = buf.ctypes.data_as(u32p)
+        for _ in range(reps):
+            for i in idx:
+                w = windows[i]
+                t0 = time.perf_counter_ns()
+                rc = L.nsmh_query_string(f._h, w, len(w), p, 4096, C.byref(cnt))
+                out_lat.append(time.perf_counter_ns() - t0)
+                if rc != 0:
+                    raise RuntimeError("nsmh_query_string failed")
+
+    res = {"what": f"{len(windows)} windows of {window_len} bases cut from the reads, nsmh_query_string per window "
+                   f"(= ReadFilter::getFilteredReads), tables over all {host_rd.numReads} reads",
+           "window_len": window_len, "threads": {}}
+    for nt in thread_counts:
+        # warm-up with the same number of threads: every concurrent caller gets its own workspace (stream, mapped
+        # buffers) the first time the pool runs dry
+        ths = [threading.Thread(target=run_thread, args=(range(t, len(windows), nt), 1, [])) for t in range(nt)]
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        lats = [[] for _ in range(nt)]
+        ths = [threading.Thread(target=run_thread, args=(range(t, len(windows), nt), 2, lats[t])) for t in range(nt)]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        wall = time.perf_counter() - t0
+        lat = np.concatenate([np.asarray(x, dtype=np.float64) for x in lats]) / 1e3
+        res["threads"][str(nt)] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
+                                   "queries_per_s": lat.size / wall}
+    res["note"] = ("host threads are Python threads here (ctypes releases the GIL inside the call, the bookkeeping between calls "
+                   "is serialised): the C++ drop-in test under OpenMP reports the same per-call latency, profiles/r2_dropin_latency_*.log")
+    # parity of the fused online kernel: the candidates of a few windows against the definition evaluated on the
+    # sketches of all reads, with the window's sketch computed by the CPU oracle
+    S_all = shard.sketches_as_tensor(f, host_rd.numReads)
+    orc = Oracle.get()
+    ok = True
+    for w in windows[:12]:
+        wb = np.frombuffer(w, dtype=np.uint8)
+        sk = orc.sketch_all(np.concatenate([wb, np.zeros(1, np.uint8)]), np.asarray([0, wb.size], dtype=np.uint64), f.k, f.n,
+                            np.asarray(f.randNumbers, dtype=np.uint64))
+        q = torch.from_numpy(sk.view(np.int64)).to(S_all.device)
+        want = torch.nonzero((S_all == q[0]).sum(dim=1) >= max(int(f.overlapSketchThreshold), 1)).flatten().cpu().numpy().astype(np.uint32)
+        got = f.getFilteredReads(w)
+        ok = ok and got.size == want.size and bool((got == want).all())
+    res["parity"] = {"ok": bool(ok), "windows_checked": min(12, len(windows)),
+                     "against": "definition on the sketches of all reads, window sketch by the CPU oracle"}
+    if ref_filter is not None:
+        lat = []
+        out = np.zeros(ref_filter.N + 1, dtype=np.uint32)
+        po = out.ctypes.data_as(u32p)
+        for w in windows[:64]:
+            t0 = time.perf_counter_ns()
+            ref_filter.ref.lib.nsref_query_string(ref_filter.h, w, len(w), po, out.size)
+            lat.append(time.perf_counter_ns() - t0)
+        lat = np.asarray(lat, dtype=np.float64) / 1e3
+        res["cpu_reference"] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99)),
+                                "what": f"the reference's getFilteredReads(string) on 64 of the windows, one host core, "
+                                        f"tables over {ref_filter.N} reads (the window's sketch dominates its cost)"}
+    return res

@@ -57,12 +57,15 @@ void DevBuf::release(cudaStream_t s) {
 static void free_ws(QueryWs &ws, cudaStream_t s) {
     DevBuf *bufs[] = {&ws.qsketch, &ws.pval, &ws.pcnt, &ws.heavy_list, &ws.heavy2_list, &ws.mid_ids, &ws.counters, &ws.hc, &ws.hoff, &ws.hout, &ws.hcnt, &ws.hstart, &ws.pairs, &ws.pairs_alt, &ws.flags,
                       &ws.qcount, &ws.qpos, &ws.tmp_ids, &ws.out_off, &ws.out_ids, &ws.nsel, &ws.cub_tmp, &ws.str_bases,
-                      &ws.tile_start};
+                      &ws.tile_start, &ws.online_scratch};
     for (DevBuf *b : bufs) b->release(s);
     ws.str_reads.release(s);
     if (ws.h_pinned) cudaFreeHost(ws.h_pinned);
     ws.h_pinned = nullptr;
     ws.h_pinned_cap = 0;
+    if (ws.h_online) cudaFreeHost(ws.h_online);
+    ws.h_online = nullptr;
+    ws.h_online_cap = 0;
 }
 
 static int ensure_pinned(QueryWs &ws, size_t bytes) {
@@ -842,6 +845,10 @@ static int query_strings_impl(nsmh_ctx *c, QueryWs &ws, const char *bases, const
     for (uint32_t i = 0; i < nq; ++i)
         if (offsets[i + 1] < offsets[i]) return fail(NSMH_EINVAL, "query_strings: offsets must be non-decreasing");
     if (offsets[0] != 0) return fail(NSMH_EINVAL, "query_strings: offsets[0] must be 0");
+    {
+        const int rc = online_query(c, ws, bases, offsets, nq, offsets_out, ids_out, cap);
+        if (rc != 1) return rc;             // answered (or failed for good); 1 = take the general path below
+    }
     // stage strings + offsets through pinned memory so concurrent callers never block each other
     const size_t off_bytes = ((size_t)nq + 1) * sizeof(uint64_t);
     NSMH_TRY(ensure_pinned(ws, off_bytes + total + 16));

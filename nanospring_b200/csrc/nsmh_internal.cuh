@@ -94,6 +94,11 @@ struct QueryWs {
     DevBuf tile_start;  // sketch scratch
     void *h_pinned = nullptr;
     size_t h_pinned_cap = 0;
+    // online fast path (online_kernels.cuh): one mapped host block that the kernel reads the strings from and
+    // writes the answer to, and a few words of device scratch
+    uint8_t *h_online = nullptr;
+    size_t h_online_cap = 0;
+    DevBuf online_scratch;
     uint64_t last_total = 0;
     uint64_t last_pairs = 0;
     uint32_t last_nq = 0;
@@ -193,6 +198,9 @@ int preclear_tables(nsmh_ctx *c, uint32_t rows);
 int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
 
 // ---- query.cu ----------------------------------------------------------------
+// one fused kernel per online query (online_kernels.cuh); 1 = the general path must take over
+int online_query(nsmh_ctx *c, QueryWs &ws, const char *bases, const uint64_t *offsets, uint32_t nq, uint64_t *offsets_out,
+                 uint32_t *ids_out, size_t cap);
 int query_sketches_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq,
                           cudaStream_t s);
 int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint32_t nq, cudaStream_t s);

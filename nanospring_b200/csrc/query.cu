@@ -24,6 +24,7 @@
 
 #include "nsmh_internal.cuh"
 #include "query_kernels.cuh"
+#include "online_kernels.cuh"
 
 namespace nsmh {
 
@@ -557,5 +558,110 @@ int probe_lists_device(nsmh_ctx *c, QueryWs &ws, const uint64_t *d_qsketch, uint
     ws.last_pairs = total;
     return NSMH_OK;
 }
+
+// The online fast path: ONE kernel reads the strings from mapped host memory, sketches, probes, counts and
+// writes the answer back to mapped host memory (online_kernels.cuh); the host waits for the stream once.
+// Returns 1 when the general path must take over (long strings, heavy id lists, results beyond the buffer).
+static constexpr uint32_t kOnlineMaxQueries = 8;
+static bool online_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("NSMH_ONLINE_FUSED");
+        return !(e && *e && atoi(e) == 0);
+    }();
+    return on;
+}
+
+int online_query(nsmh_ctx *c, QueryWs &ws, const char *bases, const uint64_t *offsets, uint32_t nq,
+                        uint64_t *offsets_out, uint32_t *ids_out, size_t cap) {
+    if (!online_enabled() || nq == 0 || nq > kOnlineMaxQueries || c->n > 32 * (uint32_t)kRegListsMax || c->sketch_mode != 0) return 1;
+    uint64_t max_len = 0, text_bytes = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        max_len = std::max(max_len, len);
+        text_bytes += (len + 15 & ~15ULL) + 16;
+    }
+    if (max_len > kOnlineMaxBases) return 1;
+    cudaStream_t s = ws.stream;
+    // mapped block: [start nq][len nq][qpos nq] u64 | [qcount nq] u32 | ids [nq][kOnlineIdsPerQuery] u32 | text
+    const size_t head = (size_t)kOnlineMaxQueries * (3 * sizeof(uint64_t) + sizeof(uint32_t));
+    const size_t ids_off = (head + 15) & ~(size_t)15;
+    const size_t text_off = ids_off + (size_t)kOnlineMaxQueries * kOnlineIdsPerQuery * sizeof(uint32_t);
+    const size_t need = text_off + text_bytes + 64;
+    if (need > ws.h_online_cap) {
+        if (ws.h_online) cudaFreeHost(ws.h_online);
+        ws.h_online = nullptr;
+        ws.h_online_cap = 0;
+        const size_t want = need + need / 2 + (64 << 10);
+        NSMH_CK(cudaHostAlloc(reinterpret_cast<void **>(&ws.h_online), want, cudaHostAllocMapped | cudaHostAllocPortable));
+        ws.h_online_cap = want;
+    }
+    NSMH_TRY(ws.online_scratch.ensure((size_t)kOnlineMaxQueries * (8 * sizeof(uint64_t) + sizeof(uint32_t)), s));
+    uint64_t *h_start = reinterpret_cast<uint64_t *>(ws.h_online), *h_len = h_start + kOnlineMaxQueries,
+             *h_qpos = h_len + kOnlineMaxQueries;
+    uint32_t *h_qcount = reinterpret_cast<uint32_t *>(h_qpos + kOnlineMaxQueries);
+    uint32_t *h_ids = reinterpret_cast<uint32_t *>(ws.h_online + ids_off);
+    uint8_t *h_text = ws.h_online + text_off;
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        const uint64_t len = offsets[i + 1] - offsets[i];
+        h_start[i] = at;
+        h_len[i] = len;
+        h_qpos[i] = ~0ULL;
+        h_qcount[i] = 0;
+        if (len) memcpy(h_text + at, bases + offsets[i], len);
+        at += (len + 15 & ~15ULL) + 16;
+    }
+    uint8_t *d_base = nullptr;
+    NSMH_CK(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_base), ws.h_online, 0));
+    OnlineArgs a;
+    a.text = d_base + text_off;
+    a.start = reinterpret_cast<const uint64_t *>(d_base);
+    a.len = a.start + kOnlineMaxQueries;
+    a.qpos = reinterpret_cast<uint64_t *>(d_base) + 2 * kOnlineMaxQueries;
+    a.qcount = reinterpret_cast<uint32_t *>(a.qpos + kOnlineMaxQueries);
+    a.tmp_ids = reinterpret_cast<uint32_t *>(d_base + ids_off);
+    a.counters = ws.online_scratch.as<unsigned long long>();
+    a.heavy_scratch = reinterpret_cast<uint32_t *>(a.counters + 8 * kOnlineMaxQueries);
+    a.rnd = c->d_rand.as<uint64_t>();
+    a.sketch_out = nullptr;
+    a.k = c->k;
+    a.thr = c->thr ? c->thr : 1;
+    Tables &T = c->tables;
+    a.tables.qsk = nullptr;
+    a.tables.slots = T.slots.as<Slot>();
+    a.tables.ids = T.ids.as<uint32_t>();
+    a.tables.pval = a.tables.pcnt = nullptr;
+    a.tables.cap = T.cap;
+    a.tables.n = c->n;
+    const uint32_t ml = (uint32_t)((max_len + 1023) & ~1023ULL);
+    const size_t smem = online_smem_bytes(ml, c->n);
+    if (smem > 48 * 1024) NSMH_CK(cudaFuncSetAttribute(online_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    online_query_kernel<<<nq, kOnlineThreads, smem, s>>>(a, ml);
+    ++ws.launches;
+    NSMH_CK(cudaGetLastError());
+    NSMH_CK(cudaStreamSynchronize(s));
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (h_qpos[i] == ~0ULL || h_qpos[i] + h_qcount[i] > kOnlineIdsPerQuery) return 1;      // heavy tiers / too many results
+        total += h_qcount[i];
+    }
+    uint64_t o = 0;
+    for (uint32_t i = 0; i < nq; ++i) {
+        if (offsets_out) offsets_out[i] = o;
+        const uint32_t *src = h_ids + (size_t)i * kOnlineIdsPerQuery + h_qpos[i];
+        for (uint32_t r = 0; r < h_qcount[i]; ++r, ++o)
+            if (ids_out && o < cap) ids_out[o] = src[r];
+    }
+    if (offsets_out) offsets_out[nq] = o;
+    ws.last_nq = nq;
+    ws.last_total = total;
+    if (total > cap) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "query: output needs %llu ids, capacity is %zu", (unsigned long long)total, cap);
+        return fail(NSMH_ERANGE, buf);
+    }
+    return NSMH_OK;
+}
+
 
 } // namespace nsmh

@@ -509,14 +509,14 @@ struct CountArgs {
 //   beyond     handed to the counting-filter tier / the global path
 // Results go to tmp_ids in completion order; a prefix sum over qcount and csr_place_kernel then
 // produce the CSR.
+// queries q_first, q_first + q_stride, ... < a.nq by ONE warp; buf = kWarpWords warp-private words
 template <typename Src, int kRegLists = kRegListsMax>
-__device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf) {
+__device__ __forceinline__ void count_queries(Src src, CountArgs a, uint32_t *buf, uint32_t q_first, uint32_t q_stride) {
     constexpr int kRegIds = Src::kInlinePairs ? 2 * kRegLists : kRegLists;      // ids per lane held in registers
     constexpr int kRegMaxIds = 32 * kRegIds;     // gathered ids that are counted in registers
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t *buf = s_buf + (size_t)warp * kWarpWords;
+    const int lane = threadIdx.x & 31;
     uint32_t *res = buf + kLookupCap;           // kResWords entries
-    const uint32_t total_warps = gridDim.x * kLookupWarps;
+    const uint32_t total_warps = q_stride;
     const uint32_t subs = src.subs();
     const bool keep_lists = subs <= (uint32_t)kRegMaxIds;
     unsigned long long pairs_local = 0, results_local = 0;
@@ -524,8 +524,8 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
 #pragma unroll
     for (int c = 0; c < kRegLists; ++c) ctx[c] = src.context(min((uint32_t)(c * 32 + lane), subs ? subs - 1 : 0u));
 
-    for (uint32_t q = blockIdx.x * kLookupWarps + warp; q < a.nq; q += total_warps) {
-        if (q + total_warps < a.nq) src.prefetch(q + total_warps, lane);    // the next query's keys, into L2
+    for (uint32_t q = q_first; q < a.nq; q += total_warps) {
+        if ((uint64_t)q + total_warps < a.nq) src.prefetch(q + total_warps, lane);    // the next query's keys, into L2
         ListRef r[kRegLists];
         uint32_t v[kRegIds];
         uint32_t T = 0xFFFFFFFFu;           // gathered ids (saturating)
@@ -700,6 +700,14 @@ __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf
     }
     if (lane == 0 && pairs_local) atomicAdd(a.counters + 1, pairs_local);
     if (lane == 0 && results_local) atomicAdd(a.counters + 2, results_local);
+}
+
+// the lookup kernel's body: blocks of kLookupWarps warps, a warp per query
+template <typename Src, int kRegLists = kRegListsMax>
+__device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf) {
+    const uint32_t warp = threadIdx.x >> 5;
+    count_queries<Src, kRegLists>(src, a, s_buf + (size_t)warp * kWarpWords, blockIdx.x * kLookupWarps + warp,
+                                  gridDim.x * kLookupWarps);
 }
 
 // ------------------------------------------------------------------ counting-filter tier --

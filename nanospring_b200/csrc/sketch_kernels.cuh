@@ -10,6 +10,7 @@
 #endif
 
 #include "nsmh_constants.h"
+#include "sketch_device.cuh"
 
 namespace nsmh {
 
@@ -28,8 +29,6 @@ struct SketchArgs {
     int lambda_log2;
     uint32_t tile_words;        // words (16 k-mer starts each) per tile
 };
-
-__device__ __forceinline__ uint64_t kmer_mask(uint32_t k) { return (1ULL << (2 * k)) - 1; }
 
 // ---- row init + tile counts ---------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -73,13 +72,6 @@ __device__ __forceinline__ uint32_t find_read_of_tile(const uint32_t *__restrict
     return lo;
 }
 
-struct TileGeom {
-    uint32_t read;
-    uint64_t rb;        // first base of the read (global)
-    uint64_t nk;        // number of k-mers
-    uint64_t w_begin, w_end;   // word range of this tile (global word indices)
-};
-
 __device__ __forceinline__ TileGeom tile_geom(const SketchArgs &a, uint32_t tile) {
     TileGeom g;
     g.read = a.tile_read ? a.tile_read[tile] : find_read_of_tile(a.tile_start, a.n_reads, tile);
@@ -91,28 +83,12 @@ __device__ __forceinline__ TileGeom tile_geom(const SketchArgs &a, uint32_t tile
     return g;
 }
 
-// valid k-mer start positions of word w: j in [lo, hi)
-__device__ __forceinline__ void valid_range(const TileGeom &g, uint64_t w, int &lo, int &hi) {
-    uint64_t p0 = w * kWordBases;
-    lo = g.rb > p0 ? (int)(g.rb - p0) : 0;
-    uint64_t end = g.rb + g.nk;   // one past the last k-mer start
-    hi = end >= p0 + kWordBases ? kWordBases : (end > p0 ? (int)(end - p0) : 0);
-}
-
 __device__ __forceinline__ int filter_bits(uint64_t nk, int lambda_log2, int max_bits, uint32_t k) {
     int b = 63 - __clzll((long long)nk) - lambda_log2;
     b = b < 0 ? 0 : b;
     b = b > max_bits ? max_bits : b;
     b = b > 2 * (int)k ? 2 * (int)k : b;
     return b;
-}
-
-// 64-bit k-mer starting at base j of word w0 (w1, w2 are the following words)
-__device__ __forceinline__ uint64_t kmer_at(uint32_t w0, uint32_t w1, uint32_t w2, int j, int kshift,
-                                            uint32_t &h32) {
-    h32 = __funnelshift_l(w1, w0, 2 * j);
-    uint32_t l32 = __funnelshift_l(w2, w1, 2 * j);
-    return (((uint64_t)h32 << 32) | l32) >> kshift;
 }
 
 // ---- bulk copy + mbarrier (sm_90+/sm_100a PTX) -------------------------------------
@@ -402,19 +378,6 @@ sketch_missing_kernel(SketchArgs a, uint32_t *__restrict__ list, unsigned int *_
             if (miss) list[base + __popc(m & ((1u << lane) - 1))] = (uint32_t)t;
         }
     }
-}
-
-// min over the k-mers starting in word w (positions [lo, hi)) of (k-mer ^ rlo), full 64 bits
-__device__ __forceinline__ uint64_t word_min64(const uint32_t *__restrict__ W, uint64_t w, int lo, int hi,
-                                               int kshift, uint64_t rlo) {
-    const uint32_t w0 = __ldg(W + w), w1 = __ldg(W + w + 1), w2 = __ldg(W + w + 2);
-    uint64_t best = ~0ULL;
-    for (int j = lo; j < hi; ++j) {
-        uint32_t h32;
-        const uint64_t y = kmer_at(w0, w1, w2, j, kshift, h32) ^ rlo;
-        best = y < best ? y : best;
-    }
-    return best;
 }
 
 // One warp per listed entry.  The scan works on the leading 32 bits of y = k-mer ^ rlo only

@@ -7,6 +7,9 @@
 // run on the GPU box by tests/test_gpu_dropin.py.  Prints "DROPIN OK" on success.
 #include <omp.h>
 
+#include <algorithm>
+#include <chrono>
+
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -90,9 +93,16 @@ int main(int argc, char **argv) {
     if (!ref) return 3;
 
     long mismatches = 0, queries = 0, total = 0;
+    std::vector<std::vector<double>> lat_gpu(omp_get_max_threads()), lat_ref(omp_get_max_threads());
+    const auto wall0 = std::chrono::steady_clock::now();
 #pragma omp parallel reduction(+ : mismatches, queries, total)
     {
         std::string s, rc;
+        auto &lg = lat_gpu[omp_get_thread_num()];
+        auto &lr = lat_ref[omp_get_thread_num()];
+        auto us = [](std::chrono::steady_clock::time_point a) {
+            return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - a).count();
+        };
         std::vector<read_t> res, resRc, want((size_t)numReads + 1);
 #pragma omp for schedule(dynamic, 4)
         for (read_t i = 0; i < numReads; ++i) {
@@ -100,9 +110,15 @@ int main(int argc, char **argv) {
             if (s.size() > 3000) s = s.substr(s.size() / 3, 2500);      // a window, like addRelatedReads
             rc.clear();
             ReadData::toReverseComplement(s.begin(), s.end(), std::inserter(rc, rc.end()));
+            auto t0 = std::chrono::steady_clock::now();
             rF->getFilteredReads(s, res);
+            lg.push_back(us(t0));
+            t0 = std::chrono::steady_clock::now();
             rF->getFilteredReads(rc, resRc);
+            lg.push_back(us(t0));
+            t0 = std::chrono::steady_clock::now();
             size_t c = nsref_query_string(ref, s.data(), s.size(), want.data(), want.size());
+            lr.push_back(us(t0));
             if (c != res.size() || !std::equal(res.begin(), res.end(), want.begin())) ++mismatches;
             total += (long)c;
             c = nsref_query_string(ref, rc.data(), rc.size(), want.data(), want.size());
@@ -117,6 +133,17 @@ int main(int argc, char **argv) {
         }
     }
     nsref_destroy(ref);
+    const double wall_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - wall0).count();
+    auto pct = [](std::vector<std::vector<double>> &v, double p) {
+        std::vector<double> all;
+        for (auto &x : v) all.insert(all.end(), x.begin(), x.end());
+        if (all.empty()) return 0.0;
+        std::sort(all.begin(), all.end());
+        return all[std::min(all.size() - 1, (size_t)(p * all.size()))];
+    };
+    std::printf("latency per getFilteredReads call, %d OpenMP threads (windows <= 2500 bases): GPU filter p50 %.1f us p99 %.1f us, "
+                "reference filter p50 %.1f us p99 %.1f us; whole loop %.3f s\n", omp_get_max_threads(), pct(lat_gpu, 0.5),
+                pct(lat_gpu, 0.99), pct(lat_ref, 0.5), pct(lat_ref, 0.99), wall_s);
     std::printf("threads %d queries %ld candidate ids %ld mismatches %ld\n", omp_get_max_threads(), queries,
                 total, mismatches);
     if (mismatches) return 1;

@@ -11,7 +11,8 @@
 #           launch  ncu launch list of a short bench run (per-launch device times: compare SHARES)
 #           ncu     ncu --set full of one launch of each hot kernel, raw + source pages exported as CSV
 #           sweep   BASELINE configs at full size with their parity checks (tests/config_sweep.py)
-#           ab      small-k lookup A/B (tools/mid_tier_ab.py) and the FASTQ-ingest kernels (tools/ingest_sweep.py)
+#           ab      the remaining switches (speculative placement, table slots per read, tile size), small-k lookup A/B
+#                   (tools/mid_tier_ab.py) and the FASTQ-ingest kernels (tools/ingest_sweep.py)
 #           peer    the peer-memory multi-rank path with 4 and 8 ranks sharing one device
 #           micro   tools/micro: the integer roof (int_roof -> copy to profiles/int_roof.json, bench.py reads it)
 #                   and the random-slot atomics benchmark
@@ -28,10 +29,28 @@ SECTION=tests
 if want; then
     (time timeout 400 python -m pytest tests -m gpu -x -q --durations=10) > "$OUT/pytest_gpu_$TAG.log" 2>&1
     tail -n 3 "$OUT/pytest_gpu_$TAG.log"
-    # experimental kernel variants (default off): parity before any of them is switched on
+    # host flows that are not the default (NSMH_LOOKUP_SPECULATE=0 etc.)
     (time NSMH_TEST_EXPERIMENTS=1 timeout 200 python -m pytest tests/test_gpu_parity.py -q -k experiment) \
         > "$OUT/pytest_experiments_$TAG.log" 2>&1
     tail -n 3 "$OUT/pytest_experiments_$TAG.log"
+    # the C++ drop-in under OpenMP: per-call latency of the online query next to the reference's
+    if [[ -x oracle/_ref/dropin_test ]]; then
+        python - <<'PY' > "$OUT/dropin_latency_$TAG.log" 2>&1
+import os, struct, subprocess, tempfile
+import numpy as np
+import nanospring_b200 as ns
+lengths = ns.synth_lengths(4000, 6000, seed=21)
+rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=400_000, genome_seed=3, read_seed=4, p_ins=0.01, p_del=0.01, p_sub=0.02))
+td = tempfile.mkdtemp()
+p = os.path.join(td, "reads.bin")
+with open(p, "wb") as f:
+    f.write(struct.pack("<I", rd.offsets.size - 1)); f.write(rd.offsets.astype(np.uint64).tobytes()); f.write(rd.bases.tobytes())
+for thr in (1, 8, 32):
+    r = subprocess.run(["oracle/_ref/dropin_test", p, "23", "60", "6", td], capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS=str(thr)))
+    print(r.stdout.strip()); print(r.stderr.strip()[-300:])
+PY
+        cat "$OUT/dropin_latency_$TAG.log"
+    fi
 fi
 
 SECTION=bench
@@ -44,7 +63,7 @@ fi
 SECTION=launch
 if want; then
     timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
-        --log-file "$OUT/launches_$TAG.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline \
+        --log-file "$OUT/launches_$TAG.csv" python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-legs \
         > "$OUT/bench_under_ncu_$TAG.log" 2>&1
     python tools/launch_list.py "$OUT/launches_$TAG.csv" 40 > "$OUT/launches_$TAG.txt" 2>&1
 fi
@@ -54,7 +73,7 @@ if want; then
     # -s skips the warm-up launches of each kernel, -c 1 captures one launch; ~40 replays each
     for K in sketch_filter_kernel table_insert_kernel count_kernel pack_ascii_kernel sketch_fixup_kernel; do
         timeout 200 ncu --set full --clock-control none --import-source on -k "regex:$K" -s 3 -c 1 \
-            -o "$OUT/prof_${K}_$TAG" -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e \
+            -o "$OUT/prof_${K}_$TAG" -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-legs \
             > "$OUT/ncu_${K}_$TAG.log" 2>&1
         if [[ -f "$OUT/prof_${K}_$TAG.ncu-rep" ]]; then
             ncu -i "$OUT/prof_${K}_$TAG.ncu-rep" --page raw --csv > "$OUT/prof_${K}_${TAG}_raw.csv" 2>/dev/null
@@ -72,22 +91,18 @@ fi
 
 SECTION=ab
 if want; then
-    # filter kernel: default phase 2 vs the balanced one (NSMH_SKETCH_BALANCED), device-resident step only
-    # ... the lookup with / without the speculative placement (NSMH_LOOKUP_SPECULATE), the fix-up scan with
-    # 4 / 8 words per lane and step (NSMH_FIXUP_WIDTH), the filter density (NSMH_LAMBDA_LOG2: a cheaper
-    # phase 2 moves the optimum towards fewer fix-ups); last line: everything together
-    for V in "0 0 4 2" "1 0 4 2" "0 1 4 2" "0 0 8 2" "0 0 4 3" "1 0 4 3" "1 1 4 3"; do
+    # switches that still exist: speculative placement of the lookup off / on, table slots per read, sketch tile size
+    for V in "1 2 640" "0 2 640" "1 4 640" "1 2 512"; do
         set -- $V
-        NSMH_SKETCH_BALANCED=$1 NSMH_LOOKUP_SPECULATE=$2 NSMH_FIXUP_WIDTH=$3 NSMH_LAMBDA_LOG2=$4 timeout 120 python bench.py \
-            --steps 10 --no-cpu-baseline --no-e2e --no-ingest > "$OUT/bench_bal$1_spec$2_fix$3_lam$4_$TAG.json" \
-            2> "$OUT/bench_bal$1_spec$2_fix$3_lam$4_$TAG.err"
-        python - "$OUT/bench_bal$1_spec$2_fix$3_lam$4_$TAG.json" "$1" "$2" "$3" "$4" <<'PY'
+        NSMH_LOOKUP_SPECULATE=$1 NSMH_TABLE_SLOTS_PER_READ=$2 NSMH_TILE_WORDS=$3 timeout 120 python bench.py \
+            --steps 10 --no-cpu-baseline --no-e2e --no-ingest --no-legs > "$OUT/bench_spec$1_slots$2_tile$3_$TAG.json" \
+            2> "$OUT/bench_spec$1_slots$2_tile$3_$TAG.err"
+        python - "$OUT/bench_spec$1_slots$2_tile$3_$TAG.json" "$1" "$2" "$3" <<'PY'
 import json, sys
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 p = d["phases_last_step"]
-print(f"balanced={sys.argv[2]} speculate={sys.argv[3]} fixup_width={sys.argv[4]} lambda_log2={sys.argv[5]}: "
-      f"ms/step {d['ms_per_step']:.4f}  sketch {p['sketch_ms']:.4f} (main kernel {p['sketch_main_kernel_ms']:.4f})  "
-      f"query {p['query_ms']:.4f}")
+print(f"speculate={sys.argv[2]} slots_per_read={sys.argv[3]} tile_words={sys.argv[4]}: ms/step {d['ms_per_step']:.4f}  "
+      f"sketch {p['sketch_ms']:.4f} (main kernel {p['sketch_main_kernel_ms']:.4f})  build {p['build_ms']:.4f}  query {p['query_ms']:.4f}")
 PY
     done
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
