@@ -576,6 +576,7 @@ def main():
             check(lib().nsmh_set_sketch_mode(f._h, 0))
             f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
             f.sketch()
+            f.build()
             roofline_brute = {"kernel": "sketch_brute_kernel", "kernel_ms": bms}
         except Exception as e:  # noqa: BLE001
             roofline_brute = {"error": f"{type(e).__name__}: {e}"[:300]}
