@@ -78,7 +78,7 @@ def check_world(L, orc, S, rows, thr, **kw):
 @pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
 def test_world_of_ranks_equals_oracle(emul, orc, world):
     n, thr = 60, 6
-    S = sketch_matrix(orc, 23, n, seed=world + 40, n_reads=500)
+    S = sketch_matrix(orc, 23, n, seed=world + 40, n_reads=180)
     total = S.shape[0]
     rng = np.random.default_rng(world)
     cuts = np.sort(rng.choice(np.arange(1, total), size=world - 1, replace=False)) if world > 1 else np.zeros(0, int)
@@ -93,7 +93,7 @@ def test_world_of_ranks_equals_oracle(emul, orc, world):
 def test_odd_hash_count_empty_rank_and_inbox_overflow(emul, orc):
     """n = 30 (not a multiple of 4: scalar key loads, odd column blocks), a rank without
     reads, and inboxes far too small for the groups (they are then read from the owners)."""
-    S = sketch_matrix(orc, 15, 30, seed=9, n_reads=400)
+    S = sketch_matrix(orc, 15, 30, seed=9, n_reads=150)
     total = S.shape[0]
     check_world(emul, orc, S, [total // 3, 0, total - total // 3], 3)
     check_world(emul, orc, S, [total // 2, total - total // 2], 3, inbox_cap=48)

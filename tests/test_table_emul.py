@@ -49,7 +49,7 @@ def query_all(L, qsk, thr, grid=2):
     return out
 
 
-def sketch_matrix(orc, k, n, seed, n_reads=700, mean=1200, dup=True):
+def sketch_matrix(orc, k, n, seed, n_reads=200, mean=1200, dup=True):
     """sketches of synthetic reads at low error (real overlaps) plus duplicated reads (groups of many
     sizes in every table), short reads (the all-zero / all-ones rows of SURVEY S5) and the key ~0"""
     rnd = ns.rand_from_seed(seed, n)
@@ -59,7 +59,7 @@ def sketch_matrix(orc, k, n, seed, n_reads=700, mean=1200, dup=True):
                                                       p_ins=0.01, p_del=0.01, p_sub=0.01))
     sk = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
     if dup:
-        reps = np.concatenate([np.repeat(np.arange(10, 20), 3), np.repeat(np.arange(40, 43), 40), np.arange(n_reads)])
+        reps = np.concatenate([np.repeat(np.arange(10, 20), 3), np.repeat(np.arange(40, 43), 24), np.arange(n_reads)])
         sk = sk[np.random.default_rng(seed).permutation(reps)]
     return np.ascontiguousarray(sk)
 
