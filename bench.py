@@ -412,6 +412,10 @@ def main():
         return f.queryAll(False, fetch=False)
 
     def e2e_step():
+        if world == 1:
+            # the reference's own call: initialize(ReadData&) = load + sketch + build (pipelined inside the library)
+            f.initialize(host_rd)
+            return f.queryAll(False, fetch=True)
         f.load(host_rd)
         f.sketch()
         if pf is not None:
@@ -496,9 +500,7 @@ def main():
             h_packed, len32 = dnabitset_host(d_bases, offsets)
 
             def e2e_packed_step():
-                f.load_dnabitset(h_packed, len32)
-                f.sketch()
-                f.build()
+                f.initialize_dnabitset(h_packed, len32)
                 return f.queryAll(False, fetch=True)
 
             for _ in range(2):
@@ -507,7 +509,7 @@ def main():
             e2e_packed = {"value": all_bases * args.steps / (ms_p * 1e-3) / 1e9, "unit": "Gbases/s",
                           "h2d_bytes_per_step": int(h_packed.nbytes + len32.nbytes), "d2h_bytes_per_step": int(off_p.nbytes + ids_p.nbytes),
                           "ms_per_step": ms_p / args.steps, "same_csr_as_ascii_path": bool((off_p == off).all() and (ids_p == ids).all()),
-                          "input": "DnaBitset bytes + u32 lengths in host memory (nsmh_load_reads_dnabitset)"}
+                          "input": "DnaBitset bytes + u32 lengths in host memory (nsmh_initialize_dnabitset)"}
             del h_packed
         except Exception as e:  # noqa: BLE001
             e2e_packed = {"error": f"{type(e).__name__}: {e}"[:300]}
@@ -655,7 +657,10 @@ def main():
                    "step": "pack + sketch + build tables + bulk forward lookup, CSR left on device"},
         "phases_last_step": phases,
         "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "call": ("MinHashReadFilter.initialize(ReadData) [nsmh_initialize_ascii: load + sketch + build, pipelined] + queryAll, "
+                         "pinned host ASCII in, CSR in host memory out" if world == 1 else
+                         "load + sketch + multi-GPU build + queryAll, pinned host ASCII in, CSR in host memory out")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,

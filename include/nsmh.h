@@ -84,6 +84,15 @@ int nsmh_load_reads_ascii_device(nsmh_handle h, const char *d_bases, const uint6
  * lengths[i] = bases of read i.  Host buffers.  Bytes are taken as exact A/C/G/T. */
 int nsmh_load_reads_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32_t *lengths,
                               uint32_t num_reads);
+/* MinHashReadFilter::initialize(ReadData&) in one call (ReadFilter.cpp:11-47: sketch every read, then
+ * populateHashTables) = nsmh_load_reads_* + nsmh_sketch + nsmh_build, pipelined: the reads that a chunk of
+ * the copy completes are packed and sketched while the following chunks are still crossing PCIe, and the
+ * tables are built behind the last chunk.  Returns as soon as the last byte has left the caller's buffers;
+ * the device finishes in stream order, so any later call on the handle sees the finished tables.  Results
+ * are those of the three separate calls, bit for bit (tests/test_gpu_parity.py). */
+int nsmh_initialize_ascii(nsmh_handle h, const char *bases, const uint64_t *offsets, uint32_t num_reads);
+int nsmh_initialize_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32_t *lengths,
+                              uint32_t num_reads);
 int nsmh_num_reads(nsmh_handle h, uint32_t *num_reads, uint64_t *total_bases);
 
 /* ---- FASTQ ingest on the device (replaces ReadData::loadFromFile for

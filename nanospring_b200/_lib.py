@@ -55,6 +55,8 @@ _SIGS = {
     "nsmh_load_reads_ascii": [C.c_void_p, C.c_void_p, u64p, C.c_uint32],
     "nsmh_load_reads_ascii_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64],
     "nsmh_load_reads_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
+    "nsmh_initialize_ascii": [C.c_void_p, C.c_void_p, u64p, C.c_uint32],
+    "nsmh_initialize_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
     "nsmh_num_reads": [C.c_void_p, u32p, u64p],
     "nsmh_set_params": [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, u64p],
     "nsmh_load_fastq": [C.c_void_p, C.c_void_p, C.c_size_t],

@@ -82,9 +82,13 @@ public:
                 offsets[i + 1] = used;
             }
             create();
-            if (m_) check(nsmh_multi_load_reads_ascii(m_, bases, offsets.data(), numReads));
-            else check(nsmh_load_reads_ascii(h_, bases, offsets.data(), numReads));
-            sketchAndBuild();
+            if (m_) {
+                check(nsmh_multi_load_reads_ascii(m_, bases, offsets.data(), numReads));
+                sketchAndBuild();
+            } else {
+                // load + sketch + build pipelined: a chunk is sketched while the next one crosses PCIe
+                check(nsmh_initialize_ascii(h_, bases, offsets.data(), numReads));
+            }
         } catch (...) {
             nsmh_host_free(bases);
             throw;
@@ -101,9 +105,12 @@ public:
         std::vector<uint32_t> len32((size_t)numReads);
         for (read_t i = 0; i < numReads; ++i) len32[i] = (uint32_t)lengths[i];
         create();
-        if (m_) check(nsmh_multi_load_reads_dnabitset(m_, packed, len32.data(), numReads));
-        else check(nsmh_load_reads_dnabitset(h_, packed, len32.data(), numReads));
-        sketchAndBuild();
+        if (m_) {
+            check(nsmh_multi_load_reads_dnabitset(m_, packed, len32.data(), numReads));
+            sketchAndBuild();
+        } else {
+            check(nsmh_initialize_dnabitset(h_, packed, len32.data(), numReads));
+        }
     }
 
     /** The same from the low-memory temp file (ReadData.cpp:181-204 writes it read after read). */

@@ -300,8 +300,55 @@ static void invalidate(nsmh_ctx *c) {
     c->id_base = 0;
 }
 
-int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
-    CTX_GUARD(c);
+// chunk size of the host loaders; NSMH_LOAD_CHUNK_BYTES lets the tests cut small inputs into many chunks
+static uint64_t load_chunk_bytes(uint64_t dflt) {
+    const char *e = getenv("NSMH_LOAD_CHUNK_BYTES");
+    if (!e || !*e) return dflt;
+    const long long v = atoll(e);
+    return v < 16 ? 16 : (uint64_t)v;
+}
+
+// sketch pass: what comes before the first and after the last sketch_reads call
+static int sketch_begin(nsmh_ctx *c) {
+    c->sketched = false;
+    c->tables.built = false;
+    c->bulk_valid = false;
+    NSMH_TRY(c->sketches.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream));
+    // the tables that the next build fills are cleared on the copy stream while the reads are sketched
+    if (c->mg && c->mg_sub()) NSMH_TRY(preclear_tables(c->mg_sub(), c->mg_total_rows()));
+    else NSMH_TRY(preclear_tables(c, c->reads.num_reads));
+    NSMH_CK(cudaEventRecord(c->ev[2], c->stream));
+    return NSMH_OK;
+}
+
+static int sketch_end(nsmh_ctx *c) {
+    NSMH_CK(cudaEventRecord(c->ev[3], c->stream));
+    c->sketched = true;
+    c->table_sketches = c->sketches.as<uint64_t>();
+    c->table_reads = c->reads.num_reads;
+    c->id_base = 0;
+    return NSMH_OK;
+}
+
+// reads [r0, r1) are complete in the packed stream: sketch them behind whatever c->stream holds
+static int sketch_range(nsmh_ctx *c, uint32_t r0, uint32_t r1) {
+    const bool last = r1 == c->reads.num_reads;     // the main-kernel events time the last range
+    return sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp, c->sketch_mode,
+                        c->stream, &c->launches, last ? c->ev[4] : nullptr, last ? c->ev[5] : nullptr, r0, r1);
+}
+
+static int build_enqueue(nsmh_ctx *c) {
+    NSMH_CK(cudaEventRecord(c->ev[6], c->stream));
+    NSMH_TRY(build_tables(c));
+    NSMH_CK(cudaEventRecord(c->ev[7], c->stream));
+    c->build_timed = true;          // no host round trip here: nsmh_get_stats reads the events
+    return NSMH_OK;
+}
+
+// Host ASCII -> packed stream.  then_sketch: the reads that a chunk completes are sketched right behind its
+// pack, i.e. while the next chunks are still crossing PCIe, and the tables are built behind the last one;
+// the call returns when the last byte has LEFT the host buffers, not when the device is done.
+static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, uint32_t num_reads, bool then_sketch) {
     if (!offsets) return fail(NSMH_EINVAL, "load_reads_ascii: null offsets");
     const uint64_t total = offsets[num_reads];
     if (total && !bases) return fail(NSMH_EINVAL, "load_reads_ascii: null bases");
@@ -309,8 +356,12 @@ int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offs
     NSMH_CK(cudaEventRecord(c->ev[0], c->stream));
     NSMH_TRY(set_offsets_host(c, offsets, num_reads));
     NSMH_TRY(alloc_packed(c->reads, total, c->stream));
+    if (then_sketch) {
+        c->reads_loaded = true;
+        NSMH_TRY(sketch_begin(c));
+    }
     // Double-buffered chunks: H2D of chunk i+1 on the copy stream overlaps the pack of chunk i.
-    const uint64_t chunk = 64ULL << 20;   // bases per chunk, multiple of 16
+    const uint64_t chunk = load_chunk_bytes(64ULL << 20) + 15 & ~15ULL;   // bases per chunk, multiple of 16
     DevBuf stage[2];
     cudaEvent_t copied[2] = {nullptr, nullptr}, packed[2] = {nullptr, nullptr};
     int rc = NSMH_OK;
@@ -323,7 +374,8 @@ int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offs
     for (int i = 0; i < 2 && !rc; ++i) rc = stage[i].ensure(stage_bytes, c->stream);
     if (!rc && cudaEventRecord(packed[0], c->stream) != cudaSuccess) rc = NSMH_ECUDA;
     if (!rc && cudaEventRecord(packed[1], c->stream) != cudaSuccess) rc = NSMH_ECUDA;
-    int bi = 0;
+    int bi = 0, last_bi = -1;
+    uint32_t r_done = 0;
     for (uint64_t b0 = 0; b0 < total && !rc; b0 += chunk, bi ^= 1) {
         const uint64_t nb = std::min<uint64_t>(chunk, total - b0);
         cudaError_t e;
@@ -333,9 +385,25 @@ int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offs
         if ((e = cudaStreamWaitEvent(c->stream, copied[bi], 0)) != cudaSuccess) { rc = cuda_fail(e, "wait", __FILE__, __LINE__); break; }
         rc = pack_ascii(c->reads, stage[bi].as<char>(), b0, nb, c->stream, &c->launches);
         if (!rc && (e = cudaEventRecord(packed[bi], c->stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
+        last_bi = bi;
+        if (!rc && then_sketch) {
+            // reads that end at or before b0 + nb are whole now
+            const uint32_t r = (uint32_t)(std::upper_bound(offsets + r_done, offsets + num_reads + 1, b0 + nb) - offsets) - 1;
+            if (r > r_done) rc = sketch_range(c, r_done, r);
+            r_done = r;
+        }
     }
-    if (!rc) {
-        cudaEventRecord(c->ev[1], c->stream);
+    if (!rc) cudaEventRecord(c->ev[1], c->stream);
+    if (!rc && then_sketch) {
+        if (r_done < num_reads) rc = sketch_range(c, r_done, num_reads);    // empty reads at the very end
+        if (!rc) rc = sketch_end(c);
+        if (!rc) rc = build_enqueue(c);
+        // the caller may reuse its buffers as soon as the last copy is through
+        if (!rc && last_bi >= 0) {
+            cudaError_t e = cudaEventSynchronize(copied[last_bi]);
+            if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+        }
+    } else if (!rc) {
         cudaError_t e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
     }
@@ -349,10 +417,20 @@ int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offs
         if (copied[i]) cudaEventDestroy(copied[i]);
         if (packed[i]) cudaEventDestroy(packed[i]);
     }
-    if (rc) return rc;
-    c->stats.h2d_pack_ms = elapsed(c->ev[0], c->ev[1]);
+    if (rc) { invalidate(c); return rc; }
+    if (!then_sketch) c->stats.h2d_pack_ms = elapsed(c->ev[0], c->ev[1]);
     c->reads_loaded = true;
     return NSMH_OK;
+}
+
+int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
+    CTX_GUARD(c);
+    return load_ascii(c, bases, offsets, num_reads, false);
+}
+
+int nsmh_initialize_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
+    CTX_GUARD(c);
+    return load_ascii(c, bases, offsets, num_reads, true);
 }
 
 int nsmh_load_reads_ascii_device(nsmh_handle c, const char *d_bases, const uint64_t *d_offsets,
@@ -375,9 +453,9 @@ int nsmh_load_reads_ascii_device(nsmh_handle c, const char *d_bases, const uint6
     return NSMH_OK;
 }
 
-int nsmh_load_reads_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths,
-                              uint32_t num_reads) {
-    CTX_GUARD(c);
+// Host DnaBitset bytes -> packed stream, in chunks of whole reads: the copy of chunk i+1 runs beside the
+// re-layout (and, then_sketch, the sketch) of chunk i.  See load_ascii for what then_sketch returns on.
+static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *lengths, uint32_t num_reads, bool then_sketch) {
     if (num_reads && (!packed || !lengths)) return fail(NSMH_EINVAL, "load_reads_dnabitset: null input");
     invalidate(c);
     std::vector<uint64_t> off((size_t)num_reads + 1, 0), boff((size_t)num_reads + 1, 0);
@@ -385,21 +463,73 @@ int nsmh_load_reads_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32
         off[i + 1] = off[i] + lengths[i];
         boff[i + 1] = boff[i] + (lengths[i] + 3) / 4;
     }
+    NSMH_CK(cudaEventRecord(c->ev[0], c->stream));
     NSMH_TRY(set_offsets_host(c, off.data(), num_reads));
     NSMH_TRY(alloc_packed(c->reads, off[num_reads], c->stream));
+    if (then_sketch) {
+        c->reads_loaded = true;
+        NSMH_TRY(sketch_begin(c));
+    }
     DevBuf d_src, d_boff;
+    cudaEvent_t ready = nullptr, copied = nullptr;
     int rc = d_src.ensure(boff[num_reads] + 16, c->stream);
     if (!rc) rc = d_boff.ensure(boff.size() * sizeof(uint64_t), c->stream);
     cudaError_t e = cudaSuccess;
-    if (!rc && (e = cudaMemcpyAsync(d_src.p, packed, boff[num_reads], cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
+    if (!rc && (e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
+    if (!rc && (e = cudaEventCreateWithFlags(&copied, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
     if (!rc && (e = cudaMemcpyAsync(d_boff.p, boff.data(), boff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
-    if (!rc) rc = pack_from_dnabitset(c->reads, d_src.as<uint8_t>(), d_boff.as<uint64_t>(), c->stream, &c->launches);
-    if (!rc && (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+    // the staging buffer was allocated in c->stream's order: the copy stream may touch it after this point
+    if (!rc && (e = cudaEventRecord(ready, c->stream)) != cudaSuccess) rc = cuda_fail(e, "record", __FILE__, __LINE__);
+    if (!rc && (e = cudaStreamWaitEvent(c->copy_stream, ready, 0)) != cudaSuccess) rc = cuda_fail(e, "wait", __FILE__, __LINE__);
+    const uint64_t chunk = load_chunk_bytes(16ULL << 20);      // source bytes per chunk (64 M bases)
+    bool any = false;
+    for (uint32_t r0 = 0; r0 < num_reads && !rc;) {
+        uint32_t r1 = (uint32_t)(std::lower_bound(boff.begin() + r0, boff.end(), boff[r0] + chunk) - boff.begin());
+        if (r1 <= r0) r1 = r0 + 1;
+        if (r1 > num_reads) r1 = num_reads;
+        const uint64_t nbytes = boff[r1] - boff[r0];
+        if (nbytes) {
+            if ((e = cudaMemcpyAsync(static_cast<uint8_t *>(d_src.p) + boff[r0], packed + boff[r0], nbytes, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
+            if ((e = cudaEventRecord(copied, c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
+            if ((e = cudaStreamWaitEvent(c->stream, copied, 0)) != cudaSuccess) { rc = cuda_fail(e, "wait", __FILE__, __LINE__); break; }
+            any = true;
+            // the word that holds the first base of read r1 is written again, whole, by the next chunk
+            rc = pack_from_dnabitset(c->reads, d_src.as<uint8_t>(), d_boff.as<uint64_t>(), c->stream, &c->launches,
+                                     off[r0] / 16, (off[r1] + 15) / 16);
+        }
+        if (!rc && then_sketch) rc = sketch_range(c, r0, r1);
+        r0 = r1;
+    }
+    if (!rc) cudaEventRecord(c->ev[1], c->stream);
+    if (!rc && then_sketch) {
+        rc = sketch_end(c);
+        if (!rc) rc = build_enqueue(c);
+        if (!rc && any && (e = cudaEventSynchronize(copied)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+    } else if (!rc && (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+    if (rc) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        cudaGetLastError();
+    }
     d_src.release(c->stream);
     d_boff.release(c->stream);
-    if (rc) return rc;
+    if (ready) cudaEventDestroy(ready);
+    if (copied) cudaEventDestroy(copied);
+    if (rc) { invalidate(c); return rc; }
     c->reads_loaded = true;
     return NSMH_OK;
+}
+
+int nsmh_load_reads_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths,
+                              uint32_t num_reads) {
+    CTX_GUARD(c);
+    return load_dnabitset(c, packed, lengths, num_reads, false);
+}
+
+int nsmh_initialize_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths,
+                              uint32_t num_reads) {
+    CTX_GUARD(c);
+    return load_dnabitset(c, packed, lengths, num_reads, true);
 }
 
 // ------------------------------------------------------------ FASTQ ingest --
@@ -603,22 +733,9 @@ int nsmh_set_sketch_mode(nsmh_handle c, int mode) {
 int nsmh_sketch(nsmh_handle c) {
     CTX_GUARD(c);
     if (!c->reads_loaded) return fail(NSMH_ESTATE, "sketch: no reads loaded");
-    c->sketched = false;
-    c->tables.built = false;
-    c->bulk_valid = false;
-    NSMH_TRY(c->sketches.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream));
-    // the tables that the next build fills are cleared on the copy stream while the reads are sketched
-    if (c->mg && c->mg_sub()) NSMH_TRY(preclear_tables(c->mg_sub(), c->mg_total_rows()));
-    else NSMH_TRY(preclear_tables(c, c->reads.num_reads));
-    NSMH_CK(cudaEventRecord(c->ev[2], c->stream));
-    NSMH_TRY(sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp,
-                          c->sketch_mode, c->stream, &c->launches, c->ev[4], c->ev[5]));
-    NSMH_CK(cudaEventRecord(c->ev[3], c->stream));
-    c->sketched = true;
-    c->table_sketches = c->sketches.as<uint64_t>();
-    c->table_reads = c->reads.num_reads;
-    c->id_base = 0;
-    return NSMH_OK;
+    NSMH_TRY(sketch_begin(c));
+    NSMH_TRY(sketch_range(c, 0, c->reads.num_reads));
+    return sketch_end(c);
 }
 
 int nsmh_get_sketches(nsmh_handle c, uint64_t *out) {
@@ -656,11 +773,7 @@ int nsmh_build(nsmh_handle c) {
         return fail(NSMH_ESTATE, "build: no sketches (call nsmh_sketch or nsmh_set_table_sketches)");
     if (!c->sketched && c->table_sketches == nullptr)
         return fail(NSMH_ESTATE, "build: no sketches (call nsmh_sketch or nsmh_set_table_sketches)");
-    NSMH_CK(cudaEventRecord(c->ev[6], c->stream));
-    NSMH_TRY(build_tables(c));
-    NSMH_CK(cudaEventRecord(c->ev[7], c->stream));
-    c->build_timed = true;          // no host round trip here: nsmh_get_stats reads the events
-    return NSMH_OK;
+    return build_enqueue(c);
 }
 
 int nsmh_table_num_keys(nsmh_handle c, uint32_t j, uint32_t *num_keys) {

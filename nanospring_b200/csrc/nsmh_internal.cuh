@@ -180,7 +180,7 @@ int pack_ascii(ReadSet &rs, const char *d_bases, uint64_t first_base, uint64_t n
 int alloc_packed(ReadSet &rs, uint64_t total_bases, cudaStream_t s);
 int pack_reverse_complement(const ReadSet &src, ReadSet &dst, cudaStream_t s, uint32_t *launches);
 int pack_from_dnabitset(ReadSet &rs, const uint8_t *d_src, const uint64_t *d_src_byte_off,
-                        cudaStream_t s, uint32_t *launches);
+                        cudaStream_t s, uint32_t *launches, uint64_t w_begin = 0, uint64_t w_end = ~0ULL);
 
 // ---- fastq.cu ----------------------------------------------------------------
 int parse_fastq_device(nsmh_ctx *c, const uint8_t *d_text, uint64_t bytes, uint64_t safe_bytes, int last_byte);
@@ -190,7 +190,7 @@ int unpack_ascii_device(nsmh_ctx *c, uint64_t b0, uint64_t nb, uint8_t *d_out, c
 int build_filter_tables(nsmh_ctx *c);
 int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &tile_start,
                  DevBuf &cub_tmp, int mode, cudaStream_t s, uint32_t *launches, cudaEvent_t ev0,
-                 cudaEvent_t ev1);
+                 cudaEvent_t ev1, uint32_t r0 = 0, uint32_t r1 = ~0u);
 
 // ---- table.cu ----------------------------------------------------------------
 int build_tables(nsmh_ctx *c);

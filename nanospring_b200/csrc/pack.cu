@@ -53,11 +53,14 @@ int pack_reverse_complement(const ReadSet &src, ReadSet &dst, cudaStream_t s, ui
 }
 
 int pack_from_dnabitset(ReadSet &rs, const uint8_t *d_src, const uint64_t *d_src_byte_off,
-                        cudaStream_t s, uint32_t *launches) {
-    if (rs.num_words == 0) return NSMH_OK;
-    int blocks = (int)((rs.num_words + 255) / 256 < 148 * 16 ? (rs.num_words + 255) / 256 : 148 * 16);
+                        cudaStream_t s, uint32_t *launches, uint64_t w_begin, uint64_t w_end) {
+    if (w_end > rs.num_words) w_end = rs.num_words;
+    if (w_begin >= w_end) return NSMH_OK;
+    const uint64_t per_block = 8ULL * 32 * kDnaWordsPerLane;       // 8 warps, one pass
+    const uint64_t want = (w_end - w_begin + per_block - 1) / per_block;
+    const int blocks = (int)(want < 148 * 16 ? want : 148 * 16);
     pack_dnabitset_kernel<<<blocks, 256, 0, s>>>(rs.d_offsets(), rs.num_reads, rs.total_bases, d_src,
-                                                 d_src_byte_off, rs.packed.as<uint32_t>());
+                                                 d_src_byte_off, rs.packed.as<uint32_t>(), w_begin, w_end);
     if (launches) ++*launches;
     NSMH_CK(cudaGetLastError());
     return NSMH_OK;

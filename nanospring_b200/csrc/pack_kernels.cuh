@@ -87,30 +87,56 @@ pack_rc_kernel(const uint64_t *__restrict__ off, uint32_t n_reads, uint64_t tota
 
 // Reads that arrive already packed the reference's way (DnaBitset: 4 bases/byte,
 // first base in bits 7..6, each read byte aligned; src/dnaToBits.cpp:11-36) are
-// re-laid into the continuous stream.
+// re-laid into the continuous stream: words [w_begin, w_end) of it.  A lane owns kDnaWordsPerLane words
+// 32 words apart (the warp's stores stay coalesced), finds the read of its first word by bisection and
+// walks forward from there.  A word that lies inside one read - all but one in several hundred - is two
+// aligned 32-bit loads and one funnel shift; a word across a read boundary goes base by base.
+// `src` must be 4-byte aligned and readable 8 bytes past the last read's last byte.
+constexpr int kDnaWordsPerLane = 8;
+
 __global__ void __launch_bounds__(256)
 pack_dnabitset_kernel(const uint64_t *__restrict__ off, uint32_t n_reads, uint64_t total_bases,
                       const uint8_t *__restrict__ src, const uint64_t *__restrict__ src_off,
-                      uint32_t *__restrict__ W) {
-    const uint64_t nwords = (total_bases + 15) / 16;
-    for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < nwords;
-         t += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t g = t * 16;
-        uint32_t i = read_of_base(off, n_reads, g);
+                      uint32_t *__restrict__ W, uint64_t w_begin, uint64_t w_end) {
+    const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src);
+    const uint64_t span = 32ULL * kDnaWordsPerLane;            // words per warp and pass
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint64_t t0 = w_begin + warp * span; t0 < w_end; t0 += warps * span) {
+        uint64_t t = t0 + lane;
+        if (t >= w_end) continue;
+        uint32_t i = read_of_base(off, n_reads, t * 16 < total_bases ? t * 16 : total_bases - 1);
         uint64_t rb = off[i], re = off[i + 1];
-        uint32_t word = 0;
 #pragma unroll 1
-        for (int j = 0; j < 16; ++j, ++g) {
-            uint32_t code = 0;
-            if (g < total_bases) {
-                while (g >= re) { ++i; rb = re; re = off[i + 1]; }
-                uint64_t lj = g - rb;
-                uint32_t byte = src[src_off[i] + (lj >> 2)];
-                code = (byte >> (6 - 2 * (int)(lj & 3))) & 3u;
+        for (int j = 0; j < kDnaWordsPerLane && t < w_end; ++j, t += 32) {
+            uint64_t g = t * 16;
+            while (g >= re && i + 1 < n_reads) { ++i; rb = re; re = off[i + 1]; }
+            uint32_t word;
+            if (g + 16 <= re) {
+                const uint64_t lj = g - rb;
+                const uint64_t a = src_off[i] + (lj >> 2);      // byte that holds base g
+                const uint32_t sh = 2 * (uint32_t)(lj & 3) + 8 * (uint32_t)(a & 3);
+                const uint32_t x0 = __byte_perm(src32[a >> 2], 0, 0x0123);          // big-endian: first base on top
+                const uint32_t x1 = __byte_perm(src32[(a >> 2) + 1], 0, 0x0123);
+                word = __funnelshift_l(x1, x0, sh);               // sh <= 30
+            } else {
+                word = 0;
+                uint32_t ii = i;
+                uint64_t b = rb, e = re;
+#pragma unroll 1
+                for (int q = 0; q < 16; ++q, ++g) {
+                    uint32_t code = 0;
+                    if (g < total_bases) {
+                        while (g >= e) { ++ii; b = e; e = off[ii + 1]; }
+                        const uint64_t lj = g - b;
+                        code = (src[src_off[ii] + (lj >> 2)] >> (6 - 2 * (int)(lj & 3))) & 3u;
+                    }
+                    word = (word << 2) | code;
+                }
             }
-            word = (word << 2) | code;
+            W[t] = word;
         }
-        W[t] = word;
     }
 }
 

@@ -60,20 +60,26 @@ int build_filter_tables(nsmh_ctx *c) {
     return NSMH_OK;
 }
 
+// Sketches reads [r0, r1) of `rs` (the whole set by default) into rows r0.. of d_sketches.  A range is what
+// the pipelined loaders use: the reads of a chunk are sketched while the next chunk is still on the bus.
+// The kernels see the range as a read set of its own - offsets stay absolute positions in the one packed
+// stream, read indices are relative to r0.
 int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &tile_start,
                  DevBuf &cub_tmp, int mode, cudaStream_t s, uint32_t *launches, cudaEvent_t ev0,
-                 cudaEvent_t ev1) {
-    if (rs.num_reads == 0) return NSMH_OK;
+                 cudaEvent_t ev1, uint32_t r0, uint32_t r1) {
+    if (r1 > rs.num_reads) r1 = rs.num_reads;
+    if (r0 >= r1) return NSMH_OK;
+    const uint32_t nr = r1 - r0;
     SketchArgs a;
-    a.off = rs.d_offsets();
+    a.off = rs.d_offsets() + r0;
     a.W = rs.packed.as<uint32_t>();
-    a.sk = d_sketches;
+    a.sk = d_sketches + (size_t)r0 * c->n;
     a.rnd = c->d_rand.as<uint64_t>();
     a.ftab_first = c->d_ftab_first.as<uint16_t>();
     a.ftab_next = c->d_ftab_next.as<uint8_t>();
     a.ftab_hit3 = c->d_ftab_hit3.as<uint8_t>();
     a.counters = c->counters.as<unsigned long long>();
-    a.n_reads = rs.num_reads;
+    a.n_reads = nr;
     a.k = c->k;
     a.n = c->n;
     a.lambda_log2 = c->lambda_log2;
@@ -88,29 +94,29 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
     // upper bound on the number of tiles: ceil(words_i / T) <= words_i / T + 1 per read, and the
     // reads' word ranges overlap by at most one word each
     // (a read's word range is widened by at most 4 words: shared boundary word + 16-byte alignment)
-    const size_t max_tiles = (size_t)((rs.num_words + 4 * (uint64_t)rs.num_reads) / a.tile_words) + rs.num_reads + 1;
-    NSMH_TRY(tile_start.ensure((((size_t)rs.num_reads + 1) * 2 + max_tiles + 2) * sizeof(uint32_t), s));
-    uint32_t *cnt = tile_start.as<uint32_t>() + rs.num_reads + 1;
+    const size_t max_tiles = (size_t)((rs.num_words + 4 * (uint64_t)nr) / a.tile_words) + nr + 1;
+    NSMH_TRY(tile_start.ensure((((size_t)nr + 1) * 2 + max_tiles + 2) * sizeof(uint32_t), s));
+    uint32_t *cnt = tile_start.as<uint32_t>() + nr + 1;
     uint32_t *ts = tile_start.as<uint32_t>();
-    uint32_t *tile_read = cnt + rs.num_reads + 1;
+    uint32_t *tile_read = cnt + nr + 1;
     a.tile_start = ts;
     a.tile_read = tile_read;
     a.tile_queue = tile_read + max_tiles;      // per call: concurrent online queries have their own
-    NSMH_CK(cudaMemsetAsync(cnt + rs.num_reads, 0, sizeof(uint32_t), s));
+    NSMH_CK(cudaMemsetAsync(cnt + nr, 0, sizeof(uint32_t), s));
     NSMH_CK(cudaMemsetAsync(a.tile_queue, 0, 2 * sizeof(uint32_t), s));      // + the fix-up list length
-    const int blocks = (int)std::min<uint64_t>(((uint64_t)rs.num_reads + 7) / 8, (uint64_t)c->num_sms * 8);
+    const int blocks = (int)std::min<uint64_t>(((uint64_t)nr + 7) / 8, (uint64_t)c->num_sms * 8);
     sketch_init_kernel<<<blocks, 256, 0, s>>>(a, cnt);
     ++*launches;
     NSMH_CK(cudaGetLastError());
     size_t tmp_bytes = 0;
-    NSMH_CK(cub_exclusive_sum_u32(nullptr, tmp_bytes, cnt, ts, (size_t)rs.num_reads + 1, s));
+    NSMH_CK(cub_exclusive_sum_u32(nullptr, tmp_bytes, cnt, ts, (size_t)nr + 1, s));
     // the same scratch buffer later holds the fix-up list (u32 per (read, hash) pair at worst)
     const size_t list_off = (tmp_bytes + 255) & ~(size_t)255;
-    if ((uint64_t)rs.num_reads * c->n >= (1ULL << 32))
+    if ((uint64_t)nr * c->n >= (1ULL << 32))
         return fail(NSMH_EINVAL, "sketch: reads*n too large for 32-bit pair indices");
-    NSMH_TRY(cub_tmp.ensure(list_off + (size_t)rs.num_reads * c->n * sizeof(uint32_t) + 16, s));
-    NSMH_CK(cub_exclusive_sum_u32(cub_tmp.p, tmp_bytes, cnt, ts, (size_t)rs.num_reads + 1, s));
-    sketch_tile_map_kernel<<<(rs.num_reads + 255) / 256, 256, 0, s>>>(ts, rs.num_reads, tile_read);
+    NSMH_TRY(cub_tmp.ensure(list_off + (size_t)nr * c->n * sizeof(uint32_t) + 16, s));
+    NSMH_CK(cub_exclusive_sum_u32(cub_tmp.p, tmp_bytes, cnt, ts, (size_t)nr + 1, s));
+    sketch_tile_map_kernel<<<(nr + 255) / 256, 256, 0, s>>>(ts, nr, tile_read);
     *launches += 3;
     NSMH_CK(cudaGetLastError());
 

@@ -193,7 +193,18 @@ class MinHashReadFilter:
         check(lib().nsmh_create(self.k, self.n, self.overlapSketchThreshold, rnd.ctypes.data_as(u64p),
                                 self.device, C.byref(h)))
         self._h = h
+        self._made_with = self._params_key()
         check(lib().nsmh_set_sketch_mode(h, int(self.sketchMode)))
+
+    def _params_key(self):
+        return (self.k, self.n, self.overlapSketchThreshold, self.device, int(self.sketchMode),
+                None if self.randNumbers is None else np.asarray(self.randNumbers, dtype=np.uint64).tobytes())
+
+    def _create_if_changed(self):
+        """A handle made with the same k, n, threshold, random numbers and device is kept (its streams, pools
+        and filter tables are expensive to remake); anything else gets a fresh one."""
+        if self._h is None or getattr(self, "_made_with", None) != self._params_key():
+            self._create()
 
     # -- initialize() split in its stages (bench / multi-GPU drive them separately) ----
     def load(self, rD):
@@ -249,10 +260,21 @@ class MinHashReadFilter:
             self.sketch()
             self.build()
             return
-        self._create()
-        self.load(rD)
-        self.sketch()
-        self.build()
+        if not isinstance(rD, ReadData):
+            rD = ReadData.from_reads(rD)
+        self._rd = rD
+        self._create_if_changed()
+        # load + sketch + build as one pipelined call: chunk i is sketched while chunk i+1 crosses PCIe
+        check(lib().nsmh_initialize_ascii(self._h, rD.bases.ctypes.data, rD.offsets.ctypes.data_as(u64p),
+                                          rD.numReads))
+
+    def initialize_dnabitset(self, packed, lengths):
+        """initialize() from the reference's 2-bit store (DnaBitset bytes + u32 lengths, dnaToBits.cpp:11-36):
+        what ReadData holds in memory / in its temp file.  Same pipelined call as initialize()."""
+        self._create_if_changed()
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        lengths = np.ascontiguousarray(lengths, dtype=np.uint32)
+        check(lib().nsmh_initialize_dnabitset(self._h, packed.ctypes.data, lengths.ctypes.data_as(u32p), lengths.size))
 
     # -- queries -------------------------------------------------------------------
     def getFilteredReads(self, s, results=None):

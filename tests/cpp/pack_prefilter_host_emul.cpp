@@ -30,7 +30,11 @@ void pp_emul_pack_rc(const uint64_t *off, uint32_t n_reads, const uint32_t *Wsrc
 void pp_emul_pack_dnabitset(const uint64_t *off, uint32_t n_reads, const uint8_t *src, const uint64_t *src_off,
                             uint32_t *W, unsigned grid) {
     const uint64_t total = off[n_reads];
-    if (total) emu_launch(grid, 64, [&] { pack_dnabitset_kernel(off, n_reads, total, src, src_off, W); });
+    if (!total) return;
+    // two word ranges, as the chunked loader converts them (the cut is anywhere, also at 0 and at the end)
+    const uint64_t nwords = (total + 15) / 16, cut = (nwords * 5) / 8;
+    emu_launch(grid, 64, [&] { pack_dnabitset_kernel(off, n_reads, total, src, src_off, W, 0, cut); });
+    emu_launch(grid, 64, [&] { pack_dnabitset_kernel(off, n_reads, total, src, src_off, W, cut, nwords); });
 }
 
 // NSMH_FLAG_* of every read (W must be followed by kPackPadWords zero words)

@@ -102,6 +102,47 @@ def test_c1_dnabitset_loader(c1_raw, c1_golden, orc):
     f.close()
 
 
+@pytest.mark.parametrize("chunk", [64, 4000, 70001, 1 << 30])
+def test_pipelined_initialize_equals_separate_calls(orc, monkeypatch, chunk):
+    """nsmh_initialize_ascii / _dnabitset (load + sketch + build pipelined: a chunk's reads are sketched while
+    the next chunk is copied) against the three separate calls and the oracle, with the chunk size forced
+    down so that reads straddle chunks, chunks hold no whole read, and empty reads sit on chunk borders."""
+    from conftest import pack_dnabitset
+    k, n, thr = 21, 24, 3
+    lengths = ns.synth_lengths(400, 1500, seed=8)
+    lengths[:10] = [0, 0, 5, k - 1, k, 16, 17, 30000, 0, 64]
+    lengths[-3:] = [0, 7, 0]
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=60_000, genome_seed=11, read_seed=12))
+    rnd = ns.rand_from_seed(99, n)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    ref = make_filter(k, n, thr, rnd)
+    ref.load(rd)
+    ref.sketch()
+    ref.build()
+    assert (ref.sketches() == want).all()
+    want_csr = ref.queryAll(False)
+    ref.close()
+    monkeypatch.setenv("NSMH_LOAD_CHUNK_BYTES", str(chunk))
+    packed, len32 = pack_dnabitset(rd.bases, rd.offsets)
+    for how in ("ascii", "dnabitset", "dnabitset_load_only"):
+        f = make_filter(k, n, thr, rnd)
+        if how == "ascii":
+            f.initialize(rd)
+        elif how == "dnabitset":
+            f.initialize_dnabitset(packed, len32)
+        else:
+            f.load_dnabitset(packed, len32)
+            f.sketch()
+            f.build()
+        assert (f.sketches() == want).all(), how
+        assert_csr_equal(f.queryAll(False), want_csr, how)
+        # a second initialize on the same handle (the wrapper keeps it) starts from a clean state
+        if how == "ascii":
+            f.initialize(rd)
+            assert_csr_equal(f.queryAll(False), want_csr, how + " again")
+        f.close()
+
+
 @pytest.mark.parametrize("k,n,thr", [(23, 60, 6), (15, 30, 3), (31, 120, 12), (16, 33, 4), (17, 7, 1)])
 def test_synthetic_reads_vs_oracle(orc, k, n, thr):
     """Nanopore-like synthetic reads (createData.py recipe, 10% error, 20x coverage of a small
