@@ -331,6 +331,12 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; this engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # host side of the e2e legs: this rank's threads and its pinned buffers live on the NUMA node its GPU hangs
+    # off (first touch), so that eight ranks loading at once do not meet on the socket interconnect
+    all_cpus = os.sched_getaffinity(0)
+    numa = C.c_int(-1)
+    check(lib().nsmh_bind_thread_near(local_rank, C.byref(numa)))
+    host_numa = {"gpu_numa_node": int(numa.value), "cpus_bound": len(os.sched_getaffinity(0)), "cpus_all": len(all_cpus)}
     dist = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout
@@ -416,8 +422,7 @@ def main():
             # the reference's own call: initialize(ReadData&) = load + sketch + build (pipelined inside the library)
             f.initialize(host_rd)
             return f.queryAll(False, fetch=True)
-        f.load(host_rd)
-        f.sketch()
+        f.load_sketch(host_rd)
         if pf is not None:
             return pf.result(lengths.size, pf.run(lengths.size, rows_per_rank))
         if world > 1:
@@ -495,12 +500,28 @@ def main():
     #      (DnaBitset, dnaToBits.cpp:11-36: 4 bases per byte, first base in bits 7..6, every read byte-aligned):
     #      what the real caller's ReadData holds (ReadData.cpp:156-235), 4x fewer bytes over PCIe ----
     e2e_packed = None
-    if not args.no_e2e and world == 1:
+    prep_ok, h_packed = 0, None
+    if not args.no_e2e:
         try:
             h_packed, len32 = dnabitset_host(d_bases, offsets)
+            prep_ok = 1
+        except Exception as e:  # noqa: BLE001
+            e2e_packed = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if dist is not None:            # the leg is collective: every rank runs it or none does
+            t = torch.tensor([prep_ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            prep_ok = int(t.item())
+    if prep_ok:
+        try:
 
             def e2e_packed_step():
-                f.initialize_dnabitset(h_packed, len32)
+                if world == 1:
+                    f.initialize_dnabitset(h_packed, len32)
+                    return f.queryAll(False, fetch=True)
+                f.load_sketch(packed=(h_packed, len32))
+                if pf is not None:
+                    return pf.result(lengths.size, pf.run(lengths.size, rows_per_rank))
+                keep["g"] = shard.gather_and_build(f, lengths.size, rows_per_rank, rank)
                 return f.queryAll(False, fetch=True)
 
             for _ in range(2):
@@ -509,7 +530,7 @@ def main():
             e2e_packed = {"value": all_bases * args.steps / (ms_p * 1e-3) / 1e9, "unit": "Gbases/s",
                           "h2d_bytes_per_step": int(h_packed.nbytes + len32.nbytes), "d2h_bytes_per_step": int(off_p.nbytes + ids_p.nbytes),
                           "ms_per_step": ms_p / args.steps, "same_csr_as_ascii_path": bool((off_p == off).all() and (ids_p == ids).all()),
-                          "input": "DnaBitset bytes + u32 lengths in host memory (nsmh_initialize_dnabitset)"}
+                          "input": "DnaBitset bytes + u32 lengths in pinned host memory, the reference's own 2-bit store (" + ("nsmh_initialize_dnabitset" if world == 1 else "nsmh_load_sketch_dnabitset + multi-GPU build") + ")"}
             del h_packed
         except Exception as e:  # noqa: BLE001
             e2e_packed = {"error": f"{type(e).__name__}: {e}"[:300]}
@@ -654,13 +675,14 @@ def main():
                    "sketch_mode": "filter" if args.sketch_mode == 0 else "brute",
                    "multi_gpu": ("n/a" if world == 1 else multi), **({"multi_gpu_note": multi_note} if multi_note else {}),
                    "l2": "inputs larger than L2 (1 GB ASCII + 0.25 GB packed per step vs 126 MB L2)",
+                   "host": host_numa,
                    "step": "pack + sketch + build tables + bulk forward lookup, CSR left on device"},
         "phases_last_step": phases,
         "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps,
                 "call": ("MinHashReadFilter.initialize(ReadData) [nsmh_initialize_ascii: load + sketch + build, pipelined] + queryAll, "
                          "pinned host ASCII in, CSR in host memory out" if world == 1 else
-                         "load + sketch + multi-GPU build + queryAll, pinned host ASCII in, CSR in host memory out")},
+                         "nsmh_load_sketch_ascii (pipelined) + multi-GPU build + queryAll, pinned host ASCII in, CSR in host memory out")},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "clocks": clocks,
@@ -701,6 +723,7 @@ def main():
     ref_for_online = None
     if n_gpus == 1 and not args.no_cpu_baseline:
         from oracle.oracle import Oracle, RefLib
+        os.sched_setaffinity(0, all_cpus)           # the CPU arm gets every core of the box
         cores = os.cpu_count() or 1
         sample_reads = 20_000
         sub = ns.ReadData(host_rd.bases[:int(offsets[sample_reads])].copy(), offsets[:sample_reads + 1].copy())

@@ -69,6 +69,13 @@ int nsmh_rand_from_seed(uint32_t seed, uint32_t n, uint64_t *out);
 /* Pinned host memory for staging reads / results (optional; any host memory works). */
 int nsmh_host_alloc(size_t bytes, void **out);
 int nsmh_host_free(void *p);
+/* The same on the NUMA node that `device` hangs off (sysfs numa_node of its PCI function; plain pinned memory
+ * when the box has no such information).  On a two-socket host a staging buffer on the far node sends every
+ * byte over the socket interconnect before PCIe - with several GPUs loading at once that link sets the rate. */
+int nsmh_host_alloc_near(int device, size_t bytes, void **out);
+/* Restricts the CALLING thread (and the threads it creates afterwards) to the CPUs of that node; *numa_node
+ * (optional) receives the node, -1 when there is nothing to bind to.  For one-process-per-GPU launches. */
+int nsmh_bind_thread_near(int device, int *numa_node);
 
 /* ---- reads -> device (replaces ReadData::getRead + DnaBitset on the host,
  *      ReadData.cpp:225-235, dnaToBits.cpp:11-103) --------------------------------- */
@@ -93,6 +100,11 @@ int nsmh_load_reads_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32
 int nsmh_initialize_ascii(nsmh_handle h, const char *bases, const uint64_t *offsets, uint32_t num_reads);
 int nsmh_initialize_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32_t *lengths,
                               uint32_t num_reads);
+/* The first two stages only (load + sketch, pipelined the same way): for callers that build the tables
+ * elsewhere - the multi-GPU flows below, which partition the tables by hash function across ranks. */
+int nsmh_load_sketch_ascii(nsmh_handle h, const char *bases, const uint64_t *offsets, uint32_t num_reads);
+int nsmh_load_sketch_dnabitset(nsmh_handle h, const uint8_t *packed, const uint32_t *lengths,
+                               uint32_t num_reads);
 int nsmh_num_reads(nsmh_handle h, uint32_t *num_reads, uint64_t *total_bases);
 
 /* ---- FASTQ ingest on the device (replaces ReadData::loadFromFile for

@@ -52,9 +52,13 @@ _SIGS = {
     "nsmh_rand_from_seed": [C.c_uint32, C.c_uint32, u64p],
     "nsmh_host_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
     "nsmh_host_free": [C.c_void_p],
+    "nsmh_host_alloc_near": [C.c_int, C.c_size_t, C.POINTER(C.c_void_p)],
+    "nsmh_bind_thread_near": [C.c_int, C.POINTER(C.c_int)],
     "nsmh_load_reads_ascii": [C.c_void_p, C.c_void_p, u64p, C.c_uint32],
     "nsmh_load_reads_ascii_device": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64],
     "nsmh_load_reads_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
+    "nsmh_load_sketch_ascii": [C.c_void_p, C.c_void_p, u64p, C.c_uint32],
+    "nsmh_load_sketch_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
     "nsmh_initialize_ascii": [C.c_void_p, C.c_void_p, u64p, C.c_uint32],
     "nsmh_initialize_dnabitset": [C.c_void_p, C.c_void_p, u32p, C.c_uint32],
     "nsmh_num_reads": [C.c_void_p, u32p, u64p],

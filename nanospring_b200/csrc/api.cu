@@ -4,9 +4,11 @@
 //   Compressor.cpp:69-76   rF.k/n/overlapSketchThreshold = ...; rF.initialize(rD)
 //   ReadFilter.cpp:11-47   initialize(): sketch all reads, populateHashTables()
 //   Consensus.cpp:189      rF->getFilteredReads(string, results)  (concurrent callers)
+#include <sched.h>
 #include <zlib.h>
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <climits>
 #include <cstdio>
@@ -146,6 +148,71 @@ int nsmh_rand_from_seed(uint32_t seed, uint32_t n, uint64_t *out) {
 int nsmh_host_alloc(size_t bytes, void **out) {
     if (!out) return fail(NSMH_EINVAL, "host_alloc: null output");
     NSMH_CK(cudaMallocHost(out, bytes ? bytes : 1));
+    return NSMH_OK;
+}
+
+// ---- host memory next to a GPU -------------------------------------------------------------------
+// On a two-socket box half of the GPUs hang off the other socket: a pinned buffer on the wrong node sends
+// every H2D byte across the socket interconnect first, and with eight ranks copying at once that link, not
+// PCIe, sets the end-to-end rate.  The node of a device comes from sysfs (its PCI function's numa_node).
+static int device_numa_cpus(int device, cpu_set_t *set) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char *q = bus; *q; ++q) *q = (char)tolower((unsigned char)*q);
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *fh = fopen(path, "r");
+    if (!fh) return -1;
+    int node = -1;
+    if (fscanf(fh, "%d", &node) != 1) node = -1;
+    fclose(fh);
+    if (node < 0) return -1;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    fh = fopen(path, "r");
+    if (!fh) return -1;
+    CPU_ZERO(set);
+    int a = 0, b = 0, count = 0;
+    while (fscanf(fh, "%d", &a) == 1) {          // "0-31,64-95"
+        b = a;
+        int ch = fgetc(fh);
+        if (ch == '-') {
+            if (fscanf(fh, "%d", &b) != 1) break;
+            ch = fgetc(fh);
+        }
+        for (int cpu = a; cpu <= b && cpu < CPU_SETSIZE; ++cpu) { CPU_SET(cpu, set); ++count; }
+        if (ch != ',') break;
+    }
+    fclose(fh);
+    if (!count) return -1;
+    // keep only what this process may run on (containers hand out a subset)
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof allowed, &allowed) == 0) {
+        cpu_set_t both;
+        CPU_AND(&both, set, &allowed);
+        if (CPU_COUNT(&both) == 0) return -1;
+        *set = both;
+    }
+    return node;
+}
+
+int nsmh_bind_thread_near(int device, int *numa_node) {
+    cpu_set_t set;
+    const int node = device_numa_cpus(device, &set);
+    if (numa_node) *numa_node = node;
+    if (node < 0) return NSMH_OK;                // single node / no topology information: nothing to do
+    if (sched_setaffinity(0, sizeof set, &set) != 0) { if (numa_node) *numa_node = -1; }
+    return NSMH_OK;
+}
+
+int nsmh_host_alloc_near(int device, size_t bytes, void **out) {
+    if (!out) return fail(NSMH_EINVAL, "host_alloc_near: null output");
+    cpu_set_t near, before;
+    const bool have_before = sched_getaffinity(0, sizeof before, &before) == 0;
+    const bool moved = have_before && device_numa_cpus(device, &near) >= 0 && sched_setaffinity(0, sizeof near, &near) == 0;
+    // pages are taken from the node of the CPU that pins them (default policy: local allocation)
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (moved) sched_setaffinity(0, sizeof before, &before);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __FILE__, __LINE__);
     return NSMH_OK;
 }
 
@@ -348,7 +415,8 @@ static int build_enqueue(nsmh_ctx *c) {
 // Host ASCII -> packed stream.  then_sketch: the reads that a chunk completes are sketched right behind its
 // pack, i.e. while the next chunks are still crossing PCIe, and the tables are built behind the last one;
 // the call returns when the last byte has LEFT the host buffers, not when the device is done.
-static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, uint32_t num_reads, bool then_sketch) {
+static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, uint32_t num_reads, int stages) {
+    const bool then_sketch = stages >= 1;       // stages: 0 load, 1 + sketch, 2 + build
     if (!offsets) return fail(NSMH_EINVAL, "load_reads_ascii: null offsets");
     const uint64_t total = offsets[num_reads];
     if (total && !bases) return fail(NSMH_EINVAL, "load_reads_ascii: null bases");
@@ -397,7 +465,7 @@ static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, u
     if (!rc && then_sketch) {
         if (r_done < num_reads) rc = sketch_range(c, r_done, num_reads);    // empty reads at the very end
         if (!rc) rc = sketch_end(c);
-        if (!rc) rc = build_enqueue(c);
+        if (!rc && stages >= 2) rc = build_enqueue(c);
         // the caller may reuse its buffers as soon as the last copy is through
         if (!rc && last_bi >= 0) {
             cudaError_t e = cudaEventSynchronize(copied[last_bi]);
@@ -425,12 +493,12 @@ static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, u
 
 int nsmh_load_reads_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
     CTX_GUARD(c);
-    return load_ascii(c, bases, offsets, num_reads, false);
+    return load_ascii(c, bases, offsets, num_reads, 0);
 }
 
 int nsmh_initialize_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
     CTX_GUARD(c);
-    return load_ascii(c, bases, offsets, num_reads, true);
+    return load_ascii(c, bases, offsets, num_reads, 2);
 }
 
 int nsmh_load_reads_ascii_device(nsmh_handle c, const char *d_bases, const uint64_t *d_offsets,
@@ -455,7 +523,8 @@ int nsmh_load_reads_ascii_device(nsmh_handle c, const char *d_bases, const uint6
 
 // Host DnaBitset bytes -> packed stream, in chunks of whole reads: the copy of chunk i+1 runs beside the
 // re-layout (and, then_sketch, the sketch) of chunk i.  See load_ascii for what then_sketch returns on.
-static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *lengths, uint32_t num_reads, bool then_sketch) {
+static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *lengths, uint32_t num_reads, int stages) {
+    const bool then_sketch = stages >= 1;
     if (num_reads && (!packed || !lengths)) return fail(NSMH_EINVAL, "load_reads_dnabitset: null input");
     invalidate(c);
     std::vector<uint64_t> off((size_t)num_reads + 1, 0), boff((size_t)num_reads + 1, 0);
@@ -464,47 +533,60 @@ static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *le
         boff[i + 1] = boff[i] + (lengths[i] + 3) / 4;
     }
     NSMH_CK(cudaEventRecord(c->ev[0], c->stream));
-    NSMH_TRY(set_offsets_host(c, off.data(), num_reads));
-    NSMH_TRY(alloc_packed(c->reads, off[num_reads], c->stream));
-    if (then_sketch) {
-        c->reads_loaded = true;
-        NSMH_TRY(sketch_begin(c));
-    }
-    DevBuf d_src, d_boff;
-    cudaEvent_t ready = nullptr, copied = nullptr;
-    int rc = d_src.ensure(boff[num_reads] + 16, c->stream);
-    if (!rc) rc = d_boff.ensure(boff.size() * sizeof(uint64_t), c->stream);
-    cudaError_t e = cudaSuccess;
-    if (!rc && (e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
-    if (!rc && (e = cudaEventCreateWithFlags(&copied, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
-    if (!rc && (e = cudaMemcpyAsync(d_boff.p, boff.data(), boff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
-    // the staging buffer was allocated in c->stream's order: the copy stream may touch it after this point
-    if (!rc && (e = cudaEventRecord(ready, c->stream)) != cudaSuccess) rc = cuda_fail(e, "record", __FILE__, __LINE__);
-    if (!rc && (e = cudaStreamWaitEvent(c->copy_stream, ready, 0)) != cudaSuccess) rc = cuda_fail(e, "wait", __FILE__, __LINE__);
-    const uint64_t chunk = load_chunk_bytes(16ULL << 20);      // source bytes per chunk (64 M bases)
-    bool any = false;
-    for (uint32_t r0 = 0; r0 < num_reads && !rc;) {
+    // chunks of whole reads, about `chunk` source bytes each
+    const uint64_t chunk = load_chunk_bytes(16ULL << 20);      // (64 M bases)
+    std::vector<uint32_t> cut(1, 0);
+    while (cut.back() < num_reads) {
+        const uint32_t r0 = cut.back();
         uint32_t r1 = (uint32_t)(std::lower_bound(boff.begin() + r0, boff.end(), boff[r0] + chunk) - boff.begin());
         if (r1 <= r0) r1 = r0 + 1;
-        if (r1 > num_reads) r1 = num_reads;
-        const uint64_t nbytes = boff[r1] - boff[r0];
-        if (nbytes) {
-            if ((e = cudaMemcpyAsync(static_cast<uint8_t *>(d_src.p) + boff[r0], packed + boff[r0], nbytes, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
-            if ((e = cudaEventRecord(copied, c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
-            if ((e = cudaStreamWaitEvent(c->stream, copied, 0)) != cudaSuccess) { rc = cuda_fail(e, "wait", __FILE__, __LINE__); break; }
-            any = true;
+        cut.push_back(std::min(r1, num_reads));
+    }
+    const size_t nchunks = cut.size() - 1;
+    DevBuf d_src, d_boff;
+    cudaEvent_t ready = nullptr;
+    std::vector<cudaEvent_t> copied(nchunks, nullptr);
+    int rc = d_src.ensure(boff[num_reads] + 16, c->stream);
+    cudaError_t e = cudaSuccess;
+    if (!rc && (e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
+    for (size_t i = 0; i < nchunks && !rc; ++i)
+        if ((e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
+    // The bus is the bottleneck: every copy is queued before anything else is set up.  (The staging buffer was
+    // allocated in c->stream's order, the copy stream may touch it after `ready`.)
+    if (!rc && (e = cudaEventRecord(ready, c->stream)) != cudaSuccess) rc = cuda_fail(e, "record", __FILE__, __LINE__);
+    if (!rc && (e = cudaStreamWaitEvent(c->copy_stream, ready, 0)) != cudaSuccess) rc = cuda_fail(e, "wait", __FILE__, __LINE__);
+    int last_copy = -1;
+    for (size_t i = 0; i < nchunks && !rc; ++i) {
+        const uint64_t b0 = boff[cut[i]], nbytes = boff[cut[i + 1]] - b0;
+        if (!nbytes) continue;
+        if ((e = cudaMemcpyAsync(static_cast<uint8_t *>(d_src.p) + b0, packed + b0, nbytes, cudaMemcpyHostToDevice, c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
+        if ((e = cudaEventRecord(copied[i], c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
+        last_copy = (int)i;
+    }
+    if (!rc) rc = set_offsets_host(c, off.data(), num_reads);
+    if (!rc) rc = alloc_packed(c->reads, off[num_reads], c->stream);
+    if (!rc) rc = d_boff.ensure(boff.size() * sizeof(uint64_t), c->stream);
+    if (!rc && (e = cudaMemcpyAsync(d_boff.p, boff.data(), boff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
+    if (!rc && then_sketch) {
+        c->reads_loaded = true;
+        rc = sketch_begin(c);       // its table clear lands on the copy stream behind the copies: beside the last chunk's sketch
+    }
+    for (size_t i = 0; i < nchunks && !rc; ++i) {
+        const uint32_t r0 = cut[i], r1 = cut[i + 1];
+        if (boff[r1] > boff[r0]) {
+            if ((e = cudaStreamWaitEvent(c->stream, copied[i], 0)) != cudaSuccess) { rc = cuda_fail(e, "wait", __FILE__, __LINE__); break; }
             // the word that holds the first base of read r1 is written again, whole, by the next chunk
             rc = pack_from_dnabitset(c->reads, d_src.as<uint8_t>(), d_boff.as<uint64_t>(), c->stream, &c->launches,
                                      off[r0] / 16, (off[r1] + 15) / 16);
         }
         if (!rc && then_sketch) rc = sketch_range(c, r0, r1);
-        r0 = r1;
     }
     if (!rc) cudaEventRecord(c->ev[1], c->stream);
     if (!rc && then_sketch) {
         rc = sketch_end(c);
-        if (!rc) rc = build_enqueue(c);
-        if (!rc && any && (e = cudaEventSynchronize(copied)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
+        if (!rc && stages >= 2) rc = build_enqueue(c);
+        // the caller may reuse its buffers as soon as the last copy is through
+        if (!rc && last_copy >= 0 && (e = cudaEventSynchronize(copied[last_copy])) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
     } else if (!rc && (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) rc = cuda_fail(e, "sync", __FILE__, __LINE__);
     if (rc) {
         cudaStreamSynchronize(c->copy_stream);
@@ -514,7 +596,8 @@ static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *le
     d_src.release(c->stream);
     d_boff.release(c->stream);
     if (ready) cudaEventDestroy(ready);
-    if (copied) cudaEventDestroy(copied);
+    for (cudaEvent_t ev : copied)
+        if (ev) cudaEventDestroy(ev);
     if (rc) { invalidate(c); return rc; }
     c->reads_loaded = true;
     return NSMH_OK;
@@ -523,13 +606,23 @@ static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *le
 int nsmh_load_reads_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths,
                               uint32_t num_reads) {
     CTX_GUARD(c);
-    return load_dnabitset(c, packed, lengths, num_reads, false);
+    return load_dnabitset(c, packed, lengths, num_reads, 0);
+}
+
+int nsmh_load_sketch_ascii(nsmh_handle c, const char *bases, const uint64_t *offsets, uint32_t num_reads) {
+    CTX_GUARD(c);
+    return load_ascii(c, bases, offsets, num_reads, 1);
+}
+
+int nsmh_load_sketch_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths, uint32_t num_reads) {
+    CTX_GUARD(c);
+    return load_dnabitset(c, packed, lengths, num_reads, 1);
 }
 
 int nsmh_initialize_dnabitset(nsmh_handle c, const uint8_t *packed, const uint32_t *lengths,
                               uint32_t num_reads) {
     CTX_GUARD(c);
-    return load_dnabitset(c, packed, lengths, num_reads, true);
+    return load_dnabitset(c, packed, lengths, num_reads, 2);
 }
 
 // ------------------------------------------------------------ FASTQ ingest --

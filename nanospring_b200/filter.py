@@ -217,6 +217,21 @@ class MinHashReadFilter:
         check(lib().nsmh_load_reads_ascii(self._h, rD.bases.ctypes.data, rD.offsets.ctypes.data_as(u64p),
                                           rD.numReads))
 
+    def load_sketch(self, rD=None, packed=None):
+        """load() + sketch() as one pipelined call (a chunk is sketched while the next one crosses PCIe), for
+        flows that build the tables elsewhere (multi-GPU).  rD: ReadData, or packed=(DnaBitset bytes, u32 lengths)."""
+        if self._h is None:
+            self._create()
+        if packed is not None:
+            pk = np.ascontiguousarray(packed[0], dtype=np.uint8)
+            ln = np.ascontiguousarray(packed[1], dtype=np.uint32)
+            check(lib().nsmh_load_sketch_dnabitset(self._h, pk.ctypes.data, ln.ctypes.data_as(u32p), ln.size))
+            return
+        if not isinstance(rD, ReadData):
+            rD = ReadData.from_reads(rD)
+        self._rd = rD
+        check(lib().nsmh_load_sketch_ascii(self._h, rD.bases.ctypes.data, rD.offsets.ctypes.data_as(u64p), rD.numReads))
+
     def load_device(self, d_bases_ptr, d_offsets_ptr, num_reads, total_bases):
         """Reads already resident on the device (ASCII bases + u64 offsets)."""
         if self._h is None:

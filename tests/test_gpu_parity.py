@@ -124,12 +124,15 @@ def test_pipelined_initialize_equals_separate_calls(orc, monkeypatch, chunk):
     ref.close()
     monkeypatch.setenv("NSMH_LOAD_CHUNK_BYTES", str(chunk))
     packed, len32 = pack_dnabitset(rd.bases, rd.offsets)
-    for how in ("ascii", "dnabitset", "dnabitset_load_only"):
+    for how in ("ascii", "dnabitset", "dnabitset_load_only", "ascii_load_sketch", "dnabitset_load_sketch"):
         f = make_filter(k, n, thr, rnd)
         if how == "ascii":
             f.initialize(rd)
         elif how == "dnabitset":
             f.initialize_dnabitset(packed, len32)
+        elif how.endswith("load_sketch"):
+            f.load_sketch(rd) if how.startswith("ascii") else f.load_sketch(packed=(packed, len32))
+            f.build()
         else:
             f.load_dnabitset(packed, len32)
             f.sketch()
