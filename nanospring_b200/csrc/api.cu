@@ -376,14 +376,15 @@ static uint64_t load_chunk_bytes(uint64_t dflt) {
 }
 
 // sketch pass: what comes before the first and after the last sketch_reads call
-static int sketch_begin(nsmh_ctx *c) {
+static int sketch_begin(nsmh_ctx *c, bool pipelined = false) {
     c->sketched = false;
     c->tables.built = false;
     c->bulk_valid = false;
     NSMH_TRY(c->sketches.ensure(std::max<size_t>((size_t)c->reads.num_reads * c->n, 1) * sizeof(uint64_t), c->stream));
     // the tables that the next build fills are cleared on the copy stream while the reads are sketched
-    if (c->mg && c->mg_sub()) NSMH_TRY(preclear_tables(c->mg_sub(), c->mg_total_rows()));
-    else NSMH_TRY(preclear_tables(c, c->reads.num_reads));
+    // (the pipelined loaders: on c->stream itself, which waits for the first chunk anyway)
+    if (c->mg && c->mg_sub()) NSMH_TRY(preclear_tables(c->mg_sub(), c->mg_total_rows(), pipelined));
+    else NSMH_TRY(preclear_tables(c, c->reads.num_reads, pipelined));
     NSMH_CK(cudaEventRecord(c->ev[2], c->stream));
     return NSMH_OK;
 }
@@ -426,7 +427,7 @@ static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, u
     NSMH_TRY(alloc_packed(c->reads, total, c->stream));
     if (then_sketch) {
         c->reads_loaded = true;
-        NSMH_TRY(sketch_begin(c));
+        NSMH_TRY(sketch_begin(c, true));
     }
     // Double-buffered chunks: H2D of chunk i+1 on the copy stream overlaps the pack of chunk i.
     const uint64_t chunk = load_chunk_bytes(64ULL << 20) + 15 & ~15ULL;   // bases per chunk, multiple of 16
@@ -551,8 +552,13 @@ static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *le
     if (!rc && (e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
     for (size_t i = 0; i < nchunks && !rc; ++i)
         if ((e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming)) != cudaSuccess) rc = cuda_fail(e, "event", __FILE__, __LINE__);
-    // The bus is the bottleneck: every copy is queued before anything else is set up.  (The staging buffer was
-    // allocated in c->stream's order, the copy stream may touch it after `ready`.)
+    // The bus is the bottleneck: the two small tables go first (pageable memory: such a copy holds the host until
+    // it is through, and behind 250 MB of queued chunks that took a millisecond), then every chunk is queued
+    // before anything else is set up.  (The staging buffer was allocated in c->stream's order, the copy stream
+    // may touch it after `ready`.)
+    if (!rc) rc = set_offsets_host(c, off.data(), num_reads);
+    if (!rc) rc = d_boff.ensure(boff.size() * sizeof(uint64_t), c->stream);
+    if (!rc && (e = cudaMemcpyAsync(d_boff.p, boff.data(), boff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
     if (!rc && (e = cudaEventRecord(ready, c->stream)) != cudaSuccess) rc = cuda_fail(e, "record", __FILE__, __LINE__);
     if (!rc && (e = cudaStreamWaitEvent(c->copy_stream, ready, 0)) != cudaSuccess) rc = cuda_fail(e, "wait", __FILE__, __LINE__);
     int last_copy = -1;
@@ -563,13 +569,10 @@ static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *le
         if ((e = cudaEventRecord(copied[i], c->copy_stream)) != cudaSuccess) { rc = cuda_fail(e, "record", __FILE__, __LINE__); break; }
         last_copy = (int)i;
     }
-    if (!rc) rc = set_offsets_host(c, off.data(), num_reads);
     if (!rc) rc = alloc_packed(c->reads, off[num_reads], c->stream);
-    if (!rc) rc = d_boff.ensure(boff.size() * sizeof(uint64_t), c->stream);
-    if (!rc && (e = cudaMemcpyAsync(d_boff.p, boff.data(), boff.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) rc = cuda_fail(e, "h2d", __FILE__, __LINE__);
     if (!rc && then_sketch) {
         c->reads_loaded = true;
-        rc = sketch_begin(c);       // its table clear lands on the copy stream behind the copies: beside the last chunk's sketch
+        rc = sketch_begin(c, true);
     }
     for (size_t i = 0; i < nchunks && !rc; ++i) {
         const uint32_t r0 = cut[i], r1 = cut[i + 1];

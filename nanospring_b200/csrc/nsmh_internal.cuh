@@ -194,7 +194,7 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
 
 // ---- table.cu ----------------------------------------------------------------
 int build_tables(nsmh_ctx *c);
-int preclear_tables(nsmh_ctx *c, uint32_t rows);
+int preclear_tables(nsmh_ctx *c, uint32_t rows, bool in_order = false);
 int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
 
 // ---- query.cu ----------------------------------------------------------------

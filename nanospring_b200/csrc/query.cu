@@ -31,11 +31,12 @@ namespace nsmh {
 constexpr bool kMidTierDefault = true;   // counting-filter tier between the warp sort and the global sort
 // count_kernel: query_kernels.cuh (count_body) - one warp per query, one pass
 // RL = lists per lane kept in registers: 2 for n <= 64 (fewer registers, more warps per SM), else 4
-template <typename Src, int RL>
+// CAP = ids per warp-private sort buffer (kLookupCap, or kLookupCapWide with RL = 4)
+template <typename Src, int RL, int CAP>
 __global__ void __launch_bounds__(kLookupWarps * 32)
 count_kernel(Src src, CountArgs a) {
     extern __shared__ __align__(16) uint32_t s_buf[];
-    count_body<Src, RL>(src, a, s_buf);
+    count_body<Src, RL, CAP>(src, a, s_buf);
 }
 
 // tmp_ids (completion order) -> CSR (query order); 8 lanes per query
@@ -159,6 +160,12 @@ static bool speculate_enabled() {
     return e && *e ? atoi(e) != 0 : true;
 }
 
+// NSMH_LOOKUP_WIDE=0: the 1024-id sort buffer also for n > 64 (A/B runs)
+static bool wide_buffer_enabled() {
+    const char *e = getenv("NSMH_LOOKUP_WIDE");
+    return e && *e ? atoi(e) != 0 : true;
+}
+
 static int grid_for(uint64_t items, int sms, int per_block = 256) {
     uint64_t b = (items + per_block - 1) / per_block;
     uint64_t cap = (uint64_t)sms * 16;
@@ -273,9 +280,12 @@ static int count_and_emit(nsmh_ctx *c, QueryWs &ws, const Src &src, uint32_t sub
     if (ws.tmp_ids.cap < (fixed_ids + (size_t)nq * 8) * sizeof(uint32_t))
         NSMH_TRY(ws.tmp_ids.ensure((fixed_ids + (size_t)nq * 8) * sizeof(uint32_t), s));
 
-    const size_t smem = (size_t)kLookupWarps * kWarpWords * sizeof(uint32_t);
+    const bool wide = subs > 64 && wide_buffer_enabled();
+    const size_t smem = (size_t)kLookupWarps * warp_words(wide ? kLookupCapWide : kLookupCap) * sizeof(uint32_t);
     // function attributes are per device: set on every call (cheap) rather than once per process
-    auto kernel = subs <= 64 ? count_kernel<Src, 2> : count_kernel<Src, kRegListsMax>;
+    auto kernel = subs <= 64 ? count_kernel<Src, 2, kLookupCap>
+                  : wide     ? count_kernel<Src, kRegListsMax, kLookupCapWide>
+                             : count_kernel<Src, kRegListsMax, kLookupCap>;
     NSMH_CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CountArgs a;
     a.qcount = ws.qcount.as<uint32_t>();

@@ -474,12 +474,16 @@ __device__ __forceinline__ uint32_t warp_filter_ids(uint32_t *buf, uint32_t T, u
 }
 
 // ------------------------------------------------------------------ the lookup kernel's body --
-constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer
+constexpr int kLookupCap = 1024;     // ids per warp-private sort buffer (n <= 64)
+constexpr int kLookupCapWide = 2048; // ... for n > 64: twice the lists, twice the ids (at k = 15, n = 120 a third of the
+                                     // queries gathered 1024..2048 ids and paid for a second tier; the registers of the
+                                     // 4-lists-per-lane variant already limit it to 3 blocks per SM, which 3 x 74 KB fit)
 constexpr int kResWords = 256;       // result list of the register path / filter counters of the sort path
 constexpr int kRegListsMax = 4;      // lists per lane that are probed once and kept in registers (n <= 128; 2 for n <= 64)
 static_assert(kResWords >= kWarpFilterBuckets / 2, "the sort path keeps its filter counters in the result area");
 static_assert(kResWords >= 2 * 32 * kRegListsMax, "thr <= 1: every gathered id is a result");
 constexpr int kWarpWords = kLookupCap + kResWords + 32;
+__host__ __device__ constexpr int warp_words(int cap) { return cap + kResWords + 32; }
 constexpr int kLookupWarps = 8;
 
 constexpr int kFixedIds = 16;        // result ids per query that have a fixed place in tmp_ids
@@ -505,17 +509,17 @@ struct CountArgs {
 //              per DISTINCT id, no shared-memory traffic (the first version counted in a shared-memory
 //              hash table: 2 atomics per id at 2 cycles per lane made the shared-memory pipe, not the
 //              DRAM latency of the probes, the kernel's bound)
-//   sort path  <= kLookupCap ids: laid out, counting filter in place, bitonic sort, run lengths
+//   sort path  <= kCap ids: laid out, counting filter in place, bitonic sort, run lengths
 //   beyond     handed to the counting-filter tier / the global path
 // Results go to tmp_ids in completion order; a prefix sum over qcount and csr_place_kernel then
 // produce the CSR.
 // queries q_first, q_first + q_stride, ... < a.nq by ONE warp; buf = kWarpWords warp-private words
-template <typename Src, int kRegLists = kRegListsMax>
+template <typename Src, int kRegLists = kRegListsMax, int kCap = kLookupCap>
 __device__ __forceinline__ void count_queries(Src src, CountArgs a, uint32_t *buf, uint32_t q_first, uint32_t q_stride) {
     constexpr int kRegIds = Src::kInlinePairs ? 2 * kRegLists : kRegLists;      // ids per lane held in registers
     constexpr int kRegMaxIds = 32 * kRegIds;     // gathered ids that are counted in registers
     const int lane = threadIdx.x & 31;
-    uint32_t *res = buf + kLookupCap;           // kResWords entries
+    uint32_t *res = buf + kCap;           // kResWords entries
     const uint32_t total_warps = q_stride;
     const uint32_t subs = src.subs();
     const bool keep_lists = subs <= (uint32_t)kRegMaxIds;
@@ -565,7 +569,7 @@ __device__ __forceinline__ void count_queries(Src src, CountArgs a, uint32_t *bu
                 const uint32_t incl = warp_incl_scan(rr.c, lane);
                 const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t off = T + incl - rr.c;
-                if ((uint64_t)T + round_total <= kLookupCap) {
+                if ((uint64_t)T + round_total <= (uint32_t)kCap) {
                     if (rr.c == 1) buf[off] = rr.ptr ? rr.ptr[0] : rr.one;
                     else if (rr.c == 2 && !rr.ptr) { buf[off] = rr.one; buf[off + 1] = rr.two; }
                     else if (rr.c > 1 && rr.c <= 8)
@@ -591,7 +595,7 @@ __device__ __forceinline__ void count_queries(Src src, CountArgs a, uint32_t *bu
             } else {
                 for (uint32_t j0 = 0; j0 < subs; j0 += 32) lay(j0 + lane < subs ? src.get(q, j0 + lane) : empty_list());
             }
-            if (T > kLookupCap) {                     // the next tier handles this query
+            if (T > (uint32_t)kCap) {                     // the next tier handles this query
                 pairs_local += lane == 0 ? T : 0;
                 if (lane == 0) {
                     a.qcount[q] = 0;
@@ -703,11 +707,11 @@ __device__ __forceinline__ void count_queries(Src src, CountArgs a, uint32_t *bu
 }
 
 // the lookup kernel's body: blocks of kLookupWarps warps, a warp per query
-template <typename Src, int kRegLists = kRegListsMax>
+template <typename Src, int kRegLists = kRegListsMax, int kCap = kLookupCap>
 __device__ __forceinline__ void count_body(Src src, CountArgs a, uint32_t *s_buf) {
     const uint32_t warp = threadIdx.x >> 5;
-    count_queries<Src, kRegLists>(src, a, s_buf + (size_t)warp * kWarpWords, blockIdx.x * kLookupWarps + warp,
-                                  gridDim.x * kLookupWarps);
+    count_queries<Src, kRegLists, kCap>(src, a, s_buf + (size_t)warp * warp_words(kCap), blockIdx.x * kLookupWarps + warp,
+                                        gridDim.x * kLookupWarps);
 }
 
 // ------------------------------------------------------------------ counting-filter tier --

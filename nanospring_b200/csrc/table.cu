@@ -49,7 +49,9 @@ static uint64_t table_cap(uint32_t rows) {
     return std::max<uint64_t>(16, per_read * rows);
 }
 
-int preclear_tables(nsmh_ctx *c, uint32_t rows) {
+// in_order: clear on the context's own stream (the pipelined loaders: that stream idles until the first chunk
+// has arrived, and the copy stream is busy with the bus) instead of the copy stream (beside the sketch kernels)
+int preclear_tables(nsmh_ctx *c, uint32_t rows, bool in_order) {
     Tables &T = c->tables;
     // an earlier clear may still run on the copy stream: nothing below may free the buffer under it
     if (c->precleared_rows) NSMH_CK(cudaStreamWaitEvent(c->stream, c->ev_cleared, 0));
@@ -58,10 +60,15 @@ int preclear_tables(nsmh_ctx *c, uint32_t rows) {
     const uint64_t nslots = (uint64_t)c->n * region_stride(cap);
     if (rows == 0 || nslots >= (1ULL << 32)) return NSMH_OK;      // build_tables reports the error
     NSMH_TRY(T.slots.ensure(nslots * sizeof(Slot), c->stream));
-    NSMH_CK(cudaEventRecord(c->ev_order, c->stream));              // allocation + earlier readers
-    NSMH_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
-    NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), c->copy_stream));
-    NSMH_CK(cudaEventRecord(c->ev_cleared, c->copy_stream));
+    if (in_order) {
+        NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), c->stream));
+        NSMH_CK(cudaEventRecord(c->ev_cleared, c->stream));
+    } else {
+        NSMH_CK(cudaEventRecord(c->ev_order, c->stream));              // allocation + earlier readers
+        NSMH_CK(cudaStreamWaitEvent(c->copy_stream, c->ev_order, 0));
+        NSMH_CK(cudaMemsetAsync(T.slots.p, 0xFF, nslots * sizeof(Slot), c->copy_stream));
+        NSMH_CK(cudaEventRecord(c->ev_cleared, c->copy_stream));
+    }
     c->precleared_rows = rows;
     c->precleared_ptr = T.slots.p;
     return NSMH_OK;

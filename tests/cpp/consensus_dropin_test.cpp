@@ -144,6 +144,15 @@ int main(int argc, char **argv) {
             gpu.overlapSketchThreshold = thr;
             gpu.tempDir = tmp;
             gpu.randNumbers = rnd;
+            // DROPIN_DEVICES="0,1,2,3": the one filter spread over several GPUs of this ONE process (tables replicated,
+            // the OpenMP threads' queries round-robin over them); the same device may be named twice on a 1-GPU box
+            if (const char *dv = std::getenv("DROPIN_DEVICES"))
+                for (const char *q = dv; *q;) {
+                    gpu.devices.push_back(std::atoi(q));
+                    while (*q && *q != ',') ++q;
+                    if (*q == ',') ++q;
+                }
+            if (!gpu.devices.empty()) std::printf("gpu filter on %zu devices\n", gpu.devices.size());
             gpu.initialize(rD);
             CountingFilter cf(&gpu);
             const double s = run_consensus(rD, &cf, tmp + "/gpu", 1);

@@ -82,6 +82,8 @@ void mid_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, ui
 // kLookupWarps warps.  qcount [nq+1], qpos [nq], heavy_list [nq], counters [4] zeroed by the caller;
 // tmp_cap >= nq * kFixedIds (the fixed places), lookup_fixed_ids() returns kFixedIds.
 uint32_t lookup_fixed_ids() { return kFixedIds; }
+static int count_emul_wide = 0;
+void count_emul_set_wide(int wide) { count_emul_wide = wide; }
 
 void count_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, uint32_t subs, uint32_t thr,
                     unsigned grid, uint32_t *qcount, uint64_t *qpos, uint32_t *tmp_ids, uint64_t tmp_cap,
@@ -96,10 +98,14 @@ void count_emul_run(const uint64_t *list_off, const uint32_t *ids, uint32_t nq, 
     a.counters = counters;
     a.nq = nq;
     a.thr = thr ? thr : 1;
-    std::vector<uint32_t> smem((size_t)grid * kLookupWarps * kWarpWords + 4, 0xA5A5A5A5u);
+    const size_t block_words = (size_t)kLookupWarps * warp_words(count_emul_wide ? kLookupCapWide : kLookupCap);
+    std::vector<uint32_t> smem((size_t)grid * block_words + 4, 0xA5A5A5A5u);
     uint32_t *base = smem.data();
     while (reinterpret_cast<uintptr_t>(base) & 15) ++base;                  // the body stores uint4
-    emu_launch(grid, kLookupWarps * 32, [&] { count_body(src, a, base + (size_t)blockIdx.x * kLookupWarps * kWarpWords); });
+    if (count_emul_wide)        // what query.cu launches for n > 64: 4 lists per lane in registers, 2048-id buffer
+        emu_launch(grid, kLookupWarps * 32, [&] { count_body<CsrSrc, kRegListsMax, kLookupCapWide>(src, a, base + (size_t)blockIdx.x * block_words); });
+    else
+        emu_launch(grid, kLookupWarps * 32, [&] { count_body(src, a, base + (size_t)blockIdx.x * block_words); });
 }
 
 // count_kernel's sort path for ONE query whose T <= 1024 gathered ids are already laid out: counting

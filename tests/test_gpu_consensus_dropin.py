@@ -52,3 +52,21 @@ def test_consensus_streams_identical_with_gpu_filter(tmp_path, k, n, thr):
     assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
     assert "CONSENSUS DROPIN OK" in r.stdout
     print(r.stdout)
+
+
+@pytest.mark.gpu
+@needs_bin
+@pytest.mark.parametrize("ndev", [2, 8])
+def test_consensus_streams_identical_with_filter_on_several_devices(tmp_path, ndev):
+    """The same with GpuMinHashReadFilter::devices set: ONE process, the reference's OpenMP threads, every GPU of
+    the box behind the one ReadFilter* (csrc/multidev.cu).  On a box with fewer GPUs the devices are named
+    round-robin (two handles on one device exercise the same code)."""
+    import torch
+    have = max(torch.cuda.device_count(), 1)
+    p = make_reads(tmp_path, 1200, 23)
+    env = dict(os.environ, DROPIN_DEVICES=",".join(str(i % have) for i in range(ndev)))
+    r = subprocess.run([BIN, str(p), "23", "60", "6", str(tmp_path), "both", "8"], capture_output=True, text=True,
+                       timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-1500:]
+    assert "CONSENSUS DROPIN OK" in r.stdout and f"gpu filter on {ndev} devices" in r.stdout
+    print(r.stdout)

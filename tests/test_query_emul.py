@@ -180,7 +180,9 @@ def test_in_place_filter_of_the_warp_sort_path(emul, thr):
 
 
 # ------------------------------------------------------------------ the lookup kernel's body --
-def run_count(L, queries, subs, thr, grid=1, tmp_cap=None):
+def run_count(L, queries, subs, thr, grid=1, tmp_cap=None, wide=False):
+    L.count_emul_set_wide.argtypes = [C.c_int]
+    L.count_emul_set_wide(1 if wide else 0)
     L.count_emul_run.argtypes = [u64p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint, u32p, u64p, u32p, C.c_uint64,
                                  u32p, C.POINTER(C.c_ulonglong)]
     L.count_emul_run.restype = None
@@ -238,6 +240,34 @@ def test_lookup_kernel_body_all_paths(emul, subs, thr):
         paths.add("registers" if T[q] <= 128 else "sort")
     assert counters[2] == emitted
     assert {"registers", "sort"} <= paths
+
+
+def test_lookup_kernel_body_wide_buffer(emul):
+    """The n > 64 instantiation (count_body<Src, 4, kLookupCapWide>): queries with 1024 < T <= 2048 gathered ids
+    are resolved by the sort path instead of being handed on; beyond 2048 they still are."""
+    rng = np.random.default_rng(77)
+    subs, thr = 120, 12
+    qs = [chance_query(rng, subs, 20, rng.integers(0, 0xFFFFFFFE, size=3, dtype=np.uint64), subs),       # ~1200 + 360
+          chance_query(rng, subs, 25, rng.integers(0, 0xFFFFFFFE, size=2, dtype=np.uint64), thr),        # ~1500
+          chance_query(rng, subs, 30, [], 0),                                                            # ~1800
+          chance_query(rng, subs, 45, rng.integers(0, 0xFFFFFFFE, size=1, dtype=np.uint64), subs),       # > 2048
+          chance_query(rng, subs, 3, rng.integers(0, 0xFFFFFFFE, size=5, dtype=np.uint64), thr + 1),
+          [np.asarray([4], np.uint32)] * subs]
+    T = [sum(len(l) for l in lists) for lists in qs]
+    assert sum(1024 < t <= 2048 for t in T) >= 3 and any(t > 2048 for t in T), T
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, grid=2, wide=True)
+    assert sorted(int(x) for x in heavy[:counters[0]]) == [q for q, t in enumerate(T) if t > 2048]
+    assert counters[1] == sum(T)
+    for q, lists in enumerate(qs):
+        if T[q] > 2048:
+            assert qcount[q] == 0 and qpos[q] == np.iinfo(np.uint64).max
+            continue
+        want = expected(lists, thr)
+        got = tmp[int(qpos[q]):int(qpos[q]) + int(qcount[q])]
+        assert got.size == want.size and (got == want).all(), f"query {q} (T = {T[q]})"
+    # the narrow instantiation hands the same three queries on
+    qcount, qpos, tmp, heavy, counters = run_count(emul, qs, subs, thr, grid=2, wide=False)
+    assert sorted(int(x) for x in heavy[:counters[0]]) == [q for q, t in enumerate(T) if t > 1024]
 
 
 def test_lookup_kernel_body_result_buffer_too_small(emul):
