@@ -266,7 +266,8 @@ int nsmh_query_sketches(nsmh_handle h, const uint64_t *sketches, uint32_t num_qu
 /* ---- instrumentation ------------------------------------------------------------------ */
 /* Device time (CUDA events on the engine's stream) of the last call of each stage, ms. */
 typedef struct {
-    float h2d_pack_ms;   /* nsmh_load_reads_ascii: H2D + pack, whole call */
+    float h2d_pack_ms;   /* host loaders: H2D + pack, whole call (nsmh_initialize_* / nsmh_load_sketch_*: up to the last chunk's pack,
+                          * the sketches of the earlier chunks included) */
     float pack_ms;       /* pack kernels only */
     float sketch_ms;     /* nsmh_sketch */
     float sketch_main_ms;   /* main sketch kernel only */

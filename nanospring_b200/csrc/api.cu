@@ -358,6 +358,7 @@ static int set_offsets_host(nsmh_ctx *c, const uint64_t *offsets, uint32_t num_r
 
 static void invalidate(nsmh_ctx *c) {
     c->reads_loaded = false;
+    c->load_timed = false;
     c->flags_valid = false;
     c->sketched = false;
     c->tables.built = false;
@@ -487,6 +488,7 @@ static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, u
         if (packed[i]) cudaEventDestroy(packed[i]);
     }
     if (rc) { invalidate(c); return rc; }
+    c->load_timed = then_sketch;       // nsmh_get_stats reads the events once the stream has drained
     if (!then_sketch) c->stats.h2d_pack_ms = elapsed(c->ev[0], c->ev[1]);
     c->reads_loaded = true;
     return NSMH_OK;
@@ -602,6 +604,7 @@ static int load_dnabitset(nsmh_ctx *c, const uint8_t *packed, const uint32_t *le
     for (cudaEvent_t ev : copied)
         if (ev) cudaEventDestroy(ev);
     if (rc) { invalidate(c); return rc; }
+    c->load_timed = true;
     c->reads_loaded = true;
     return NSMH_OK;
 }
@@ -1132,6 +1135,7 @@ int nsmh_get_stats(nsmh_handle c, nsmh_stats *out) {
     NSMH_CK(cudaStreamSynchronize(c->stream));
     // device-resident loads return before the pack kernel has run: its events are read here
     if (c->reads.external_offsets && c->reads_loaded) c->stats.pack_ms = elapsed(c->ev[0], c->ev[1]);
+    if (c->load_timed) c->stats.h2d_pack_ms = elapsed(c->ev[0], c->ev[1]);     // pipelined: includes the sketches of all but the last chunk
     if (c->build_timed) c->stats.build_ms = elapsed(c->ev[6], c->ev[7]);
     if (c->sketched) {
         c->stats.sketch_ms = elapsed(c->ev[2], c->ev[3]);

@@ -118,6 +118,7 @@ struct nsmh_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[10] = {};
     bool build_timed = false;
+    bool load_timed = false;        // ev[0], ev[1] bracket a pipelined load that returned before the device finished
     int sketch_mode = 0;
     int num_sms = 148;
 

@@ -15,12 +15,6 @@ __device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, 
 __device__ __forceinline__ void stg256(void *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
-// Hint: bring `bytes` (multiple of 16) starting at p (16-byte aligned) into L2, asynchronously, by ONE thread
-// (cp.async.bulk.prefetch.L2, sm_90+).  The table kernels work through the hash functions in order and ask
-// for the slice of the NEXT regions while they hammer the current ones with random accesses.
-__device__ __forceinline__ void l2_prefetch_bulk(const void *p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void l2_prefetch_line(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 // Bulk copy shared -> global (cp.async.bulk, sm_90+): ONE thread hands `bytes` (multiple of 16; both addresses
 // 16-byte aligned) to the copy engine, which writes full lines - to local memory or to a peer's over NVLink.
@@ -42,7 +36,6 @@ __device__ __forceinline__ void bulk_store_commit() {}
 template <int N>
 __device__ __forceinline__ void bulk_store_wait_read() {}
 __device__ __forceinline__ void bulk_store_wait_all() {}
-__device__ __forceinline__ void l2_prefetch_bulk(const void *, uint32_t) {}
 __device__ __forceinline__ void l2_prefetch_line(const void *) {}
 __device__ __forceinline__ void ldg256(const void *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d) {
     const uint64_t *q = static_cast<const uint64_t *>(p);
@@ -53,19 +46,5 @@ __device__ __forceinline__ void stg256(void *p, uint64_t a, uint64_t b, uint64_t
     q[0] = a; q[1] = b; q[2] = c; q[3] = d;
 }
 #endif
-
-// Work units are (column group, chunk of rows), column group major.  The unit (cg, chunk) asks for slice
-// `chunk` of every region of column group cg + 1: by the time the grid gets there (chunks units later) the
-// regions are L2 resident and the random bucket accesses hit.  Called by the first `cols` threads of a block.
-__device__ __forceinline__ void prefetch_next_regions(const void *slots, uint64_t region_bytes, uint32_t n, uint32_t cols,
-                                                      uint32_t cg, uint32_t chunk, uint32_t chunks, uint32_t t) {
-    const uint32_t l = (cg + 1) * cols + t;
-    if (t >= cols || l >= n) return;
-    const uint64_t slice = ((region_bytes + chunks - 1) / chunks + 15) & ~15ULL;
-    const uint64_t off = slice * chunk;
-    if (off >= region_bytes) return;
-    const uint64_t len = region_bytes - off < slice ? (region_bytes - off) & ~15ULL : slice;
-    if (len) l2_prefetch_bulk(static_cast<const uint8_t *>(slots) + (uint64_t)l * region_bytes + off, (uint32_t)len);
-}
 
 } // namespace nsmh
