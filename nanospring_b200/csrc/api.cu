@@ -428,7 +428,8 @@ static int load_ascii(nsmh_ctx *c, const char *bases, const uint64_t *offsets, u
     NSMH_TRY(alloc_packed(c->reads, total, c->stream));
     if (then_sketch) {
         c->reads_loaded = true;
-        NSMH_TRY(sketch_begin(c, true));
+        const int rc0 = sketch_begin(c, true);
+        if (rc0) { invalidate(c); return rc0; }
     }
     // Double-buffered chunks: H2D of chunk i+1 on the copy stream overlaps the pack of chunk i.
     const uint64_t chunk = load_chunk_bytes(64ULL << 20) + 15 & ~15ULL;   // bases per chunk, multiple of 16

@@ -287,10 +287,12 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
     }
     if (const char *dbg = getenv("NSMH_MG_DEBUG_LOCAL_STORES")) {
         // timing experiment only (results are wrong): the probe results of ALL reads go to this rank's own arena
-        if (atoi(dbg) != 0)
+        // 1: result tiles and inbox ids stay local; 2: only the inbox ids do; 3: only the result tiles do
+        const int mode = atoi(dbg);
+        if (mode != 0)
             for (uint32_t r = 0; r < m->world; ++r) {
-                pd.pr[r] = reinterpret_cast<uint64_t *>(m->arena + m->self.off_pr);
-                pd.inbox[r] = reinterpret_cast<uint32_t *>(m->arena + m->self.off_inbox) + (size_t)m->rank * m->self.inbox_cap;
+                if (mode != 2) pd.pr[r] = reinterpret_cast<uint64_t *>(m->arena + m->self.off_pr);
+                if (mode != 3) pd.inbox[r] = reinterpret_cast<uint32_t *>(m->arena + m->self.off_inbox) + (size_t)m->rank * m->self.inbox_cap;
             }
     }
     ba.world = sa.world = pd.world = pl.world = m->world;

@@ -72,7 +72,7 @@ inline MgLayout mg_layout(uint32_t total_rows, uint32_t ncols, uint32_t my_rows,
     if (cap < 64) cap = 64;
     if (cap > (1ull << 30)) cap = 1ull << 30;
     if (inbox_cap_override > 0) cap = (uint64_t)(inbox_cap_override < (1ll << 30) ? inbox_cap_override : (1ll << 30));
-    t.inbox_cap = (uint32_t)cap;
+    t.inbox_cap = (uint32_t)(cap + 3 & ~3ull);          // segments and the bulk copies into them stay 16-byte aligned
     t.off_inbox = off;  off = align256(off + (size_t)world * t.inbox_cap * sizeof(uint32_t));
     t.off_flags = off;  off = align256(off + (3 * kMgMaxRanks + 8) * sizeof(uint32_t));
     t.arena_bytes = off;

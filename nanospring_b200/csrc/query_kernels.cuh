@@ -178,14 +178,26 @@ probe_items_kernel(ProbeSrc src, uint32_t nq) {
 // as ONE dense run per read owner into that owner's memory (peer mapping over NVLink): consecutive threads
 // store consecutive 8-byte words, i.e. full 128-byte lines.  (The first version stored 32 bytes per thread
 // at a stride of ncols * 8 bytes - half-written lines - and its time tripled from 2 to 8 ranks.)
-// A group of two travels inside the result word; groups of 3..kInboxMaxGroup members are pushed along: their ids are copied into this rank's segment of
-// the read owner's inbox (space comes from a LOCAL cursor, one warp-aggregated atomic per warp), so the
-// counting kernel over there finds them in its own memory instead of paying an NVLink round trip per
-// list.  Larger groups and anything beyond the inbox capacity stay behind and are read remotely on demand.
+// A group of two travels inside the result word; groups of 3..kInboxMaxGroup members are pushed along: their ids
+// go into this rank's segment of the read owner's inbox, so the counting kernel over there finds them in its own
+// memory instead of paying an NVLink round trip per list.  The ids of a tile are STAGED in shared memory and leave
+// as one bulk copy next to the tile (space from a LOCAL cursor, one atomic per tile).  (The first version let every
+// thread store its lists' ids straight into the peer's inbox, 4 bytes at a time: measured on 8 GPUs those
+// scattered remote stores were 0.15 of the kernel's 0.36 ms, the 16 KB tiles cost nothing -
+// profiles/r2_remote_store_split_s26.txt.)  Larger groups, what does not fit the staging area or the inbox, and
+// the few tiles whose rows belong to two owners (direct stores there) stay behind and are read remotely on demand.
+#ifndef NSMH_STAGE_IDS
+#define NSMH_STAGE_IDS 1792            // (the host emulation builds with a small value so that tiles overflow it)
+#endif
+constexpr int kStageIds = NSMH_STAGE_IDS;      // ids staged per tile (7 per row on average; beyond that lists stay behind)
+static_assert(kStageIds % 4 == 0, "the staged ids leave in 16-byte pieces");
+
 __global__ void __launch_bounds__(kProbeRows, 4)
 probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
     __align__(128) __shared__ uint64_t s_tile[2][kProbeRows * kPeerCols];     // two tiles: one may still be leaving
-    const int lane = threadIdx.x & 31;
+    __align__(16) __shared__ uint32_t s_ids[2][kStageIds];                     // ... and the inbox ids that go with them
+    __shared__ uint32_t s_wsum[kProbeRows / 32], s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t chunks = (nq + kProbeRows - 1) / kProbeRows;
     const uint32_t colblocks = (src.n + kPeerCols - 1) / kPeerCols;
     const uint32_t units = chunks * colblocks;
@@ -194,25 +206,30 @@ probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
     uint32_t round = 0;
     for (uint32_t u = blockIdx.x; u < units; u += gridDim.x, ++round) {
         uint64_t *tile = s_tile[round & 1];
+        uint32_t *stage = s_ids[round & 1];
         // every rank starts with the chunks of its own reads and walks on from there: at any time the ranks
         // store into DIFFERENT peers (all of them starting at row 0 put 7 senders on one receiver's links)
         const uint32_t cbk = u / chunks;
         uint32_t chunk = u - cbk * chunks + dst.chunk0;
         chunk = chunk >= chunks ? chunk - chunks : chunk;
-        const uint32_t q = chunk * kProbeRows + threadIdx.x;
+        const uint32_t q0 = chunk * kProbeRows, nr = min((uint32_t)kProbeRows, nq - q0);
+        const uint32_t q = q0 + threadIdx.x;
         const uint32_t c0 = cbk * kPeerCols, w = min((uint32_t)kPeerCols, src.n - c0);     // this group's hash functions
         const bool active = q < nq;
-        uint32_t o = 0;
-        if (active)
+        uint32_t o_first = 0;
+        while (o_first + 1 < dst.world && q0 >= dst.row_end[o_first]) ++o_first;
+        const bool one_owner = q0 + nr <= dst.row_end[o_first];     // block-uniform
+        uint32_t o = o_first;
+        if (active && !one_owner)
             while (o + 1 < dst.world && q >= dst.row_end[o]) ++o;        // owner of read q
-        // the copy that took this buffer two rounds ago has read it (the issuing thread waits, the barrier tells the rest)
-        if (threadIdx.x == 0) bulk_store_wait_read<1>();
-        __syncthreads();
-        for (uint32_t l0 = c0; l0 < c0 + kPeerCols; l0 += kProbeCols) {
-            uint32_t val[kProbeCols], cnt[kProbeCols];
-            uint32_t need = 0;
+        // ---- probe: kPeerCols tables, kProbeCols at a time ----
+        uint32_t val[kPeerCols], cnt[kPeerCols];
+        uint32_t need = 0;
 #pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) val[j] = cnt[j] = 0;
+        for (int g = 0; g < kPeerCols / kProbeCols; ++g) {
+            const uint32_t l0 = c0 + g * kProbeCols;
+#pragma unroll
+            for (int j = 0; j < kProbeCols; ++j) val[g * kProbeCols + j] = cnt[g * kProbeCols + j] = 0;
             if (active && l0 < c0 + w) {
                 const size_t t0 = (size_t)q * src.n + l0;
                 uint64_t key[kProbeCols];
@@ -231,51 +248,76 @@ probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
 #pragma unroll
                 for (int j = 0; j < kProbeCols; ++j) {
                     const Slot *region = src.slots + (uint64_t)min(l0 + j, src.n - 1) * rstride;
+                    uint32_t v = 0, c = 0;
                     for (;;) {
-                        if (key[j] == kEmptyKey || sa[j] == key[j]) { val[j] = (uint32_t)sb[j]; cnt[j] = (uint32_t)(sb[j] >> 32) + 1u; break; }
-                        if (sa[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
-                        if (sc[j] == key[j]) { val[j] = (uint32_t)sd[j]; cnt[j] = (uint32_t)(sd[j] >> 32) + 1u; break; }
-                        if (sc[j] == kEmptyKey) { val[j] = 0; cnt[j] = 0; break; }
+                        if (key[j] == kEmptyKey || sa[j] == key[j]) { v = (uint32_t)sb[j]; c = (uint32_t)(sb[j] >> 32) + 1u; break; }
+                        if (sa[j] == kEmptyKey) break;
+                        if (sc[j] == key[j]) { v = (uint32_t)sd[j]; c = (uint32_t)(sd[j] >> 32) + 1u; break; }
+                        if (sc[j] == kEmptyKey) break;
                         b[j] = b[j] + 1 == nb ? 0 : b[j] + 1;
                         ldg256(region + 2 * b[j], sa[j], sb[j], sc[j], sd[j]);
                     }
-                    if (l0 + j >= c0 + w) val[j] = cnt[j] = 0;
-                    if (cnt[j] >= 3 && cnt[j] <= (uint32_t)kInboxMaxGroup) need += cnt[j];
+                    if (l0 + j >= c0 + w) v = c = 0;
+                    val[g * kProbeCols + j] = v;
+                    cnt[g * kProbeCols + j] = c;
+                    if (c >= 3 && c <= (uint32_t)kInboxMaxGroup) need += c;
                 }
-            }
-            // inbox space: one atomic per warp for the lanes that share the first lane's destination
-            const uint32_t o_lead = __shfl_sync(0xffffffffu, o, 0);
-            const bool agg = active && o == o_lead;
-            const uint32_t incl = warp_incl_scan(agg ? need : 0u, lane);
-            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t base = 0;
-            if (tot) {
-                if (lane == 31) base = inbox_take(dst.cursor + o_lead, tot, dst.inbox_cap[o_lead]);
-                base = __shfl_sync(0xffffffffu, base, 31);
-            }
-            uint32_t pos = agg ? base + incl - need : (need ? inbox_take(dst.cursor + o, need, dst.inbox_cap[o]) : 0u);
-            const bool fits = need && (uint64_t)pos + need <= dst.inbox_cap[o];
-#pragma unroll
-            for (int j = 0; j < kProbeCols; ++j) {
-                uint64_t out = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
-                if (cnt[j] == 2) {
-                    // a group of two travels inside the result word (ids < 2^31: checked by nsmh_mg_init)
-                    const uint32_t i0 = src.ids[val[j]], i1 = src.ids[val[j] + 1];
-                    out = (uint64_t)i0 | ((uint64_t)i1 << 31) | ((uint64_t)kPairFlag << 32);
-                } else if (fits && cnt[j] >= 3 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
-                    uint32_t *box = dst.inbox[o] + pos;
-                    for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
-                    out = (uint64_t)pos | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
-                    pos += cnt[j];
-                }
-                tile[threadIdx.x * kPeerCols + (l0 - c0) + j] = out;        // rows past nq / unused columns: zeroes
             }
         }
+        // ---- inbox space for the tile's small groups ----
+        // the copies that took these buffers two rounds ago have read them (the issuing thread waits, the
+        // barriers below tell the rest)
+        if (threadIdx.x == 0) bulk_store_wait_read<1>();
+        uint32_t pos;           // where this thread's ids go: in the staging area (one owner) or in the inbox itself
+        bool fits;
+        uint32_t staged = 0;    // ids of the tile that leave through the staging area
+        if (one_owner) {
+            const uint32_t incl = warp_incl_scan(need, lane);
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            uint32_t before = 0, total = 0;
+#pragma unroll
+            for (int ww = 0; ww < kProbeRows / 32; ++ww) {
+                const uint32_t t = s_wsum[ww];
+                before += ww < warp ? t : 0u;
+                total += t;
+            }
+            pos = before + incl - need;
+            staged = min(total, (uint32_t)kStageIds) + 3u & ~3u;       // whole 16-byte pieces (the tail is padding)
+            if (threadIdx.x == 0) {
+                uint32_t base = 0xFFFFFFFFu;
+                if (staged) {
+                    base = inbox_take(dst.cursor + o_first, staged, dst.inbox_cap[o_first]);
+                    if ((uint64_t)base + staged > dst.inbox_cap[o_first]) base = 0xFFFFFFFFu;
+                }
+                s_base = base;
+            }
+            __syncthreads();
+            fits = need && s_base != 0xFFFFFFFFu && pos + need <= (uint32_t)kStageIds;
+        } else {
+            // rows of two owners (at most world - 1 tiles): every thread for itself, straight into the inbox
+            const uint32_t take = need + 3u & ~3u;                      // the cursors stay multiples of 4
+            pos = take ? inbox_take(dst.cursor + o, take, dst.inbox_cap[o]) : 0u;
+            fits = need && (uint64_t)pos + take <= dst.inbox_cap[o];
+            __syncthreads();
+        }
+        const uint32_t base = one_owner ? s_base : 0u;
+#pragma unroll
+        for (int j = 0; j < kPeerCols; ++j) {
+            uint64_t out = (uint64_t)val[j] | ((uint64_t)cnt[j] << 32);
+            if (cnt[j] == 2) {
+                // a group of two travels inside the result word (ids < 2^31: checked by nsmh_mg_init)
+                const uint32_t i0 = src.ids[val[j]], i1 = src.ids[val[j] + 1];
+                out = (uint64_t)i0 | ((uint64_t)i1 << 31) | ((uint64_t)kPairFlag << 32);
+            } else if (fits && cnt[j] >= 3 && cnt[j] <= (uint32_t)kInboxMaxGroup) {
+                uint32_t *box = one_owner ? stage + pos : dst.inbox[o] + pos;
+                for (uint32_t i = 0; i < cnt[j]; ++i) box[i] = src.ids[val[j] + i];
+                out = (uint64_t)(base + pos) | ((uint64_t)(cnt[j] | kInboxFlag) << 32);
+                pos += cnt[j];
+            }
+            tile[threadIdx.x * kPeerCols + j] = out;        // rows past nq / unused columns: zeroes
+        }
         // ---- the tile [rows of the chunk][kPeerCols] leaves: a dense, 64-byte-aligned run per read owner ----
-        const uint32_t q0 = chunk * kProbeRows, nr = min((uint32_t)kProbeRows, nq - q0);
-        uint32_t o_first = 0;
-        while (o_first + 1 < dst.world && q0 >= dst.row_end[o_first]) ++o_first;
-        const bool one_owner = q0 + nr <= dst.row_end[o_first];
         bulk_store_fence();                 // the tile's stores are visible to the copy engine
         __syncthreads();
         if (one_owner) {
@@ -283,6 +325,7 @@ probe_to_peers_kernel(ProbeSrc src, uint32_t nq, PeerDst dst) {
                 const uint32_t r0 = o_first ? dst.row_end[o_first - 1] : 0u, rows_o = dst.row_end[o_first] - r0;
                 bulk_store(dst.pr[o_first] + (size_t)rows_o * dst.pcol0 + peer_result_index(rows_o, q0 - r0, c0),
                            tile, nr * kPeerCols * (uint32_t)sizeof(uint64_t));
+                if (s_base != 0xFFFFFFFFu) bulk_store(dst.inbox[o_first] + s_base, stage, staged * (uint32_t)sizeof(uint32_t));
                 bulk_store_commit();
             }
         } else {

@@ -7,6 +7,7 @@
 // barriers are not needed: a stage finishes on all ranks before the next begins.
 // tests/test_multigpu_emul.py compares every rank's candidate lists with the oracle.
 #define NSMH_HOST_EMUL 1
+#define NSMH_STAGE_IDS 96       // probe_to_peers_kernel: some tiles overflow the staging area of their inbox ids, some do not
 #include "cuda_host_shim.h"
 
 #include <algorithm>
