@@ -64,14 +64,14 @@ public:
         std::string s;
         size_t cap = (size_t)rD.avgReadLen * numReads + (size_t)rD.maxReadLen + 1024, used = 0;
         char *bases = nullptr;
-        check(nsmh_host_alloc(cap, reinterpret_cast<void **>(&bases)));
+        check(nsmh_host_alloc_near(stagingDevice(), cap, reinterpret_cast<void **>(&bases)));
         try {
             for (read_t i = 0; i < numReads; ++i) {
                 rD.getRead(i, s);
                 if (used + s.size() > cap) {
                     size_t ncap = (used + s.size()) * 2;
                     char *nb = nullptr;
-                    check(nsmh_host_alloc(ncap, reinterpret_cast<void **>(&nb)));
+                    check(nsmh_host_alloc_near(stagingDevice(), ncap, reinterpret_cast<void **>(&nb)));
                     std::copy(bases, bases + used, nb);
                     nsmh_host_free(bases);
                     bases = nb;
@@ -119,7 +119,7 @@ public:
         size_t bytes = 0;
         for (auto l : lengths) bytes += ((size_t)l + 3) / 4;
         uint8_t *buf = nullptr;
-        check(nsmh_host_alloc(bytes ? bytes : 1, reinterpret_cast<void **>(&buf)));
+        check(nsmh_host_alloc_near(stagingDevice(), bytes ? bytes : 1, reinterpret_cast<void **>(&buf)));
         FILE *fp = std::fopen(path.c_str(), "rb");
         const size_t got = fp ? std::fread(buf, 1, bytes, fp) : 0;
         if (fp) std::fclose(fp);
@@ -261,6 +261,8 @@ private:
             check(nsmh_create((uint32_t)k, (uint32_t)n, (uint32_t)overlapSketchThreshold, randNumbers.data(),
                               devices.empty() ? device : devices[0], &h_));
     }
+    /** the device whose NUMA node the pinned staging buffers are taken from */
+    int stagingDevice() const { return devices.empty() ? device : devices[0]; }
     void sketchAndBuild() {
         if (m_) {
             check(nsmh_multi_sketch(m_));
