@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-ingest", action="store_true", help="skip the FASTQ-ingest side measurement (N=1 only)")
+    ap.add_argument("--separate-build", action="store_true", help="nsmh_sketch then nsmh_build instead of nsmh_sketch_build (A/B)")
     ap.add_argument("--no-legs", action="store_true", help="skip the side legs (other BASELINE configs, brute-force roofline)")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the parity checks of the multi-GPU result")
     ap.add_argument("--multi", default="auto", choices=["auto", "peer", "replicated", "partitioned"],
@@ -408,6 +409,9 @@ def main():
 
     def device_step():
         f.load_device(d_bases.data_ptr(), d_off.data_ptr(), lengths.size, total_bases)
+        if world == 1 and not args.separate_build:
+            f.sketch_build()        # nsmh_sketch_build: the sketch's fix-up pass beside the table insert
+            return f.queryAll(False, fetch=False)
         f.sketch()
         if pf is not None:
             return pf.run(lengths.size, rows_per_rank)

@@ -115,11 +115,11 @@ class Leg:
     def step(self):
         f = self.f
         f.load_device(self.d_bases.data_ptr(), self.d_off.data_ptr(), self.offsets.size - 1, self.bases)
+        if self.pf is None:
+            f.sketch_build()
+            return f.queryAll(False, fetch=False)
         f.sketch()
-        if self.pf is not None:
-            return self.pf.run()
-        f.build()
-        return f.queryAll(False, fetch=False)
+        return self.pf.run()
 
     def csr(self, total):
         if self.pf is not None:

@@ -145,6 +145,11 @@ int nsmh_set_table_sketches(nsmh_handle h, const uint64_t *d_sketches, uint32_t 
                             uint32_t id_base);
 /* populateHashTables() (ReadFilter.cpp:159-172): build the n key -> read-id tables. */
 int nsmh_build(nsmh_handle h);
+/* nsmh_sketch + nsmh_build as one call (the body of MinHashReadFilter::initialize once the reads are on the
+ * device, ReadFilter.cpp:21-47): the exact fix-up pass of the sketch runs on a second stream beside the table
+ * insert, and the few entries it produces are inserted from a list afterwards.  Sketches and tables are those of
+ * the two separate calls (tests/test_gpu_parity.py::test_sketch_build_overlap_equals_separate_calls). */
+int nsmh_sketch_build(nsmh_handle h);
 /* Number of distinct keys of table j (BBHashMap::numKeys, BBHashMap.cpp:35). */
 int nsmh_table_num_keys(nsmh_handle h, uint32_t j, uint32_t *num_keys);
 

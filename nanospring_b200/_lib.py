@@ -77,6 +77,7 @@ _SIGS = {
     "nsmh_sketches_device_ptr": [C.c_void_p, C.POINTER(C.c_void_p)],
     "nsmh_set_table_sketches": [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32],
     "nsmh_build": [C.c_void_p],
+    "nsmh_sketch_build": [C.c_void_p],
     "nsmh_table_num_keys": [C.c_void_p, C.c_uint32, u32p],
     "nsmh_query_all": [C.c_void_p, C.c_int, u64p],
     "nsmh_query_all_result": [C.c_void_p, u64p, u32p],

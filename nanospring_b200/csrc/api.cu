@@ -324,7 +324,8 @@ int nsmh_destroy(nsmh_handle h) {
         free_ws(h->bulk, s);
         DevBuf *bufs[] = {&h->d_rand, &h->d_ftab_first, &h->d_ftab_next, &h->d_ftab_hit3, &h->sketches,
                           &h->tile_start, &h->read_flags, &h->counters, &h->build_multi, &h->build_tmp,
-                          &h->tables.slots, &h->tables.ids};
+                          &h->tables.slots, &h->tables.ids, &h->defer.buf};
+        if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);      // a deferred fix-up may still read its buffers
         for (DevBuf *b : bufs) b->release(s);
         if (h->reads.external_offsets) { h->reads.offsets.p = nullptr; h->reads.offsets.cap = 0; }
         h->reads.release(s);
@@ -333,6 +334,8 @@ int nsmh_destroy(nsmh_handle h) {
         for (auto &ev : h->ev) if (ev) cudaEventDestroy(ev);
         if (h->ev_order) cudaEventDestroy(h->ev_order);
         if (h->ev_cleared) cudaEventDestroy(h->ev_cleared);
+        if (h->defer.filtered) cudaEventDestroy(h->defer.filtered);
+        if (h->defer.fixed) cudaEventDestroy(h->defer.fixed);
         if (h->stream && h->owns_stream) cudaStreamDestroy(h->stream);
         if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
         cudaGetLastError();
@@ -406,9 +409,9 @@ static int sketch_range(nsmh_ctx *c, uint32_t r0, uint32_t r1) {
                         c->stream, &c->launches, last ? c->ev[4] : nullptr, last ? c->ev[5] : nullptr, r0, r1);
 }
 
-static int build_enqueue(nsmh_ctx *c) {
+static int build_enqueue(nsmh_ctx *c, SketchDeferred *defer = nullptr) {
     NSMH_CK(cudaEventRecord(c->ev[6], c->stream));
-    NSMH_TRY(build_tables(c));
+    NSMH_TRY(build_tables(c, defer));
     NSMH_CK(cudaEventRecord(c->ev[7], c->stream));
     c->build_timed = true;          // no host round trip here: nsmh_get_stats reads the events
     return NSMH_OK;
@@ -836,6 +839,35 @@ int nsmh_sketch(nsmh_handle c) {
     NSMH_TRY(sketch_begin(c));
     NSMH_TRY(sketch_range(c, 0, c->reads.num_reads));
     return sketch_end(c);
+}
+
+// sketch + build with the sketch's exact fix-up (sketch_missing / sketch_fixup kernels, ALU-bound) on the second
+// stream beside the table insert (bound by the L2 atomic rate): the two do not compete for the same unit, and the
+// handful of entries the fix-up produces are inserted from a list afterwards.  When the call returns everything is
+// queued on the context's stream in order, so any later call sees final sketches and tables.
+int nsmh_sketch_build(nsmh_handle c) {
+    CTX_GUARD(c);
+    if (!c->reads_loaded) return fail(NSMH_ESTATE, "sketch_build: no reads loaded");
+    const bool overlap = c->sketch_mode == 0 && c->n <= 255 && !c->mg;      // the brute-force kernel has no fix-up
+    NSMH_TRY(sketch_begin(c));
+    SketchDeferred *d = nullptr;
+    if (overlap) {
+        d = &c->defer;
+        d->aux = c->copy_stream;
+        if (!d->filtered) NSMH_CK(cudaEventCreateWithFlags(&d->filtered, cudaEventDisableTiming));
+        if (!d->fixed) NSMH_CK(cudaEventCreateWithFlags(&d->fixed, cudaEventDisableTiming));
+        d->pending = false;
+    }
+    NSMH_TRY(sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp, c->sketch_mode, c->stream,
+                          &c->launches, c->ev[4], c->ev[5], 0, ~0u, d));
+    NSMH_TRY(sketch_end(c));
+    const int rc = build_enqueue(c, d);
+    if (rc && d && d->pending) {        // the fix-up never ran or its values were not stored: the sketches are not final
+        cudaStreamSynchronize(c->copy_stream);
+        c->sketched = false;
+        d->pending = false;
+    }
+    return rc;
 }
 
 int nsmh_get_sketches(nsmh_handle c, uint64_t *out) {

@@ -5,6 +5,7 @@
 
 #include <mutex>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include "../../include/nsmh.h"
@@ -111,6 +112,21 @@ struct MgState;
 
 } // namespace nsmh
 
+// nsmh_sketch_build: the exact fix-up of the sketch (entries no k-mer matched on the filter prefix) runs on a second
+// stream beside the table insert; its values wait here until table_insert_list_kernel stores and inserts them.
+struct SketchDeferred {
+    nsmh::DevBuf buf;                         // vals u64 [entries] | list u32 [entries]
+    cudaStream_t aux = nullptr;         // the context's copy stream
+    cudaEvent_t filtered = nullptr, fixed = nullptr;
+    uint64_t *vals = nullptr;
+    uint32_t *list = nullptr;           // entry index = read * n + hash
+    unsigned int *count = nullptr;
+    uint64_t *sk = nullptr;             // the sketch matrix the entries belong to
+    uint32_t n = 0;
+    bool pending = false;
+    std::function<int()> launch;        // queues the two fix-up kernels on aux (called once the insert kernel is queued)
+};
+
 struct nsmh_ctx {
     int device = 0;
     uint32_t k = 0, n = 0, thr = 0;
@@ -118,6 +134,7 @@ struct nsmh_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[10] = {};
     bool build_timed = false;
+    SketchDeferred defer;           // nsmh_sketch_build
     bool load_timed = false;        // ev[0], ev[1] bracket a pipelined load that returned before the device finished
     int sketch_mode = 0;
     int num_sms = 148;
@@ -191,10 +208,10 @@ int unpack_ascii_device(nsmh_ctx *c, uint64_t b0, uint64_t nb, uint8_t *d_out, c
 int build_filter_tables(nsmh_ctx *c);
 int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &tile_start,
                  DevBuf &cub_tmp, int mode, cudaStream_t s, uint32_t *launches, cudaEvent_t ev0,
-                 cudaEvent_t ev1, uint32_t r0 = 0, uint32_t r1 = ~0u);
+                 cudaEvent_t ev1, uint32_t r0 = 0, uint32_t r1 = ~0u, SketchDeferred *defer = nullptr);
 
 // ---- table.cu ----------------------------------------------------------------
-int build_tables(nsmh_ctx *c);
+int build_tables(nsmh_ctx *c, SketchDeferred *defer = nullptr);
 int preclear_tables(nsmh_ctx *c, uint32_t rows, bool in_order = false);
 int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
 

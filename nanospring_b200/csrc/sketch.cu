@@ -66,7 +66,7 @@ int build_filter_tables(nsmh_ctx *c) {
 // stream, read indices are relative to r0.
 int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &tile_start,
                  DevBuf &cub_tmp, int mode, cudaStream_t s, uint32_t *launches, cudaEvent_t ev0,
-                 cudaEvent_t ev1, uint32_t r0, uint32_t r1) {
+                 cudaEvent_t ev1, uint32_t r0, uint32_t r1, SketchDeferred *defer) {
     if (r1 > rs.num_reads) r1 = rs.num_reads;
     if (r0 >= r1) return NSMH_OK;
     const uint32_t nr = r1 - r0;
@@ -139,10 +139,39 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
         if (ev1) NSMH_CK(cudaEventRecord(ev1, s));
         uint32_t *miss_list = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(cub_tmp.p) + list_off);
         unsigned int *miss_count = a.tile_queue + 1;
-        sketch_missing_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
-        sketch_fixup_kernel<4><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+        if (defer) {
+            // The fix-up runs on the second stream, beside whatever the caller queues next on `s` (the table
+            // insert), and leaves its values in a buffer of their own: the sketch matrix keeps all-ones for the
+            // listed entries until table_insert_list_kernel stores and inserts them.
+            const size_t entries = (size_t)nr * c->n;
+            NSMH_TRY(defer->buf.ensure(entries * (sizeof(uint32_t) + sizeof(uint64_t)) + 16, s));
+            defer->vals = defer->buf.as<uint64_t>();
+            defer->list = reinterpret_cast<uint32_t *>(defer->vals + entries);
+            defer->count = miss_count;
+            defer->sk = a.sk;
+            defer->n = c->n;
+            NSMH_CK(cudaEventRecord(defer->filtered, s));
+            // queued by build_tables right after its insert kernel, so that the insert's blocks are resident first
+            // and these kernels take what is left of every SM (NSMH_FIXUP_BLOCKS: their blocks per SM)
+            const char *fe = getenv("NSMH_FIXUP_BLOCKS");
+            const int per_sm = fe && *fe && atoi(fe) > 0 ? atoi(fe) : 2;       // measured: profiles/r2_sketch_build_overlap_s31.txt
+            const int grid = c->num_sms * per_sm;
+            SketchDeferred *d = defer;
+            defer->launch = [a, d, miss_count, grid]() -> int {
+                NSMH_CK(cudaStreamWaitEvent(d->aux, d->filtered, 0));
+                sketch_missing_kernel<<<grid, 256, 0, d->aux>>>(a, d->list, miss_count);
+                sketch_fixup_kernel<4><<<grid, 256, 0, d->aux>>>(a, d->list, miss_count, d->vals);
+                NSMH_CK(cudaGetLastError());
+                NSMH_CK(cudaEventRecord(d->fixed, d->aux));
+                return NSMH_OK;
+            };
+            defer->pending = true;
+        } else {
+            sketch_missing_kernel<<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count);
+            sketch_fixup_kernel<4><<<c->num_sms * 8, 256, 0, s>>>(a, miss_list, miss_count, nullptr);
+            NSMH_CK(cudaGetLastError());
+        }
         *launches += 2;
-        NSMH_CK(cudaGetLastError());
     } else {
         int occ = 0;
         NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sketch_brute_kernel<8>, 256, 0));

@@ -388,9 +388,12 @@ sketch_missing_kernel(SketchArgs a, uint32_t *__restrict__ list, unsigned int *_
 // entry falls back to a plain 64-bit scan, so the result is exact in every case.
 // U = words per lane and step (4 by default; NSMH_FIXUP_WIDTH=8 is an experiment: half as many
 // dependent L2 round trips for the long reads that make up the kernel's tail).
+// vals (optional): entry e's value goes to vals[e] instead of the sketch matrix - for the build that runs beside
+// this kernel and must keep seeing all-ones for the listed entries (table_insert_list_kernel stores them later).
 template <int U>
 __global__ void __launch_bounds__(256)
-sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ count) {
+sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ count,
+                    uint64_t *__restrict__ vals) {
     const int lane = threadIdx.x & 31;
     const uint32_t warps = gridDim.x * (blockDim.x >> 5);
     const uint64_t mask = kmer_mask(a.k);
@@ -402,7 +405,10 @@ sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsig
         const uint32_t t = list[e];
         const uint32_t i = t / a.n, lf = t - i * a.n;
         const uint64_t rb = a.off[i], len = a.off[i + 1] - rb;
-        if (len < a.k) continue;          // len == k-1: all-ones is the reference's value (ReadFilter.cpp:119-124)
+        if (len < a.k) {                  // len == k-1: all-ones is the reference's value (ReadFilter.cpp:119-124)
+            if (vals && lane == 0) vals[e] = ~0ULL;
+            continue;
+        }
         TileGeom g;
         g.read = i;
         g.rb = rb;
@@ -468,7 +474,8 @@ sketch_fixup_kernel(SketchArgs a, const uint32_t *__restrict__ list, const unsig
             best = other < best ? other : best;
         }
         if (lane == 0) {
-            a.sk[t] = (r & ~mask) | best;
+            if (vals) vals[e] = (r & ~mask) | best;
+            else a.sk[t] = (r & ~mask) | best;
             atomicAdd(a.counters, 1ULL);
         }
     }

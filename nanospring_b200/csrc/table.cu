@@ -74,7 +74,21 @@ int preclear_tables(nsmh_ctx *c, uint32_t rows, bool in_order) {
     return NSMH_OK;
 }
 
-int build_tables(nsmh_ctx *c) {
+// NSMH_BUILD_LEAVE_BLOCKS: blocks per SM the insert kernel leaves free when the sketch fix-up runs beside it.
+// (The insert kernel's blocks fill the register file: without room the fix-up only runs before or after it.  One
+// block less - 4 of 5 - and two fix-up blocks per SM was the best of the combinations measured,
+// profiles/r2_sketch_build_overlap_s31.txt; the insert kernel's time follows its resident blocks, so the gain is
+// 3-4 % of the step, not the 8 % a free overlap would give.)
+static int build_leave_blocks() {
+    const char *e = getenv("NSMH_BUILD_LEAVE_BLOCKS");
+    return e && *e ? std::max(0, atoi(e)) : 1;
+}
+
+// defer (nsmh_sketch_build): the sketch entries that are still all-ones are being recomputed on the second stream;
+// the insert kernel leaves them out (and leaves that stream room on every SM), table_insert_list_kernel adds them
+// once they are there.  The tables are the same set of groups either way.
+int build_tables(nsmh_ctx *c, SketchDeferred *defer) {
+    if (defer && !defer->pending) defer = nullptr;
     Tables &T = c->tables;
     cudaStream_t s = c->stream;
     const uint32_t n = c->n, rows = c->table_reads;
@@ -93,6 +107,7 @@ int build_tables(nsmh_ctx *c) {
     int occ = 0;
     NSMH_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_insert_kernel, kBuildRows, 0));
     const uint64_t units = (uint64_t)((rows + kBuildRows - 1) / kBuildRows) * ((n + kBuildCols - 1) / kBuildCols);
+    if (defer && occ > 2) occ = std::max(2, occ - build_leave_blocks());
     const uint32_t blocks = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(units, (uint64_t)c->num_sms * (occ > 0 ? occ : 1)));
     const uint32_t seg_cap = kBuildRows * kBuildCols;           // one segment per work unit
     const size_t nseg = (size_t)units * seg_cap;
@@ -120,8 +135,17 @@ int build_tables(nsmh_ctx *c) {
         a.n = n;
         a.seg_cap = seg_cap;
         a.segments = (uint32_t)units;
+        a.skip_empty = defer ? 1u : 0u;
         table_insert_kernel<<<blocks, kBuildRows, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
+        if (defer) {
+            NSMH_TRY(defer->launch());
+            NSMH_CK(cudaStreamWaitEvent(s, defer->fixed, 0));
+            table_insert_list_kernel<<<c->num_sms * 2, 256, 0, s>>>(a, defer->list, defer->count, defer->vals, defer->sk);
+            NSMH_CK(cudaGetLastError());
+            ++c->launches;
+            defer->pending = false;
+        }
         table_groups_kernel<<<c->num_sms * 4, 256, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
         table_fill_kernel<<<c->num_sms * 4, 256, 0, s>>>(a);

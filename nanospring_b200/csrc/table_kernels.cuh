@@ -27,6 +27,7 @@ struct BuildArgs {
     unsigned int *seg_count;            // [2*segments] members, groups of every segment
     uint64_t cap;
     uint32_t rows, n, seg_cap, segments;
+    uint32_t skip_empty;    // 1: all-ones keys are left to table_insert_list_kernel (their values are still being computed)
 };
 
 #ifndef NSMH_HOST_EMUL
@@ -86,7 +87,13 @@ __device__ __forceinline__ uint64_t slot_key_now(const Slot *p) { return __atomi
 // longest probe sequence, and the loop body stays small (the kernel is bound by the L2
 // atomic rate, ~50 G atomics/s whatever their width: tools/micro/atom_bench.cu).
 // Buckets are the two slots of one 32-byte sector.
-__global__ void __launch_bounds__(kBuildRows)
+// 5 resident blocks per SM (48 registers, 4 bytes of spill) instead of the 4 the compiler's 50 registers allow: the
+// kernel's time follows its resident warps (build 0.244 -> 0.228 ms; 6 and 8 blocks spill more and are slower again,
+// profiles/r2_sketch_build_overlap_s31.txt).
+#ifndef NSMH_INSERT_MIN_BLOCKS
+#define NSMH_INSERT_MIN_BLOCKS 5
+#endif
+__global__ void __launch_bounds__(kBuildRows, NSMH_INSERT_MIN_BLOCKS)
 table_insert_kernel(BuildArgs a) {
     __shared__ unsigned int s_count[2];
     const int lane = threadIdx.x & 31;
@@ -137,7 +144,7 @@ table_insert_kernel(BuildArgs a) {
             int state[kBuildCols];          // 0 nothing, 1 claim sent, 2 the key is there already
 #pragma unroll
             for (int jj = 0; jj < kBuildCols; ++jj) {
-                done[jj] = false;
+                done[jj] = a.skip_empty && (uint32_t)jj < nj && keys[jj] == kEmptyKey;      // not this kernel's business
                 frank[jj] = fslot[jj] = 0;
                 state[jj] = 0;
                 hk0[jj] = hk1[jj] = 0;
@@ -269,6 +276,61 @@ table_insert_kernel(BuildArgs a) {
                 }
             }
             if (__all_sync(0xffffffffu, j >= nj)) break;
+        }
+    }
+}
+
+// The entries a build with skip_empty left out, from a list: entry list[e] = row * n + hash function, its key in
+// vals[e] (stored into the sketch matrix on the way).  Same claims and counters as above, one key per thread; a
+// member that is not the first of its group is appended to the segment of the work unit its (row, column) belongs
+// to (the unit's own appends are over: this kernel runs after table_insert_kernel), so the two kernels below need
+// not know about it.  Thousands of entries, not millions: global atomics on the segment counters are fine here.
+__global__ void __launch_bounds__(256)
+table_insert_list_kernel(BuildArgs a, const uint32_t *__restrict__ list, const unsigned int *__restrict__ count,
+                         const uint64_t *__restrict__ vals, uint64_t *__restrict__ sk) {
+    const uint32_t todo = *count;
+    const uint32_t chunks = (a.rows + kBuildRows - 1) / kBuildRows;
+    const uint64_t nb = a.cap >> 1;
+    const uint64_t stride = region_stride(a.cap);
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < todo; e += gridDim.x * blockDim.x) {
+        const uint32_t t = list[e];
+        const uint32_t row = t / a.n, l = t - row * a.n;
+        const uint64_t key = vals[e];
+        if (key != kEmptyKey) sk[t] = key;
+        Slot *region = a.slots + (uint64_t)l * stride;
+        Slot *p;
+        uint32_t rank = 0;
+        if (key == kEmptyKey) {
+            p = region + a.cap;                 // the extra slot, see table_insert_kernel
+            rank = atomicAdd(&p->cntm1, 1u) + 1u;
+            if (rank == 0) p->val = row;
+        } else {
+            uint64_t b = slot_index(key, nb);
+            for (;;) {
+                uint64_t k0, v0, k1, v1;
+                bucket_now(region + 2 * b, k0, v0, k1, v1);
+                const int tt = (k0 == key || k0 == kEmptyKey) ? 0 : (k1 == key || k1 == kEmptyKey) ? 1 : 2;
+                if (tt == 2) { b = b + 1 == nb ? 0 : b + 1; continue; }
+                p = region + 2 * b + tt;
+                uint64_t cur = tt ? k1 : k0;
+                if (cur == kEmptyKey) {
+                    uint64_t old_hi;
+                    slot_cas(p, ~0ULL, ~0ULL, key, (uint64_t)row, cur, old_hi);     // {key, val = id, cnt-1 = 0}
+                    if (cur == kEmptyKey) break;                                    // rank 0: first of its group
+                }
+                if (cur == key) { rank = atomicAdd(&p->cntm1, 1u) + 1u; break; }
+                // another key took the slot meanwhile: look again
+            }
+        }
+        if (rank >= 1) {
+            const uint32_t u = (l / kBuildCols) * chunks + row / kBuildRows;
+            const size_t seg0 = (size_t)u * a.seg_cap;
+            const size_t pos = seg0 + atomicAdd(&a.seg_count[2 * (size_t)u], 1u);
+            const uint32_t sidx = (uint32_t)(p - a.slots);
+            a.m_slot[pos] = sidx;
+            a.m_id[pos] = row;
+            a.m_rank[pos] = rank;
+            if (rank == 1) a.g_slot[seg0 + atomicAdd(&a.seg_count[2 * (size_t)u + 1], 1u)] = sidx;
         }
     }
 }

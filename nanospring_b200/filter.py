@@ -254,6 +254,10 @@ class MinHashReadFilter:
     def build(self):
         check(lib().nsmh_build(self._h))
 
+    def sketch_build(self):
+        """sketch() + build() as one call: the sketch's exact fix-up pass runs beside the table insert."""
+        check(lib().nsmh_sketch_build(self._h))
+
     def _adopt(self, rD):
         """Reads already packed on the device by GpuReadData: take its handle, set k/n/thr/rand."""
         self.close()
@@ -272,8 +276,7 @@ class MinHashReadFilter:
         """ReadFilter.cpp:11-47: sketch every read, then populate the n hash tables."""
         if isinstance(rD, GpuReadData):
             self._adopt(rD)
-            self.sketch()
-            self.build()
+            self.sketch_build()
             return
         if not isinstance(rD, ReadData):
             rD = ReadData.from_reads(rD)

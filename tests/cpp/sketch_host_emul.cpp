@@ -14,7 +14,10 @@
 
 using namespace nsmh;
 
+static int sketch_emul_deferred = 0;
 extern "C" {
+void sketch_emul_set_deferred(int on) { sketch_emul_deferred = on; }
+
 
 // W: packed stream followed by kPackPadWords zero words.  mode 0 = filter kernel + exact fix-up,
 // 1 = brute force.  sk [n_reads][n] out; *fixups = entries the fix-up pass recomputed.  Returns 0,
@@ -62,7 +65,17 @@ int sketch_emul_run(const uint32_t *W, const uint64_t *off, uint32_t n_reads, ui
         free(smem);
         std::vector<uint32_t> miss((size_t)n_reads * n + 1, 0);
         emu_launch(grid, 64, [&] { sketch_missing_kernel(a, miss.data(), queue + 1); });
-        emu_launch(grid, 64, [&] { sketch_fixup_kernel<4>(a, miss.data(), queue + 1); });
+        if (sketch_emul_deferred) {
+            // nsmh_sketch_build: the values go to a buffer of their own; table_insert_list_kernel stores them later
+            std::vector<uint64_t> vals((size_t)n_reads * n + 1, 0x1111111111111111ULL);
+            emu_launch(grid, 64, [&] { sketch_fixup_kernel<4>(a, miss.data(), queue + 1, vals.data()); });
+            for (unsigned int e = 0; e < queue[1]; ++e) {
+                if (a.sk[miss[e]] != ~0ULL) return 7;                       // the matrix must not have been touched
+                a.sk[miss[e]] = vals[e];
+            }
+        } else {
+            emu_launch(grid, 64, [&] { sketch_fixup_kernel<4>(a, miss.data(), queue + 1, nullptr); });
+        }
         *fixups = counters[0];
     } else {
         emu_launch(grid, 64, [&] { sketch_brute_kernel<8>(a); });

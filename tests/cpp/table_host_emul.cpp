@@ -28,7 +28,22 @@ extern "C" {
 
 // sk [rows][n] -> tables kept inside the library (one set at a time).  max_blocks bounds the grid of the
 // insert kernel (build_tables uses the resident blocks of the device).  Returns 0.
+// deferred entries (nsmh_sketch_build): list [count] = row * n + column of the entries of sk that still hold all-ones,
+// vals [count] their keys; sk receives them.  list == nullptr: the plain build.
+static int build_impl(uint64_t *sk, uint32_t rows, uint32_t n, unsigned max_blocks, const uint32_t *list,
+                      unsigned int count, const uint64_t *vals);
+
 int table_emul_build(const uint64_t *sk, uint32_t rows, uint32_t n, unsigned max_blocks) {
+    return build_impl(const_cast<uint64_t *>(sk), rows, n, max_blocks, nullptr, 0, nullptr);
+}
+
+int table_emul_build_deferred(uint64_t *sk, uint32_t rows, uint32_t n, unsigned max_blocks, const uint32_t *list,
+                              unsigned int count, const uint64_t *vals) {
+    return build_impl(sk, rows, n, max_blocks, list, count, vals);
+}
+
+static int build_impl(uint64_t *sk, uint32_t rows, uint32_t n, unsigned max_blocks, const uint32_t *list,
+                      unsigned int count, const uint64_t *vals) {
     g_t = EmulTables();
     g_t.rows = rows;
     g_t.n = n;
@@ -61,7 +76,9 @@ int table_emul_build(const uint64_t *sk, uint32_t rows, uint32_t n, unsigned max
     a.n = n;
     a.seg_cap = seg_cap;
     a.segments = (uint32_t)units;
+    a.skip_empty = list ? 1u : 0u;
     emu_launch_block(blocks, kBuildRows, [&] { table_insert_kernel(a); });
+    if (list) emu_launch(2, 256, [&] { table_insert_list_kernel(a, list, &count, vals, sk); });
     emu_launch(2, 256, [&] { table_groups_kernel(a); });
     emu_launch(2, 256, [&] { table_fill_kernel(a); });
     return 0;

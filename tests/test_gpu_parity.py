@@ -102,6 +102,42 @@ def test_c1_dnabitset_loader(c1_raw, c1_golden, orc):
     f.close()
 
 
+@pytest.mark.parametrize("k,n,thr", [(23, 60, 6), (15, 30, 3), (31, 120, 12), (9, 33, 2)])
+def test_sketch_build_overlap_equals_separate_calls(orc, k, n, thr):
+    """nsmh_sketch_build: the sketch's fix-up pass runs on the second stream beside the table insert, which leaves
+    the all-ones entries to table_insert_list_kernel.  Sketches, distinct keys per table and both bulk lookups must
+    be those of nsmh_sketch + nsmh_build; reads of k-1 bases (legitimate all-ones rows), empty reads, reads shorter
+    than the filter prefix and low-complexity reads (many fix-ups) are in the set."""
+    lengths = ns.synth_lengths(900, 2500, seed=k)
+    lengths[:8] = [0, 1, k - 2 if k > 2 else 0, k - 1, k - 1, k, k + 3, 70000]
+    rd = ns.synth_reads_host(lengths, ns.synth_params(genome_len=150_000, genome_seed=k, read_seed=n))
+    b = rd.bases.copy()
+    o = rd.offsets
+    b[int(o[20]):int(o[21])] = ord("A")                      # homopolymer / dinucleotide reads: hardly any distinct k-mer
+    b[int(o[21]):int(o[22]):2] = ord("C")
+    rd = ReadData(b, o)
+    rnd = ns.rand_from_seed(5 * k + n, n)
+    want = orc.sketch_all(rd.bases, rd.offsets, k, n, rnd)
+    ref = make_filter(k, n, thr, rnd)
+    ref.load(rd)
+    ref.sketch()
+    ref.build()
+    keys = [ref.tableNumKeys(j) for j in range(0, n, 7)]
+    fwd, rc = ref.queryAll(False), ref.queryAll(True)
+    assert (ref.sketches() == want).all()
+    ref.close()
+    f = make_filter(k, n, thr, rnd)
+    for rep in range(2):                                        # twice on one handle: buffers and events are reused
+        f.load(rd)
+        f.sketch_build()
+        assert (f.sketches() == want).all(), "sketches"
+        assert [f.tableNumKeys(j) for j in range(0, n, 7)] == keys
+        assert_csr_equal(f.queryAll(False), fwd, "fwd")
+        assert_csr_equal(f.queryAll(True), rc, "rc")
+    assert f.stats()["sketch_fixups"] > 0
+    f.close()
+
+
 @pytest.mark.parametrize("chunk", [64, 4000, 70001, 1 << 30])
 def test_pipelined_initialize_equals_separate_calls(orc, monkeypatch, chunk):
     """nsmh_initialize_ascii / _dnabitset (load + sketch + build pipelined: a chunk's reads are sketched while

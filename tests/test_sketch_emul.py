@@ -27,7 +27,9 @@ def emul():
     return L
 
 
-def sketch(L, bases, offsets, k, n, rnd, mode=0, lam=2, tile_words=640, grid=2):
+def sketch(L, bases, offsets, k, n, rnd, mode=0, lam=2, tile_words=640, grid=2, deferred=False):
+    L.sketch_emul_set_deferred.argtypes = [C.c_int]
+    L.sketch_emul_set_deferred(1 if deferred else 0)
     W = np.concatenate([expected_packed(bases), np.zeros(8, np.uint32)])
     N = offsets.size - 1
     sk = np.full((max(N, 1), n), 0x5555555555555555, dtype=np.uint64)
@@ -58,6 +60,9 @@ def test_filter_and_brute_kernels_equal_oracle(emul, orc, k, n):
     got, fixups = sketch(emul, bases, offsets, k, n, rnd, mode=0)
     bad = np.argwhere(got != want)
     assert bad.size == 0, f"filter kernel: first difference at (read, hash) {bad[:3].tolist()}"
+    # the fix-up with its values in a buffer of their own (nsmh_sketch_build), stored afterwards
+    got_d, fixups_d = sketch(emul, bases, offsets, k, n, rnd, mode=0, deferred=True)
+    assert (got_d == want).all() and fixups_d == fixups
     if k > 2:
         assert fixups > 0, "the homopolymer / dinucleotide reads need the fix-up pass"
     got, _ = sketch(emul, bases, offsets, k, n, rnd, mode=1)

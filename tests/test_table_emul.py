@@ -93,6 +93,41 @@ def test_tables_and_lookup_equal_oracle(emul, orc, k, n, thr, blocks):
             assert g.size == want.size and (g == want).all(), f"foreign query {q}"
 
 
+@pytest.mark.parametrize("k,n,thr,blocks,frac", [(23, 60, 6, 3, 0.02), (15, 30, 3, 2, 0.3), (31, 7, 2, 8, 1.0)])
+def test_build_with_deferred_entries_equals_plain_build(emul, orc, k, n, thr, blocks, frac):
+    """nsmh_sketch_build: the insert kernel leaves the all-ones entries out (skip_empty), table_insert_list_kernel
+    stores and inserts them from a list afterwards - pending sketch values and the legitimate all-ones entries of
+    the len == k-1 reads alike.  Same distinct keys, same answers as the plain build of the final matrix."""
+    sk = sketch_matrix(orc, k, n, seed=k + n + 1)
+    rows = sk.shape[0]
+    rng = np.random.default_rng(k)
+    ones = np.uint64(0xFFFFFFFFFFFFFFFF)
+    pending = rng.random(sk.shape) < frac
+    assert (sk == ones).any(), "the set must hold legitimate all-ones entries too"
+    work = sk.copy()
+    work[pending] = ones
+    lst = np.flatnonzero(work.ravel() == ones).astype(np.uint32)           # what sketch_missing_kernel lists
+    lst = lst[rng.permutation(lst.size)]
+    vals = np.ascontiguousarray(sk.ravel()[lst])
+    L = emul
+    L.table_emul_build_deferred.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint, u32p, C.c_uint, u64p]
+    assert L.table_emul_build_deferred(work.ctypes.data_as(u64p), rows, n, blocks, lst.ctypes.data_as(u32p), lst.size,
+                                       vals.ctypes.data_as(u64p)) == 0
+    assert (work == sk).all(), "the list kernel stores the values into the sketch matrix"
+    T = orc.build_tables(sk)
+    for j in range(n):
+        assert L.table_emul_num_keys(j) == T.num_keys(j), f"distinct keys of table {j}"
+    got = query_all(L, sk, thr)
+    resolved = 0
+    for q in range(rows):
+        if got[q] is None:
+            continue
+        want = T.query_sketch(sk[q], thr)
+        assert got[q].size == want.size and (got[q] == want).all(), f"query {q}"
+        resolved += 1
+    assert resolved > rows // 2
+
+
 def test_empty_and_tiny_tables(emul, orc):
     n = 8
     sk = np.zeros((0, n), dtype=np.uint64)
