@@ -412,9 +412,11 @@ def main():
         if world == 1 and not args.separate_build:
             f.sketch_build()        # nsmh_sketch_build: the sketch's fix-up pass beside the table insert
             return f.queryAll(False, fetch=False)
-        f.sketch()
         if pf is not None:
-            return pf.run(lengths.size, rows_per_rank)
+            if args.separate_build:
+                f.sketch()
+            return pf.run(lengths.size, rows_per_rank, sketch=not args.separate_build)
+        f.sketch()
         if world > 1:
             keep["g"] = shard.gather_and_build(f, lengths.size, rows_per_rank, rank)
         else:

@@ -118,8 +118,7 @@ class Leg:
         if self.pf is None:
             f.sketch_build()
             return f.queryAll(False, fetch=False)
-        f.sketch()
-        return self.pf.run()
+        return self.pf.run(sketch=True)
 
     def csr(self, total):
         if self.pf is not None:

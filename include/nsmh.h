@@ -215,6 +215,9 @@ int nsmh_mg_init(nsmh_handle h, uint32_t rank, uint32_t world, const uint32_t *r
                  void *token_out /* NSMH_MG_TOKEN_BYTES */);
 int nsmh_mg_connect(nsmh_handle h, const void *tokens /* world * NSMH_MG_TOKEN_BYTES, rank order */);
 int nsmh_mg_run(nsmh_handle h, uint64_t *total_ids);
+/* nsmh_sketch + nsmh_mg_run as one call: the sketch's exact fix-up pass runs on a second stream beside the column
+ * scatter, the entries it produces are sent after it.  Same results (bench.py's parity check at N > 1 runs on it). */
+int nsmh_mg_sketch_run(nsmh_handle h, uint64_t *total_ids);
 /* Device time of the stages of the last nsmh_mg_run, ms: scatter columns, barrier, build owned
  * tables, probe + store to peers, barrier, count. */
 int nsmh_mg_stage_ms(nsmh_handle h, float *out /* [6] */);

@@ -87,6 +87,7 @@ _SIGS = {
     "nsmh_mg_init": [C.c_void_p, C.c_uint32, C.c_uint32, u32p, C.c_void_p],
     "nsmh_mg_connect": [C.c_void_p, C.c_void_p],
     "nsmh_mg_run": [C.c_void_p, u64p],
+    "nsmh_mg_sketch_run": [C.c_void_p, u64p],
     "nsmh_mg_stage_ms": [C.c_void_p, C.POINTER(C.c_float)],
     "nsmh_mg_shutdown": [C.c_void_p],
     "nsmh_multi_create": [C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)],

@@ -870,6 +870,34 @@ int nsmh_sketch_build(nsmh_handle c) {
     return rc;
 }
 
+// The same idea for the multi-GPU flow: nsmh_sketch + nsmh_mg_run as one call, the fix-up pass beside the column
+// scatter (which sends all-ones for the entries concerned; their values follow in mg_scatter_list_kernel).
+int nsmh_mg_sketch_run(nsmh_handle c, uint64_t *total_ids) {
+    CTX_GUARD(c);
+    if (!c->reads_loaded) return fail(NSMH_ESTATE, "mg_sketch_run: no reads loaded");
+    if (!c->mg) return fail(NSMH_ESTATE, "mg_sketch_run: call nsmh_mg_init and nsmh_mg_connect first");
+    const bool overlap = c->sketch_mode == 0 && c->n <= 255 && c->reads.num_reads > 0;
+    NSMH_TRY(sketch_begin(c));
+    SketchDeferred *d = nullptr;
+    if (overlap) {
+        d = &c->defer;
+        d->aux = c->copy_stream;
+        if (!d->filtered) NSMH_CK(cudaEventCreateWithFlags(&d->filtered, cudaEventDisableTiming));
+        if (!d->fixed) NSMH_CK(cudaEventCreateWithFlags(&d->fixed, cudaEventDisableTiming));
+        d->pending = false;
+    }
+    NSMH_TRY(sketch_reads(c, c->reads, c->sketches.as<uint64_t>(), c->tile_start, c->build_tmp, c->sketch_mode, c->stream,
+                          &c->launches, c->ev[4], c->ev[5], 0, ~0u, d));
+    NSMH_TRY(sketch_end(c));
+    const int rc = mg_run_impl(c, total_ids, d);
+    if (d && d->pending) {              // the run failed before the fix-up was queued: the sketches are not final
+        cudaStreamSynchronize(c->copy_stream);
+        c->sketched = false;
+        d->pending = false;
+    }
+    return rc;
+}
+
 int nsmh_get_sketches(nsmh_handle c, uint64_t *out) {
     CTX_GUARD(c);
     if (!c->sketched) return fail(NSMH_ESTATE, "get_sketches: call nsmh_sketch first");

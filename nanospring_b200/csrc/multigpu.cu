@@ -252,6 +252,14 @@ int nsmh_mg_connect(nsmh_handle c, const void *tokens) {
 
 int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
     if (!c) return fail(NSMH_EINVAL, "null handle");
+    return nsmh::mg_run_impl(c, total_ids, nullptr);
+}
+
+} // extern "C"
+
+// defer (nsmh_mg_sketch_run): the exact fix-up pass of the sketch has not run yet - it is queued on the second
+// stream once the column scatter is, and what it produces is sent after it (mg_scatter_list_kernel).
+int nsmh::mg_run_impl(nsmh_ctx *c, uint64_t *total_ids, SketchDeferred *defer) {
     MgState *m = c->mg;
     if (!m || !m->connected) return fail(NSMH_ESTATE, "mg_run: call nsmh_mg_init and nsmh_mg_connect first");
     if (!c->sketched) return fail(NSMH_ESTATE, "mg_run: call nsmh_sketch first");
@@ -321,10 +329,25 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
     if (rows) {
         const size_t smem = (size_t)kScatterRows * c->n * sizeof(uint64_t);
         if (smem > 48 * 1024) NSMH_CK(cudaFuncSetAttribute(mg_scatter_columns_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int blocks = (int)std::min<uint64_t>(((uint64_t)rows + kScatterRows - 1) / kScatterRows, (uint64_t)c->num_sms * 8);
+        // NSMH_MG_SCATTER_BLOCKS / NSMH_MG_FIXUP_BLOCKS: blocks per SM of the scatter and of the fix-up pass that runs
+        // beside it (nsmh_mg_sketch_run).  Measured on 8 GPUs: whatever the split, the two hardly overlap
+        // (profiles/r2_mg_sketch_run_overlap_s34.txt), so both keep their usual 8.
+        const char *sbe = getenv("NSMH_MG_SCATTER_BLOCKS"), *fbe = getenv("NSMH_MG_FIXUP_BLOCKS");
+        const int scatter_per_sm = sbe && *sbe && atoi(sbe) > 0 ? atoi(sbe) : 8;
+        const int fixup_per_sm = fbe && *fbe && atoi(fbe) > 0 ? atoi(fbe) : 8;
+        const int blocks = (int)std::min<uint64_t>(((uint64_t)rows + kScatterRows - 1) / kScatterRows, (uint64_t)c->num_sms * scatter_per_sm);
         mg_scatter_columns_kernel<<<blocks, 256, smem, s>>>(c->sketches.as<uint64_t>(), rows, c->n, sa);
         ++c->launches;
         NSMH_CK(cudaGetLastError());
+        if (defer && defer->pending) {
+            NSMH_TRY(defer->launch(fixup_per_sm));
+            NSMH_CK(cudaStreamWaitEvent(s, defer->fixed, 0));
+            mg_scatter_list_kernel<<<c->num_sms * 2, 256, 0, s>>>(c->sketches.as<uint64_t>(), c->n, defer->list, defer->count,
+                                                                 defer->vals, sa);
+            ++c->launches;
+            NSMH_CK(cudaGetLastError());
+            defer->pending = false;
+        }
     }
     NSMH_CK(cudaEventRecord(m->ev[1], s));
     mg_barrier_kernel<<<1, 32, 0, s>>>(ba, epoch, 0);
@@ -368,6 +391,8 @@ int nsmh_mg_run(nsmh_handle c, uint64_t *total_ids) {
     if (total_ids) *total_ids = c->bulk.last_total;
     return NSMH_OK;
 }
+
+extern "C" {
 
 int nsmh_mg_stage_ms(nsmh_handle c, float *out) {
     if (!c || !out) return fail(NSMH_EINVAL, "mg_stage_ms: null argument");

@@ -127,4 +127,24 @@ mg_scatter_columns_kernel(const uint64_t *__restrict__ S, uint32_t rows, uint32_
     }
 }
 
+// Entries whose values arrived after the scatter (nsmh_mg_sketch_run: the sketch's exact fix-up pass runs on the
+// second stream beside mg_scatter_columns_kernel, which sent all-ones for them): list[e] = local row * n + column,
+// vals[e] the value.  It goes into the local sketch matrix and into the owner's column block.
+__global__ void __launch_bounds__(256)
+mg_scatter_list_kernel(uint64_t *__restrict__ S, uint32_t n, const uint32_t *__restrict__ list,
+                       const unsigned int *__restrict__ count, const uint64_t *__restrict__ vals, ScatterArgs a) {
+    const uint32_t todo = *count;
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < todo; e += gridDim.x * blockDim.x) {
+        const uint64_t v = vals[e];
+        if (v == ~0ULL) continue;           // a read of k-1 bases: all-ones is its value, and that was sent
+        const uint32_t t = list[e];
+        const uint32_t row = t / n, l = t - row * n;
+        S[t] = v;
+        uint32_t o = 0, cb = 0;
+        while (o + 1 < a.world && l >= a.col_end[o]) { cb = a.col_end[o]; ++o; }
+        const uint32_t nc = a.col_end[o] - cb;
+        a.m[o][(size_t)(a.row0 + row) * nc + (l - cb)] = v;
+    }
+}
+
 } // namespace nsmh

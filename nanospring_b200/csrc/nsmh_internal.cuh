@@ -124,7 +124,8 @@ struct SketchDeferred {
     uint64_t *sk = nullptr;             // the sketch matrix the entries belong to
     uint32_t n = 0;
     bool pending = false;
-    std::function<int()> launch;        // queues the two fix-up kernels on aux (called once the insert kernel is queued)
+    std::function<int(int)> launch;     // queues the two fix-up kernels on aux, `blocks per SM` each (0: the build's default);
+                                        // called once the kernel they run beside is queued
 };
 
 struct nsmh_ctx {
@@ -212,6 +213,8 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
 
 // ---- table.cu ----------------------------------------------------------------
 int build_tables(nsmh_ctx *c, SketchDeferred *defer = nullptr);
+// multigpu.cu: nsmh_mg_run; defer: see nsmh_mg_sketch_run
+int mg_run_impl(nsmh_ctx *c, uint64_t *total_ids, SketchDeferred *defer);
 int preclear_tables(nsmh_ctx *c, uint32_t rows, bool in_order = false);
 int table_num_keys(nsmh_ctx *c, uint32_t j, uint32_t *out);
 

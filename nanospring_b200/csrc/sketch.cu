@@ -154,10 +154,11 @@ int sketch_reads(nsmh_ctx *c, const ReadSet &rs, uint64_t *d_sketches, DevBuf &t
             // queued by build_tables right after its insert kernel, so that the insert's blocks are resident first
             // and these kernels take what is left of every SM (NSMH_FIXUP_BLOCKS: their blocks per SM)
             const char *fe = getenv("NSMH_FIXUP_BLOCKS");
-            const int per_sm = fe && *fe && atoi(fe) > 0 ? atoi(fe) : 2;       // measured: profiles/r2_sketch_build_overlap_s31.txt
-            const int grid = c->num_sms * per_sm;
+            const int dflt = fe && *fe && atoi(fe) > 0 ? atoi(fe) : 2;         // measured: profiles/r2_sketch_build_overlap_s31.txt
+            const int sms = c->num_sms;
             SketchDeferred *d = defer;
-            defer->launch = [a, d, miss_count, grid]() -> int {
+            defer->launch = [a, d, miss_count, dflt, sms](int per_sm) -> int {
+                const int grid = sms * (per_sm > 0 ? per_sm : dflt);
                 NSMH_CK(cudaStreamWaitEvent(d->aux, d->filtered, 0));
                 sketch_missing_kernel<<<grid, 256, 0, d->aux>>>(a, d->list, miss_count);
                 sketch_fixup_kernel<4><<<grid, 256, 0, d->aux>>>(a, d->list, miss_count, d->vals);

@@ -139,7 +139,7 @@ int build_tables(nsmh_ctx *c, SketchDeferred *defer) {
         table_insert_kernel<<<blocks, kBuildRows, 0, s>>>(a);
         NSMH_CK(cudaGetLastError());
         if (defer) {
-            NSMH_TRY(defer->launch());
+            NSMH_TRY(defer->launch(0));
             NSMH_CK(cudaStreamWaitEvent(s, defer->fixed, 0));
             table_insert_list_kernel<<<c->num_sms * 2, 256, 0, s>>>(a, defer->list, defer->count, defer->vals, defer->sk);
             NSMH_CK(cudaGetLastError());

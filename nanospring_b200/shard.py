@@ -255,13 +255,14 @@ class PeerPartitionedFilter:
         check(lib().nsmh_mg_connect(self.f._h, blob))
         self.last_ms = {}
 
-    def run(self, n_local=None, rows_per_rank=None):
-        """After self.f.sketch(): scatter columns, build owned tables, probe, count.  Returns the
-        number of candidate ids of the local reads; the CSR stays on the device."""
+    def run(self, n_local=None, rows_per_rank=None, sketch=False):
+        """After self.f.sketch() - or, sketch=True, including it (nsmh_mg_sketch_run: the sketch's fix-up pass runs
+        beside the column scatter): scatter columns, build owned tables, probe, count.  Returns the number of
+        candidate ids of the local reads; the CSR stays on the device."""
         from ._lib import check, lib
         C = self.C
         total = C.c_uint64(0)
-        check(lib().nsmh_mg_run(self.f._h, C.byref(total)))
+        check((lib().nsmh_mg_sketch_run if sketch else lib().nsmh_mg_run)(self.f._h, C.byref(total)))
         ms = (C.c_float * 6)()
         check(lib().nsmh_mg_stage_ms(self.f._h, ms))
         self.last_ms = dict(zip(("scatter_columns", "barrier_1", "build_owned_tables", "probe_to_peers",

@@ -61,9 +61,24 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         }
         sa.world = world;
         sa.row0 = r ? row_end[r - 1] : 0u;
-        const uint64_t *Sr = S + (size_t)sa.row0 * n;
+        // nsmh_mg_sketch_run: some entries are still all-ones when the columns are scattered (the sketch's fix-up pass
+        // runs beside the scatter); their values follow from a list (mg_scatter_list_kernel).  Every 7th entry here.
+        std::vector<uint64_t> Sr(S + (size_t)sa.row0 * n, S + (size_t)(sa.row0 + rows[r]) * n);
+        std::vector<uint32_t> list;
+        std::vector<uint64_t> vals;
+        for (size_t t = 0; t < Sr.size(); ++t)
+            if (t % 7 == 3 || Sr[t] == ~0ULL) {                 // sketch_missing_kernel lists every all-ones entry
+                list.push_back((uint32_t)t);
+                vals.push_back(Sr[t]);
+                Sr[t] = ~0ULL;
+            }
+        const unsigned int count = (unsigned int)list.size();
+        list.push_back(0);
+        vals.push_back(0);
         std::vector<uint64_t> tile((size_t)kScatterRows * n + 2, 0xA5A5A5A5A5A5A5A5ull);
-        emu_launch_block(grid, 256, [&] { mg_scatter_columns_kernel(Sr, rows[r], n, sa, reinterpret_cast<uint8_t *>(tile.data())); });
+        emu_launch_block(grid, 256, [&] { mg_scatter_columns_kernel(Sr.data(), rows[r], n, sa, reinterpret_cast<uint8_t *>(tile.data())); });
+        emu_launch(2, 64, [&] { mg_scatter_list_kernel(Sr.data(), n, list.data(), &count, vals.data(), sa); });
+        if (memcmp(Sr.data(), S + (size_t)sa.row0 * n, Sr.size() * sizeof(uint64_t)) != 0) return -7;
     }
     // ---- stage 2: every owner builds its tables over all rows ----
     const uint64_t cap = std::max<uint64_t>(16, 2ULL * total_rows);
@@ -94,6 +109,7 @@ int mg_emul_run(const uint64_t *S, const uint32_t *rows, uint32_t world, uint32_
         a.n = ncols;
         a.seg_cap = seg_cap;
         a.segments = (uint32_t)units;
+        a.skip_empty = 0;
         emu_launch_block(blocks, kBuildRows, [&] { table_insert_kernel(a); });
         emu_launch(2, 256, [&] { table_groups_kernel(a); });
         emu_launch(2, 256, [&] { table_fill_kernel(a); });
