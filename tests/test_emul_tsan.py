@@ -26,7 +26,7 @@ def test_no_unexpected_data_race_in_the_emulated_kernels():
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4 exitcode=0")
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=900, env=env)
     assert r.returncode == 0, r.stderr[-3000:]
-    for stage in ("sketch mode 0 done", "sketch mode 1 done", "lookup done", "count body done",
+    for stage in ("sketch mode 0 done", "sketch mode 1 done", "deferred build done: matrix restored", "lookup done", "count body done",
                   "mid tier done", "fastq done"):
         assert stage in r.stdout, r.stdout
     reports = [b for b in re.split(r"={18,}\n", r.stderr) if "WARNING: ThreadSanitizer" in b]
