@@ -116,7 +116,8 @@ class Leg:
         f = self.f
         f.load_device(self.d_bases.data_ptr(), self.d_off.data_ptr(), self.offsets.size - 1, self.bases)
         if self.pf is None:
-            f.sketch_build()
+            f.sketch()
+            f.build()
             return f.queryAll(False, fetch=False)
         return self.pf.run(sketch=True)
 

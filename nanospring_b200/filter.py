@@ -276,7 +276,8 @@ class MinHashReadFilter:
         """ReadFilter.cpp:11-47: sketch every read, then populate the n hash tables."""
         if isinstance(rD, GpuReadData):
             self._adopt(rD)
-            self.sketch_build()
+            self.sketch()
+            self.build()
             return
         if not isinstance(rD, ReadData):
             rD = ReadData.from_reads(rD)
