@@ -14,6 +14,8 @@
 #           ab      the remaining switches (speculative placement, table slots per read, tile size), small-k lookup A/B
 #                   (tools/mid_tier_ab.py) and the FASTQ-ingest kernels (tools/ingest_sweep.py)
 #           peer    the peer-memory multi-rank path with 4 and 8 ranks sharing one device
+#           sanitize compute-sanitizer memcheck / initcheck / racecheck over tools/sanitize_smoke.py (every kernel family)
+#           e2e     tools/e2e_breakdown.py: host wall time of every call of the host-buffer path, the pipelined calls, the bare copy
 #           micro   tools/micro: the integer roof (int_roof -> copy to profiles/int_roof.json, bench.py reads it)
 #                   and the random-slot atomics benchmark
 # No number printed by a run under ncu is a bench value.
@@ -105,9 +107,33 @@ print(f"speculate={sys.argv[2]} slots_per_read={sys.argv[3]} tile_words={sys.arg
       f"sketch {p['sketch_ms']:.4f} (main kernel {p['sketch_main_kernel_ms']:.4f})  build {p['build_ms']:.4f}  query {p['query_ms']:.4f}")
 PY
     done
+    # nsmh_sketch_build (fix-up pass beside the table insert) against the separate calls
+    for F in "" "--separate-build"; do
+        timeout 120 python bench.py --steps 10 --no-cpu-baseline --no-e2e --no-ingest --no-legs $F 2>/dev/null | python -c "
+import json, sys
+d = json.loads(sys.stdin.read().strip().splitlines()[-1]); p = d['phases_last_step']
+print('$F'.strip() or 'nsmh_sketch_build', 'ms/step %.4f' % d['ms_per_step'], 'sketch %.4f build %.4f query %.4f' % (p['sketch_ms'], p['build_ms'], p['query_ms']))"
+    done
     timeout 120 python tools/mid_tier_ab.py > "$OUT/mid_tier_ab_$TAG.jsonl" 2> "$OUT/mid_tier_ab_$TAG.err"
     timeout 120 python tools/ingest_sweep.py --iters 16 32 64 > "$OUT/ingest_sweep_$TAG.jsonl" 2> "$OUT/ingest_sweep_$TAG.err"
     cat "$OUT/mid_tier_ab_$TAG.jsonl" "$OUT/ingest_sweep_$TAG.jsonl"
+fi
+
+SECTION=sanitize
+if want; then
+    for T in memcheck initcheck; do
+        timeout 300 compute-sanitizer --tool $T --error-exitcode 1 python tools/sanitize_smoke.py > "$OUT/sanitize_${T}_$TAG.log" 2>&1
+        echo "$T rc=$?"; tail -n 2 "$OUT/sanitize_${T}_$TAG.log"
+    done
+    timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 400 python tools/sanitize_smoke.py \
+        > "$OUT/sanitize_racecheck_$TAG.log" 2>&1
+    grep "and \(Read\|Write\) access" "$OUT/sanitize_racecheck_$TAG.log" | sed 's/0x[0-9a-f]*//g; s/\[[0-9]* hazards\]//' | sort | uniq -c
+fi
+
+SECTION=e2e
+if want; then
+    timeout 200 python tools/e2e_breakdown.py > "$OUT/e2e_breakdown_$TAG.json" 2> "$OUT/e2e_breakdown_$TAG.err"
+    cat "$OUT/e2e_breakdown_$TAG.json"
 fi
 
 SECTION=micro
