@@ -139,3 +139,34 @@ def test_tables_any_key_multiplicity(table_emul, orc, rows, n, keyspace, thr, se
         if got[q] is not None:
             want = T.query_sketch(S[q], thr)
             assert got[q].size == want.size and (got[q] == want).all()
+
+
+@settings(max_examples=15, **COMMON)
+@given(rows=st.integers(1, 300), n=st.integers(1, 9), keyspace=st.sampled_from([1, 3, 40, 2**40]), thr=st.integers(1, 4),
+       frac=st.sampled_from([0.0, 0.05, 0.5, 1.0]), seed=st.integers(0, 2**31))
+def test_tables_with_deferred_entries(table_emul, orc, rows, n, keyspace, thr, frac, seed):
+    """nsmh_sketch_build's table build: any subset of the entries is still all-ones when the insert kernel runs
+    and arrives from a list afterwards (table_insert_list_kernel), rows beyond one 256-row work unit included;
+    tables and matrix must be those of the plain build"""
+    rng = np.random.default_rng(seed)
+    S = rng.integers(0, keyspace, size=(rows, n), dtype=np.uint64)
+    ones = np.uint64(0xFFFFFFFFFFFFFFFF)
+    S[rng.random((rows, n)) < 0.1] = ones
+    S = np.ascontiguousarray(S)
+    work = S.copy()
+    work[rng.random((rows, n)) < frac] = ones
+    lst = np.flatnonzero(work.ravel() == ones).astype(np.uint32)
+    lst = np.ascontiguousarray(np.concatenate([lst[rng.permutation(lst.size)], np.zeros(1, np.uint32)]))
+    vals = np.ascontiguousarray(S.ravel()[lst])
+    table_emul.table_emul_build_deferred.argtypes = [u64p, C.c_uint32, C.c_uint32, C.c_uint, u32p, C.c_uint, u64p]
+    assert table_emul.table_emul_build_deferred(work.ctypes.data_as(u64p), rows, n, 2, lst.ctypes.data_as(u32p), lst.size - 1,
+                                                vals.ctypes.data_as(u64p)) == 0
+    assert (work == S).all()
+    T = orc.build_tables(S)
+    for j in range(n):
+        assert table_emul.table_emul_num_keys(j) == T.num_keys(j)
+    got = query_all(table_emul, S, thr, grid=1)
+    for q in range(rows):
+        if got[q] is not None:
+            want = T.query_sketch(S[q], thr)
+            assert got[q].size == want.size and (got[q] == want).all()

@@ -89,3 +89,33 @@ def test_reference_static_kats_through_the_kernels(emul, orc):
     for mode in (0, 1):
         got, _ = sketch(emul, bases, offsets, 4, 2, np.array([0, 0xFF], dtype=np.uint64), mode=mode)
         assert got[0, 0] == 45 and got[0, 1] == (224 ^ 0xFF)
+
+
+@pytest.mark.parametrize("k,n", [(23, 24), (15, 9)])
+def test_read_ranges_as_the_pipelined_loaders_sketch_them(emul, orc, k, n):
+    """sketch_reads(r0, r1): the kernels see a range of the reads as a read set of its own - the offsets stay
+    absolute positions in the one packed stream (so off[0] != 0), the rows are those of the range.  Every
+    range, stitched together, must give the sketch matrix of the whole set (nsmh_initialize_* / nsmh_load_sketch_*)."""
+    rng = np.random.default_rng(k)
+    bases, offsets = read_set(rng, k)
+    rnd = ns.rand_from_seed(k * n, n)
+    want = orc.sketch_all(bases, offsets, k, n, rnd)
+    N = offsets.size - 1
+    W = np.concatenate([expected_packed(bases), np.zeros(8, np.uint32)])
+    emul.sketch_emul_set_deferred.argtypes = [C.c_int]
+    emul.sketch_emul_set_deferred(0)
+    rnd_c = np.ascontiguousarray(rnd, dtype=np.uint64)
+    cuts = [0, 1, 5, 6, N // 2, N - 1, N]
+    got = np.full((N, n), 0x5555555555555555, dtype=np.uint64)
+    for r0, r1 in zip(cuts[:-1], cuts[1:]):
+        if r1 <= r0:
+            continue
+        off = np.ascontiguousarray(offsets[r0:r1 + 1])
+        sk = np.full((r1 - r0, n), 0x5555555555555555, dtype=np.uint64)
+        fix = C.c_ulonglong(0)
+        rc = emul.sketch_emul_run(W.ctypes.data_as(u32p), off.ctypes.data_as(u64p), r1 - r0, k, n, rnd_c.ctypes.data_as(u64p),
+                                  0, 2, 640, 2, sk.ctypes.data_as(u64p), C.byref(fix))
+        assert rc == 0
+        got[r0:r1] = sk
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, f"first difference at (read, hash) {bad[:3].tolist()}"
