@@ -414,6 +414,7 @@ static int build_enqueue(nsmh_ctx *c, SketchDeferred *defer = nullptr) {
     NSMH_TRY(build_tables(c, defer));
     NSMH_CK(cudaEventRecord(c->ev[7], c->stream));
     c->build_timed = true;          // no host round trip here: nsmh_get_stats reads the events
+    ++c->build_epoch;               // query workspaces order their streams behind ev[7] (order_after_build)
     return NSMH_OK;
 }
 
@@ -1086,6 +1087,17 @@ static QueryWs *acquire_ws(nsmh_ctx *c) {
     return ws;
 }
 
+// nsmh_build / nsmh_initialize_* / nsmh_sketch_build only QUEUE the build on the context's stream; a query
+// workspace has a stream of its own, so before its first query against new tables it waits for the event that
+// marks their completion (once per build and workspace: the online path stays at one launch + one wait per call).
+static int order_after_build(nsmh_ctx *c, QueryWs &ws) {
+    if (ws.stream != c->stream && ws.seen_build_epoch != c->build_epoch) {
+        NSMH_CK(cudaStreamWaitEvent(ws.stream, c->ev[7], 0));
+        ws.seen_build_epoch = c->build_epoch;
+    }
+    return NSMH_OK;
+}
+
 static void release_ws(nsmh_ctx *c, QueryWs *ws) {
     std::lock_guard<std::mutex> lk(c->pool_mu);
     c->launches += ws->launches;
@@ -1152,7 +1164,8 @@ int nsmh_query_strings(nsmh_handle c, const char *bases, const uint64_t *offsets
     if (!c->tables.built) return fail(NSMH_ESTATE, "query_strings: call nsmh_build first");
     QueryWs *ws = acquire_ws(c);
     if (!ws) return fail(NSMH_ENOMEM, "query_strings: cannot create a query workspace");
-    int rc = query_strings_impl(c, *ws, bases, offsets, num_strings, offsets_out, ids_out, cap);
+    int rc = order_after_build(c, *ws);
+    if (!rc) rc = query_strings_impl(c, *ws, bases, offsets, num_strings, offsets_out, ids_out, cap);
     release_ws(c, ws);
     return rc;
 }
@@ -1175,6 +1188,7 @@ int nsmh_query_sketches(nsmh_handle c, const uint64_t *sketches, uint32_t num_qu
     int rc = NSMH_OK;
     const size_t bytes = (size_t)num_queries * c->n * sizeof(uint64_t);
     do {
+        if ((rc = order_after_build(c, *ws))) break;
         if ((rc = ws->qsketch.ensure(std::max<size_t>(bytes, 8), ws->stream))) break;
         if ((rc = ensure_pinned(*ws, bytes + 16))) break;
         memcpy(ws->h_pinned, sketches, bytes);

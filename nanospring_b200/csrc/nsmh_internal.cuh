@@ -106,6 +106,7 @@ struct QueryWs {
     uint32_t last_heavy = 0;    // queries of the last call that overflowed the warp buffer
     uint32_t last_sorted = 0;   // ... of which went through the global sort
     uint32_t launches = 0;
+    uint64_t seen_build_epoch = 0;  // the last build this workspace's stream has been ordered behind
 };
 
 struct MgState;
@@ -135,6 +136,7 @@ struct nsmh_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[10] = {};
     bool build_timed = false;
+    uint64_t build_epoch = 0;       // builds queued so far; ev[7] marks the end of the last one on `stream`
     SketchDeferred defer;           // nsmh_sketch_build
     bool load_timed = false;        // ev[0], ev[1] bracket a pipelined load that returned before the device finished
     int sketch_mode = 0;
